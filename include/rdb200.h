@@ -1,0 +1,107 @@
+/* rdb200.h — C ABI of librdb200.so: B200-native batched dynamics / Jacobian evaluation for the
+ * RobotDynamics.jl hot path.  Plain pointers and sizes only; what a Julia `ccall` (or ctypes / cgo) binds.
+ *
+ * Every entry point cites the reference interface it replaces (file:line in RobotDynamics.jl v0.4.8).
+ * The reference evaluates ONE knot point per call inside the caller's `for k in 1:N` loop; each entry point
+ * here evaluates the whole batch of N independent knot points in one call.
+ *
+ * Conventions
+ *   - return 0 on success, a negative rdb_status on argument errors, a positive cudaError_t on CUDA failures;
+ *     rdb_strerror() explains either.  Nothing is thrown, nothing is allocated for the caller.
+ *   - data pointers may be DEVICE pointers (the call only enqueues work on `stream`; the caller synchronises)
+ *     or HOST pointers (the call copies in, computes and copies out through an internal pinned, double-buffered
+ *     pipeline and returns when the outputs are valid).  All data pointers of one call must be of one kind.
+ *   - dtype selects the arithmetic AND the storage type of Z/X/J/... (float or double).  t and dt are always
+ *     double, like KnotPoint.t / KnotPoint.dt (src/knotpoint.jl:148-153).
+ *   - layout RDB_AOS is the reference's own memory image: Z is the Julia Matrix{T}(n+m, N) of `getdata(z)` columns,
+ *     J the Array{T,3}(n, n+m, N) of column-major [A B] DynamicsJacobian data (src/jacobian.jl:26-37), x+ the
+ *     Matrix{T}(n, N).  RDB_SOA is component-major: Z is (N, n+m) as a Julia matrix, i.e. each component of [x;u] is a
+ *     unit-stride stream of N values; J has n*(n+m) such streams (entry i + n*j), x+ has n.
+ *   - t may be NULL (all shipped models are time-invariant, src/dynamics.jl:83); dt may be NULL (then dt0 is
+ *     used for every knot point).  Knot points with dt == 0 (terminal, src/knotpoint.jl:57-67) yield J = [I 0].
+ */
+#ifndef RDB200_H
+#define RDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rdb_context rdb_context; /* one per (process, GPU): device id, SM count, staging pipeline */
+typedef struct rdb_model rdb_model;     /* immutable model description; replaces an AbstractModel instance */
+
+typedef enum { RDB_F32 = 0, RDB_F64 = 1 } rdb_dtype;
+typedef enum { RDB_AOS = 0, RDB_SOA = 1 } rdb_layout;
+/* QuadratureRule subtypes: src/integration.jl:69 (Euler), :109 (RK3), :258 (RK4); RK2 = explicit midpoint
+ * (v0.3 name kept by BASELINE; semantics pinned by test/old_tests/linear_tests.jl:135-141). */
+typedef enum { RDB_EULER = 0, RDB_RK2 = 1, RDB_RK3 = 2, RDB_RK4 = 3 } rdb_integrator;
+/* model families: test/cartpole_model.jl, test/quadrotor.jl, test/rigidbody_test.jl:23-56 (= the Satellite of
+ * examples/single_satellite.jl:7-35 with other parameters), test/double_integrator.jl:97-127 */
+typedef enum { RDB_CARTPOLE = 0, RDB_QUADROTOR = 1, RDB_BODY = 2, RDB_DOUBLE_INTEGRATOR = 3 } rdb_model_kind;
+/* rotation parameterisation R of RigidBody{R} (src/liestate.jl:42-46) and velocity_frame (src/rigidbody.jl:258) */
+typedef enum { RDB_ROT_NONE = 0, RDB_ROT_QUAT = 1, RDB_ROT_MRP = 2, RDB_ROT_RP = 3 } rdb_rot;
+typedef enum { RDB_FRAME_WORLD = 0, RDB_FRAME_BODY = 1 } rdb_frame;
+
+typedef enum {
+    RDB_OK = 0,
+    RDB_ERR_ARG = -1,            /* bad enum / NULL / negative size        -> Julia ArgumentError           */
+    RDB_ERR_NOT_IMPLEMENTED = -2, /* combination has no kernel              -> RobotDynamics.NotImplementedError (src/utils.jl:1-8) */
+    RDB_ERR_POINTER_MIX = -3,    /* host and device data pointers mixed in one call                         */
+    RDB_ERR_NO_DEVICE = -4       /* no CUDA device / library built without the kernels                      */
+} rdb_status;
+
+int rdb_version(void);
+const char* rdb_strerror(int code);
+
+int rdb_create(int device, rdb_context** ctx);
+int rdb_destroy(rdb_context* ctx);
+/* pinned host memory for the HOST-pointer path (optional; pageable memory also works, slower) */
+void* rdb_host_alloc(size_t bytes);
+void rdb_host_free(void* p);
+
+/* params packing per kind (doubles):
+ *   CARTPOLE          [mc, mp, l, g]                                          test/cartpole_model.jl:9
+ *   QUADROTOR         [mass, J(9, row-major), gravity(3), motor_dist, kf, km]  test/quadrotor.jl:36-46
+ *   BODY              [mass, J(9, row-major)]                                  test/rigidbody_test.jl:53-54
+ *   DOUBLE_INTEGRATOR [D]  (1..3)                                              test/double_integrator.jl:97-100 */
+int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const double* params, int nparams, rdb_model** model);
+int rdb_model_destroy(rdb_model* model);
+/* state_dim / control_dim / errstate_dim  (src/functionbase.jl:124-135, src/liestate.jl:124) */
+int rdb_model_dims(const rdb_model* model, int* n, int* m, int* nerr);
+
+/* dynamics(model, x, u, t)                                   src/dynamics.jl:81-83 */
+int rdb_dynamics(const rdb_model* model, int dtype, int layout, int64_t N, const void* Z, const double* t,
+                 void* xdot, void* stream);
+/* discrete_dynamics(DiscretizedDynamics{L,Q}, x, u, t, dt)   src/discrete_dynamics.jl:80-81, src/discretized_dynamics.jl:203-206 */
+int rdb_discrete_dynamics(const rdb_model* model, int integrator, int dtype, int layout, int64_t N, const void* Z,
+                          const double* t, const double* dt, double dt0, void* xn, void* stream);
+/* jacobian!(sig, diff, model::ContinuousDynamics, J, xdot, z)  src/functionbase.jl:242, src/jacobian_gen.jl:485-529
+ * xdot may be NULL */
+int rdb_jacobian(const rdb_model* model, int dtype, int layout, int64_t N, const void* Z, const double* t, void* J,
+                 void* xdot, void* stream);
+/* jacobian!(sig, diff, DiscretizedDynamics{L,Q}, J, y, z)  == v0.3 discrete_jacobian!(Q, J, model, z)
+ * src/discretized_dynamics.jl:169-219, src/integration.jl:85-93,149-177,302-337.  xn (= x+) may be NULL. */
+int rdb_discrete_jacobian(const rdb_model* model, int integrator, int dtype, int layout, int64_t N, const void* Z,
+                          const double* t, const double* dt, double dt0, void* J, void* xn, void* stream);
+/* errstate_jacobian!(model, G, x)                            src/statevectortype.jl:119-122, src/liestate.jl:262-298
+ * X: N states with leading dimension ldx (>= n; pass n+m to read the states straight out of Z).
+ * G: (n, nerr, N) column-major per knot, fully written (zeros included). */
+int rdb_errstate_jacobian(const rdb_model* model, int dtype, int64_t N, const void* X, int ldx, void* G, void* stream);
+/* ∇errstate_jacobian!(model, ∇G, x, xbar)                    src/liestate.jl:300-320.  H: (nerr, nerr, N), fully written. */
+int rdb_grad_errstate_jacobian(const rdb_model* model, int dtype, int64_t N, const void* X, int ldx, const void* Xbar,
+                               int ldb, void* H, void* stream);
+/* state_diff(model, x, x0)  (CayleyMap)                      src/liestate.jl:210-260.  dX: (nerr, N). */
+int rdb_state_diff(const rdb_model* model, int dtype, int64_t N, const void* X, int ldx, const void* X0, int ldx0,
+                   void* dX, void* stream);
+/* rollout!(sig, dmodel, Z, x0)                               src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235
+ * x0 (n, ntraj); U (m, K-1, ntraj); t, dt (K, ntraj) or NULL; X (n, K, ntraj) out.  Parallel over trajectories. */
+int rdb_rollout(const rdb_model* model, int integrator, int dtype, int64_t ntraj, int K, const void* x0, const void* U,
+                const double* t, const double* dt, double dt0, void* X, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDB200_H */

@@ -1,0 +1,10 @@
+"""Import shim: loads the directory `robotdynamics.jl_b200/` (whose name is not a Python identifier) as package `rdb200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "robotdynamics.jl_b200")
+_spec = importlib.util.spec_from_file_location("rdb200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["rdb200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,367 @@
+"""Host-side mirror of the RobotDynamics.jl interface for the hot path (Python stands in for the Julia shim that
+cannot run in this image; `julia/RobotDynamicsB200.jl` is the same thing spelled with `ccall`).
+
+Names, argument order and error behaviour follow the reference; Julia's `f!` is spelled `f_`:
+
+    jacobian_(sig, diff, model, J, y, z)          jacobian!(sig, diff, fun, J, y, z)     src/functionbase.jl:242
+    discrete_jacobian_(Q, J, model, z)            v0.3 discrete_jacobian!(Q, ∇f, model, z)  README.md:81-82
+    dynamics(model, z) / dynamics(model, x, u[, t])                                       src/dynamics.jl:81-83
+    discrete_dynamics(dmodel, z) / (dmodel, x, u, t, dt) / (Q, model, z)                  src/discrete_dynamics.jl:80-81
+    errstate_jacobian_(model, G, z) / ∇errstate_jacobian_ / state_diff                    src/statevectortype.jl:89-141
+    rollout_(sig, dmodel, Z, x0)                                                          src/trajectories.jl:436-441
+
+Every function takes ONE knot point (API fidelity) or a whole batch — a `SampledTrajectory`, or raw arrays /
+CUDA tensors — and evaluates the batch in a single C-ABI call.  Nothing here computes: all arithmetic happens in
+librdb200.so on the GPU.
+"""
+import numpy as np
+
+from . import _abi
+from ._abi import AOS, SOA, NotImplementedModelError  # noqa: F401
+
+
+# ---------------------------------------------------------------------------------------------------
+# traits (reference: src/functionbase.jl:78-120, src/integration.jl:69,109,258, src/statevectortype.jl:63-73)
+# ---------------------------------------------------------------------------------------------------
+class FunctionSignature: pass
+class InPlace(FunctionSignature): pass
+class StaticReturn(FunctionSignature): pass
+
+class DiffMethod: pass
+class ForwardAD(DiffMethod): pass
+class FiniteDifference(DiffMethod): pass
+class UserDefined(DiffMethod): pass
+class B200(DiffMethod):
+    """The extension point the reference documents ("Users are free to add more DiffMethod types",
+    docs/src/autodiff.md:20-21): batched forward-mode evaluation on the GPU."""
+
+class QuadratureRule:
+    code = None
+class Euler(QuadratureRule): code = _abi.EULER
+class RK2(QuadratureRule): code = _abi.RK2
+class RK3(QuadratureRule): code = _abi.RK3
+class RK4(QuadratureRule): code = _abi.RK4
+
+class QuatRotation: code = _abi.ROT_QUAT
+class UnitQuaternion(QuatRotation): pass
+class MRP: code = _abi.ROT_MRP
+class RodriguesParam: code = _abi.ROT_RP
+
+class EuclideanState: pass
+class RotationState: pass
+
+
+def _qcode(Q):
+    if isinstance(Q, int):
+        return Q
+    if isinstance(Q, QuadratureRule) or (isinstance(Q, type) and issubclass(Q, QuadratureRule)):
+        return Q.code
+    raise TypeError(f"not a QuadratureRule: {Q!r}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# models (reference: src/dynamics.jl:2,68; test/cartpole_model.jl; test/quadrotor.jl; test/rigidbody_test.jl:23-56;
+#         examples/single_satellite.jl:7-35; test/double_integrator.jl:97-127)
+# ---------------------------------------------------------------------------------------------------
+class AbstractModel:
+    """ContinuousDynamics model bound to a GPU through an rdb_model handle."""
+    statevectortype = EuclideanState
+
+    def __init__(self, kind, rot, frame, params, device=None):
+        self._h = _abi.ModelHandle(kind, rot, frame, params, device)
+
+    @property
+    def n(self): return self._h.n
+    @property
+    def m(self): return self._h.m
+
+
+class ContinuousDynamics(AbstractModel): pass
+
+
+class Cartpole(ContinuousDynamics):
+    def __init__(self, mc=1.0, mp=0.2, l=0.5, g=9.81, device=None):
+        super().__init__(_abi.CARTPOLE, _abi.ROT_NONE, 0, [mc, mp, l, g], device)
+
+
+class DoubleIntegrator(ContinuousDynamics):
+    def __init__(self, D=1, device=None):
+        super().__init__(_abi.DOUBLE_INTEGRATOR, _abi.ROT_NONE, 0, [D], device)
+
+
+class RigidBody(ContinuousDynamics):
+    """RigidBody{R} <: LieGroupModel; LieState(R, (3, 6))  (reference: src/rigidbody.jl:46-48)."""
+    statevectortype = RotationState
+
+
+def _inertia(J):
+    J = np.asarray(J, dtype=np.float64)
+    return np.diag(J) if J.ndim == 1 else J
+
+
+class Quadrotor(RigidBody):
+    def __init__(self, R=QuatRotation, mass=0.5, J=(0.0023, 0.0023, 0.004), gravity=(0.0, 0.0, -9.81), motor_dist=0.175,
+                 kf=1.0, km=0.0245, bodyframe=False, device=None):
+        super().__init__(_abi.QUADROTOR, R.code, int(bool(bodyframe)),
+                         [mass, *_inertia(J).reshape(-1), *gravity, motor_dist, kf, km], device)
+
+
+class Body(RigidBody):
+    """test/rigidbody_test.jl:23-56: F_world = q*u[1:3], M_body = u[4:6], mass 2, J = diag(2,3,1)."""
+    def __init__(self, R=QuatRotation, mass=2.0, J=(2.0, 3.0, 1.0), bodyframe=False, device=None):
+        super().__init__(_abi.BODY, R.code, int(bool(bodyframe)), [mass, *_inertia(J).reshape(-1)], device)
+
+
+class Satellite(Body):
+    """examples/single_satellite.jl:7-35: the same wrench with mass 1, J = I."""
+    def __init__(self, R=QuatRotation, bodyframe=False, device=None):
+        super().__init__(R, 1.0, (1.0, 1.0, 1.0), bodyframe, device)
+
+
+class DiscreteDynamics(AbstractModel): pass
+
+
+class DiscretizedDynamics(DiscreteDynamics):
+    """DiscretizedDynamics{L,Q}(model)  (reference: src/discretized_dynamics.jl:169-191)."""
+    def __init__(self, model, Q=RK4):
+        self.continuous_dynamics, self.integrator = model, Q
+        self._h, self.statevectortype = model._h, model.statevectortype
+
+
+def state_dim(f): return f._h.n if hasattr(f, "_h") else f.n
+def control_dim(f): return f._h.m if hasattr(f, "_h") else f.m
+def errstate_dim(f): return f._h.nerr
+def output_dim(f): return state_dim(f)
+def jacobian_width(f): return errstate_dim(f) + control_dim(f)          # src/functionbase.jl:135
+def dims(f): return state_dim(f), control_dim(f), output_dim(f)
+def default_diffmethod(f): return ForwardAD() if isinstance(f, DiscretizedDynamics) else UserDefined()
+def default_signature(f): return StaticReturn()
+
+
+# ---------------------------------------------------------------------------------------------------
+# containers (reference: src/knotpoint.jl:146-219, src/trajectories.jl:40-50, src/jacobian.jl:26-43)
+# ---------------------------------------------------------------------------------------------------
+class KnotPoint:
+    """z = [x;u], t, dt.  KnotPoint(x, u, t, dt) or KnotPoint(n, m, z, t, dt)."""
+
+    def __init__(self, *args):
+        if len(args) == 4:
+            x, u, t, dt = args
+            x, u = np.asarray(x), np.asarray(u)
+            self.n, self.m, self.z = len(x), len(u), np.concatenate([x, u])
+        elif len(args) == 5:
+            n, m, z, t, dt = args
+            assert n > 0 and m > 0 and n + m == len(z)
+            self.n, self.m, self.z = int(n), int(m), np.array(z)
+        else:
+            raise TypeError("KnotPoint(x, u, t, dt) or KnotPoint(n, m, z, t, dt)")
+        self.t, self.dt = float(t), float(dt)
+
+StaticKnotPoint = KnotPoint
+
+
+def state(z): return z.z[:z.n]
+def control(z): return z.z[z.n:] * (0.0 if is_terminal(z) else 1.0)     # zeros at a terminal knot (src/knotpoint.jl:67)
+def getdata(z): return z.z
+def time(z): return z.t
+def timestep(z): return z.dt
+def is_terminal(z): return z.dt == 0.0
+
+
+class SampledTrajectory:
+    """A vector of knot points, stored as the batched arrays the GPU consumes: data (N, n+m), times (N,), dt (N,)."""
+
+    def __init__(self, X, U=None, dt=None, t0=0.0, dtype=np.float64):
+        if U is None:                       # list of KnotPoints
+            kps = list(X)
+            self.n, self.m = kps[0].n, kps[0].m
+            self.data = np.ascontiguousarray(np.stack([k.z for k in kps]), dtype=dtype)
+            self.times = np.array([k.t for k in kps], dtype=np.float64)
+            self.dts = np.array([k.dt for k in kps], dtype=np.float64)
+        else:
+            X, U = np.asarray(X), np.asarray(U)
+            N = X.shape[0]
+            self.n, self.m = X.shape[1], U.shape[1]
+            Uf = np.zeros((N, self.m))
+            Uf[:U.shape[0]] = U
+            self.data = np.ascontiguousarray(np.concatenate([X, Uf], axis=1), dtype=dtype)
+            self.dts = np.broadcast_to(np.asarray(dt, dtype=np.float64), (N,)).copy()
+            if U.shape[0] == N - 1:
+                self.dts[-1] = 0.0          # no terminal control -> terminal dt = 0 (src/trajectories.jl:82-83,110)
+            self.times = t0 + np.concatenate([[0.0], np.cumsum(self.dts[:-1])])
+
+    def __len__(self): return self.data.shape[0]
+    def __getitem__(self, k): return KnotPoint(self.n, self.m, self.data[k], self.times[k], self.dts[k])
+    def __iter__(self): return (self[k] for k in range(len(self)))
+
+
+def states(Z): return Z.data[:, :Z.n]
+def controls(Z): return Z.data[:, Z.n:]
+def gettimes(Z): return Z.times
+def setstates_(Z, X): Z.data[:, :Z.n] = X
+def setcontrols_(Z, U): Z.data[:len(U), Z.n:] = U
+
+
+class DynamicsJacobian:
+    """n x (n+m) column-major [A B] with .A / .B views (reference: src/jacobian.jl:26-37).  `data` is stored as the
+    (n+m, n) C-order array whose memory equals Julia's column-major Matrix{T}(n, n+m)."""
+
+    def __init__(self, n, m=None, dtype=np.float64, data=None):
+        if m is None and hasattr(n, "_h"):
+            n, m = state_dim(n), control_dim(n)
+        self.n, self.m = n, m
+        self.data = np.zeros((n + m, n), dtype=dtype) if data is None else data
+
+    @property
+    def A(self): return self.data[:self.n].T
+    @property
+    def B(self): return self.data[self.n:].T
+    def matrix(self): return self.data.T
+    def __array__(self, dtype=None, copy=None): return np.asarray(self.data.T, dtype=dtype)
+
+
+def get_data(D): return D.data.T
+
+
+# ---------------------------------------------------------------------------------------------------
+# argument plumbing
+# ---------------------------------------------------------------------------------------------------
+def _batch(z):
+    """-> (Z (N, n+m) array/tensor, t, dt, single?)."""
+    if isinstance(z, KnotPoint):
+        return np.ascontiguousarray(z.z[None, :]), np.array([z.t]), np.array([z.dt]), True
+    if isinstance(z, SampledTrajectory):
+        return z.data, z.times, z.dts, False
+    raise TypeError(f"expected a KnotPoint or SampledTrajectory, got {type(z).__name__}")
+
+
+def _write(dst, src, single):
+    if dst is None:
+        return src[0] if single else src
+    if isinstance(dst, DynamicsJacobian):
+        dst.data[...] = src[0]
+    elif single:
+        dst[...] = src[0].T if src[0].ndim == 2 else src[0]
+    elif dst is not src:
+        dst[...] = src
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------------
+# the hot path
+# ---------------------------------------------------------------------------------------------------
+def dynamics(model, *args, out=None):
+    """dynamics(model, z) | dynamics(model, x, u[, t]) | dynamics(model, Z::SampledTrajectory) -> xdot."""
+    if len(args) == 1:
+        Z, _, _, single = _batch(args[0])
+    else:
+        x, u = np.asarray(args[0]), np.asarray(args[1])
+        Z, single = np.ascontiguousarray(np.concatenate([x, u])[None, :]), True
+    r = model._h.dynamics(Z, out=None if single else out)
+    return r[0] if single else r
+
+
+def dynamics_(model, xdot, *args):
+    xdot[...] = dynamics(model, *args)
+    return None
+
+
+def evaluate(fun, z):                                              # src/functionbase.jl:214-238
+    return discrete_dynamics(fun, z) if isinstance(fun, DiscreteDynamics) else dynamics(fun, z)
+
+
+def discrete_dynamics(*args, out=None):
+    """discrete_dynamics(dmodel, z) | (dmodel, x, u, t, dt) | v0.3 (Q, model, z) -> x+."""
+    if isinstance(args[0], (QuadratureRule, type)) and not isinstance(args[0], AbstractModel):
+        args = (DiscretizedDynamics(args[1], args[0]),) + tuple(args[2:])
+    dmodel = args[0]
+    if len(args) == 2:
+        Z, _, dt, single = _batch(args[1])
+    else:
+        x, u, _, h = args[1:5]
+        Z, dt, single = np.ascontiguousarray(np.concatenate([np.asarray(x), np.asarray(u)])[None, :]), np.array([float(h)]), True
+    r = dmodel._h.discrete_dynamics(_qcode(dmodel.integrator), Z, dt, out=None if single else out)
+    return r[0] if single else r
+
+
+def discrete_dynamics_(dmodel, xn, *args):
+    xn[...] = discrete_dynamics(dmodel, *args)
+    return None
+
+
+def jacobian_(sig, diff, fun, J, y, z):
+    """jacobian!(sig, diff, fun, J, y, z): J <- d fun / d [x;u]; y <- fun(z) (the reference leaves y unspecified for
+    StaticReturn; here it is always the true output when given).  FiniteDifference is refused:
+    the GPU path is exact forward mode (== ForwardAD == UserDefined chain rule to rounding, test/integration_tests.jl:13-17)."""
+    if isinstance(diff, FiniteDifference) or diff is FiniteDifference:
+        raise NotImplementedModelError(_abi.ERR_NOT_IMPLEMENTED, "jacobian!(::FiniteDifference) on the B200 path")
+    Z, _, dt, single = _batch(z)
+    h = fun._h
+    yb = None
+    if y is not None:
+        yb = np.empty((Z.shape[0], h.n), dtype=Z.dtype) if single or not hasattr(y, "shape") else y
+    if isinstance(fun, DiscretizedDynamics):
+        Jb = h.discrete_jacobian(_qcode(fun.integrator), Z, dt, J=None if single or isinstance(J, DynamicsJacobian) else J, xn=yb)
+    else:
+        Jb = h.jacobian(Z, J=None if single or isinstance(J, DynamicsJacobian) else J, xdot=yb)
+    _write(J, Jb, single)
+    if y is not None and yb is not y:
+        y[...] = yb[0] if single else yb
+    return None
+
+
+def discrete_jacobian_(Q, J, model, z):
+    """v0.3 spelling: discrete_jacobian!(RK4, ∇f, model, z)  (README.md:81-82)."""
+    return jacobian_(StaticReturn(), B200(), DiscretizedDynamics(model, Q), J, None, z)
+
+
+def _states_of(model, x):
+    """x: KnotPoint | SampledTrajectory | (n,) | (N, >=n) -> (X (N, ld), single?)."""
+    if isinstance(x, KnotPoint):
+        return np.ascontiguousarray(x.z[None, :]), True
+    if isinstance(x, SampledTrajectory):
+        return x.data, False
+    if _abi._is_torch(x):
+        return (x[None, :].contiguous(), True) if x.dim() == 1 else (x, False)
+    x = np.asarray(x)
+    return (np.ascontiguousarray(x[None, :]), True) if x.ndim == 1 else (x, False)
+
+
+def errstate_jacobian_(model, G, x):
+    """errstate_jacobian!(model, G, x|z): G (n x nerr) fully written (reference writes only the non-zeros)."""
+    X, single = _states_of(model, x)
+    Gb = model._h.errstate_jacobian(X, G=None if single else G)
+    if single:
+        G[...] = Gb[0].T if not _abi._is_torch(Gb) else Gb[0].T
+    return None
+
+
+def grad_errstate_jacobian_(model, dG, x, xbar):
+    """∇errstate_jacobian!(model, ∇G, x, x̄)."""
+    X, single = _states_of(model, x)
+    B, _ = _states_of(model, xbar)
+    Hb = model._h.grad_errstate_jacobian(X, B, H=None if single else dG)
+    if single:
+        dG[...] = Hb[0].T
+    return None
+
+
+def state_diff(model, x, x0):
+    X, single = _states_of(model, x)
+    X0, _ = _states_of(model, x0)
+    d = model._h.state_diff(X, X0)
+    return d[0] if single else d
+
+
+def rollout_(sig, dmodel, Z, x0=None):
+    """rollout!(sig, dmodel, Z, x0): overwrite the states of Z with the simulated trajectory (one trajectory)."""
+    x0 = states(Z)[0] if x0 is None else np.asarray(x0)
+    X = dmodel._h.rollout(_qcode(dmodel.integrator), np.ascontiguousarray(x0[None, :], dtype=Z.data.dtype),
+                          np.ascontiguousarray(controls(Z)[None, :-1]), np.ascontiguousarray(Z.dts[None, :]))
+    setstates_(Z, X[0])
+    return None
+
+
+def rollout_batch(dmodel, x0, U, dt):
+    """Many independent trajectories at once: x0 (ntraj, n), U (ntraj, K-1, m), dt scalar or (ntraj, K) -> X (ntraj, K, n)."""
+    return dmodel._h.rollout(_qcode(dmodel.integrator), x0, U, dt)

@@ -1,0 +1,47 @@
+// integrators.cuh — explicit Runge-Kutta steps x+ = integrate(Q, f, x, u, h), generic over the scalar kind.
+//
+//   Euler  reference: src/integration.jl:73-76        x + h f(x,u)
+//   RK2    explicit midpoint (not in src/ at v0.4.8; pinned by test/old_tests/linear_tests.jl:135-141)
+//   RK3    reference: src/integration.jl:130-135      k3 at x - k1 + 2 k2, weights (1,4,1)/6
+//   RK4    reference: src/integration.jl:280-286      classic, weights (1,2,2,1)/6
+//
+// The reference forms k_i = f(.)*h and sums them; here h is folded into the stage coefficients
+// (x + (h/2) f1 instead of x + (f1*h)/2), which is the same map up to rounding (~1 ulp) and saves one
+// multiply per partial when the scalars are sparse duals.  Called with seeded duals this IS the discrete
+// Jacobian (forward mode through the integrator, reference: src/jacobian_gen.jl:485-507), and it equals the
+// chain rule of src/integration.jl:302-337 to rounding.  t is accepted for API fidelity; every shipped
+// model is time-invariant (reference: src/dynamics.jl:83).
+#pragma once
+#include "models.cuh"
+
+namespace rdb {
+
+template <int Q, class T, class Model, class X, class U>
+RDB_HD auto integrate(const Model& model, const X& x, const U& u, T h) {
+    if constexpr (Q == Q_CONTINUOUS) {
+        return model.f(x, u);
+    } else if constexpr (Q == Q_EULER) {
+        return axpy(x, h, model.f(x, u));
+    } else if constexpr (Q == Q_RK2) {
+        auto f1 = model.f(x, u);
+        auto f2 = model.f(axpy(x, T(0.5) * h, f1), u);
+        return axpy(x, h, f2);
+    } else if constexpr (Q == Q_RK3) {
+        auto f1 = model.f(x, u);
+        auto f2 = model.f(axpy(x, T(0.5) * h, f1), u);
+        auto f3 = model.f(axpy(axpy(x, -h, f1), T(2) * h, f2), u);
+        auto acc = axpy(vadd(f1, f3), T(4), f2);
+        return axpy(x, h / T(6), acc);
+    } else {
+        static_assert(Q == Q_RK4, "unknown quadrature rule");
+        auto f1 = model.f(x, u);
+        auto f2 = model.f(axpy(x, T(0.5) * h, f1), u);
+        auto acc1 = axpy(f1, T(2), f2);
+        auto f3 = model.f(axpy(x, T(0.5) * h, f2), u);
+        auto acc2 = axpy(acc1, T(2), f3);
+        auto f4 = model.f(axpy(x, h, f3), u);
+        return axpy(x, h / T(6), vadd(acc2, f4));
+    }
+}
+
+}  // namespace rdb

@@ -1,0 +1,163 @@
+// lie.cu — LieState error-state maps for RigidBody{R} states (K4/K5 of SURVEY.md §2), one thread per OUTPUT
+// element so every store is coalesced; the rotation block entries are recomputed from the knot's attitude.
+//
+//   errstate_jacobian!   reference: src/liestate.jl:262-298 (block-diag I / Rotations.∇differential), Euclidean
+//                        fall-back src/statevectortype.jl:149-155.  Unlike the reference the whole matrix is written.
+//   ∇errstate_jacobian!  reference: src/liestate.jl:300-320 (Rotations.∇²differential on the rotation block)
+//   state_diff           reference: src/liestate.jl:210-260 (vector parts x - x0, rotations Cayley error of q0\q)
+//
+// Here the attitude IS normalised (default R(w,x,y,z) constructor), unlike inside dynamics.
+#include "lie.h"
+
+namespace rdb {
+
+template <class T> __device__ __forceinline__ T rsq(T a);
+template <> __device__ __forceinline__ float rsq<float>(float a) { return 1.0f / sqrtf(a); }
+template <> __device__ __forceinline__ double rsq<double>(double a) { return 1.0 / sqrt(a); }
+
+// unit quaternion of an attitude parameterisation
+template <class T>
+__device__ __forceinline__ void unit_quat(int rot, const T* p, T* q) {
+    if (rot == ROT_QUAT) {
+        const T s = rsq(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+        q[0] = p[0] * s; q[1] = p[1] * s; q[2] = p[2] * s; q[3] = p[3] * s;
+    } else if (rot == ROT_MRP) {
+        const T n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        const T i1 = T(1) / (T(1) + n2), M = T(2) * i1;
+        q[0] = (T(1) - n2) * i1; q[1] = M * p[0]; q[2] = M * p[1]; q[3] = M * p[2];
+    } else {
+        const T M = rsq(T(1) + p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        q[0] = M; q[1] = M * p[0]; q[2] = M * p[1]; q[3] = M * p[2];
+    }
+}
+
+// entry (i,j) of Rotations.∇differential(R):  quat 4x3 L(q)H,  MRP (1-|p|^2) I + 2(skew(p) + p p'),  RP I + skew(g) + g g'
+template <class T>
+__device__ __forceinline__ T grad_differential(int rot, const T* p, int i, int j) {
+    if (rot == ROT_QUAT) {
+        T q[4]; unit_quat(rot, p, q);
+        const T w = q[0], x = q[1], y = q[2], z = q[3];
+        const T G[4][3] = {{-x, -y, -z}, {w, -z, y}, {z, w, -x}, {-y, x, w}};
+        return G[i][j];
+    }
+    const T sk[3][3] = {{T(0), -p[2], p[1]}, {p[2], T(0), -p[0]}, {-p[1], p[0], T(0)}};
+    const T I = (i == j) ? T(1) : T(0);
+    if (rot == ROT_MRP) {
+        const T n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+        return (T(1) - n2) * I + T(2) * (sk[i][j] + p[i] * p[j]);
+    }
+    return I + sk[i][j] + p[i] * p[j];
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) errstate_jacobian_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx, T* __restrict__ G) {
+    const long long total = N * (long long)n * ne;
+    const int per = n * ne;
+    const int np = (rot == ROT_QUAT) ? 4 : 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / per;
+        const int e = int(idx - k * per), j = e / n, i = e - j * n;
+        T v;
+        if (rot == ROT_NONE) v = (i == j) ? T(1) : T(0);
+        else if (i < 3) v = (j == i) ? T(1) : T(0);
+        else if (i < 3 + np) v = (j >= 3 && j < 6) ? grad_differential(rot, X + k * ldx + 3, i - 3, j - 3) : T(0);
+        else v = (j == i - np + 3) ? T(1) : T(0);
+        G[idx] = v;
+    }
+}
+
+// ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p)
+template <class T>
+__global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx,
+                                                                     const T* __restrict__ B, int ldb, T* __restrict__ H) {
+    const long long total = N * (long long)ne * ne;
+    const int per = ne * ne;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / per;
+        const int e = int(idx - k * per), j = e / ne, i = e - j * ne;
+        T v = T(0);
+        if (rot != ROT_NONE && i >= 3 && i < 6 && j >= 3 && j < 6) {
+            const T* p = X + k * ldx + 3;
+            const T* b = B + k * ldb + 3;
+            const int a = i - 3, c = j - 3;
+            if (rot == ROT_QUAT) {
+                if (a == c) { T q[4]; unit_quat(rot, p, q); v = -(q[0] * b[0] + q[1] * b[1] + q[2] * b[2] + q[3] * b[3]); }
+            } else {
+                const T pb = p[0] * b[0] + p[1] * b[1] + p[2] * b[2];
+                const T skb[3][3] = {{T(0), -b[2], b[1]}, {b[2], T(0), -b[0]}, {-b[1], b[0], T(0)}};
+                T s = T(0);
+                for (int r = 0; r < 3; ++r) {
+                    const T I = (a == r) ? T(1) : T(0);
+                    const T dG = (rot == ROT_MRP) ? (T(-2) * b[a] * p[r] + T(2) * skb[a][r] + T(2) * (pb * I + p[a] * b[r]))
+                                                  : (skb[a][r] + pb * I + p[a] * b[r]);
+                    s += dG * grad_differential(rot, p, r, c);
+                }
+                v = s;
+            }
+        }
+        H[idx] = v;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) state_diff_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx,
+                                                         const T* __restrict__ X0, int ldx0, T* __restrict__ dX) {
+    const long long total = N * (long long)ne;
+    const int np = (rot == ROT_QUAT) ? 4 : 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / ne;
+        const int i = int(idx - k * ne);
+        const T* x = X + k * ldx;
+        const T* x0 = X0 + k * ldx0;
+        T v;
+        if (rot == ROT_NONE || i < 3) v = x[i] - x0[i];
+        else if (i >= 6) v = x[i + np - 3] - x0[i + np - 3];
+        else {
+            T q[4], q0[4];
+            unit_quat(rot, x + 3, q);
+            unit_quat(rot, x0 + 3, q0);
+            // e = conj(q0) (x) q ;  Cayley map: vec(e) / scalar(e)
+            const T c0 = q0[0], c1 = -q0[1], c2 = -q0[2], c3 = -q0[3];
+            const T e0 = c0 * q[0] - c1 * q[1] - c2 * q[2] - c3 * q[3];
+            T ev;
+            if (i == 3) ev = c0 * q[1] + c1 * q[0] + c2 * q[3] - c3 * q[2];
+            else if (i == 4) ev = c0 * q[2] - c1 * q[3] + c2 * q[0] + c3 * q[1];
+            else ev = c0 * q[3] + c1 * q[2] - c2 * q[1] + c3 * q[0];
+            v = ev / e0;
+        }
+        dX[idx] = v;
+    }
+}
+
+static unsigned grid_for(long long total, int sm_count) {
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)sm_count * 8;
+    if (g > cap) g = cap;
+    return unsigned(g < 1 ? 1 : g);
+}
+
+int lie_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, void* G, int sm_count, cudaStream_t st) {
+    if (N <= 0) return 0;
+    const unsigned g = grid_for(N * (long long)n * ne, sm_count);
+    if (dtype == 0) errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (float*)G);
+    else errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (double*)G);
+    return int(cudaGetLastError());
+}
+int lie_grad_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, const void* B, int ldb, void* H,
+                               int sm_count, cudaStream_t st) {
+    if (N <= 0) return 0;
+    const unsigned g = grid_for(N * (long long)ne * ne, sm_count);
+    if (dtype == 0) grad_errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (const float*)B, ldb, (float*)H);
+    else grad_errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (const double*)B, ldb, (double*)H);
+    return int(cudaGetLastError());
+}
+int lie_state_diff(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, const void* X0, int ldx0, void* dX,
+                   int sm_count, cudaStream_t st) {
+    if (N <= 0) return 0;
+    const unsigned g = grid_for(N * (long long)ne, sm_count);
+    if (dtype == 0) state_diff_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
+    else state_diff_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);
+    return int(cudaGetLastError());
+}
+
+}  // namespace rdb

@@ -1,0 +1,182 @@
+// models.cuh — continuous dynamics xdot = f(x,u) of the models the reference's hot path is exercised with,
+// written once, generically over the scalar kind (plain T, or SD<T,MASK> sparse duals from sdual.cuh).
+//
+//   Cartpole           reference: test/cartpole_model.jl:9-30           (n=4,  m=1)
+//   RigidBody{R}       reference: src/rigidbody.jl:213-236              (n=13 quat / 12 MRP,RP)
+//     Quadrotor wrench reference: test/quadrotor.jl:56-96               (m=4)
+//     Body/Satellite   reference: test/rigidbody_test.jl:26-31, examples/single_satellite.jl:17-27  (m=6)
+//   DoubleIntegrator   reference: test/double_integrator.jl:97-106      (n=2D, m=D)
+//
+// Rotation arithmetic restates the published formulas of Rotations.jl 1.x (not vendored in the reference;
+// SURVEY.md §8c): Hamilton quaternion [w,x,y,z], q*r = (w^2 - v.v) r + 2 v (v.r) + 2 w (v x r) WITHOUT
+// normalisation (the state quaternion is built with renorm=false, src/rigidbody.jl:101-105).
+#pragma once
+#include "sdual.cuh"
+
+namespace rdb {
+
+enum ModelKind { KIND_CARTPOLE = 0, KIND_QUADROTOR = 1, KIND_BODY = 2, KIND_DOUBLE_INTEGRATOR = 3 };
+enum RotKind { ROT_NONE = 0, ROT_QUAT = 1, ROT_MRP = 2, ROT_RP = 3 };
+enum FrameKind { FRAME_WORLD = 0, FRAME_BODY = 1 };
+enum QuadRule { Q_EULER = 0, Q_RK2 = 1, Q_RK3 = 2, Q_RK4 = 3, Q_CONTINUOUS = 4 };
+
+// Parameter block shared by host and device (passed to kernels by value).
+template <class T>
+struct ModelParams {
+    // cartpole
+    T mc, mp, l, g;
+    // rigid bodies
+    T mass, inv_mass;
+    T J[9], Jinv[9];
+    T mg[3];             // mass * gravity
+    T motor_dist, kf, km;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Cartpole
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct Cartpole {
+    static constexpr int n = 4, m = 1, nerr = 4, rot = ROT_NONE;
+    ModelParams<T> p;
+    template <class X, class U>
+    RDB_HD auto f(const X& x, const U& u) const {
+        const T mpl = p.mp * p.l;
+        const auto& qd0 = get<2>(x);
+        const auto& qd1 = get<3>(x);
+        auto th = get<1>(x);
+        auto s = th, c = th;
+        sincos_(th, s, c);
+        // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s]
+        const T H00 = p.mc + p.mp, H11 = mpl * p.l;
+        auto H01 = mpl * c;
+        auto r0 = -(mpl * (qd1 * s) * qd1) - get<0>(u);
+        auto r1 = (mpl * p.g) * s;
+        // qdd = -H \ r   (closed-form 2x2 solve, like StaticArrays)
+        auto idet = T(1) / (H00 * H11 - H01 * H01);
+        auto qdd0 = (H01 * r1 - H11 * r0) * idet;
+        auto qdd1 = (H01 * r0 - H00 * r1) * idet;
+        return vec(qd0, qd1, qdd0, qdd1);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Double integrator
+// ------------------------------------------------------------------------------------------------
+template <class T, int D>
+struct DoubleIntegrator {
+    static constexpr int n = 2 * D, m = D, nerr = 2 * D, rot = ROT_NONE;
+    ModelParams<T> p;
+    template <class X, class U>
+    RDB_HD auto f(const X& x, const U& u) const { return cat(slice<D, D>(x), u); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Rotation helpers (generic over element kinds)
+// ------------------------------------------------------------------------------------------------
+// q * r, un-normalised polynomial form.  q = Vec<w,x,y,z>, r = Vec<3>.
+template <class T, class Q, class R>
+RDB_HD auto quat_rotate(const Q& q, const R& r) {
+    const auto& w = get<0>(q);
+    auto v = slice<1, 3>(q);
+    auto a = w * w - dot3(v, v);
+    auto vr2 = T(2) * dot3(v, r);
+    auto w2 = T(2) * w;
+    auto c = cross3(v, r);
+    return vec(a * get<0>(r) + get<0>(v) * vr2 + w2 * get<0>(c),
+               a * get<1>(r) + get<1>(v) * vr2 + w2 * get<1>(c),
+               a * get<2>(r) + get<2>(v) * vr2 + w2 * get<2>(c));
+}
+template <class Q> RDB_HD auto quat_conj(const Q& q) { return vec(get<0>(q), -get<1>(q), -get<2>(q), -get<3>(q)); }
+
+// 3-parameter attitude -> the unit quaternion Rotations.jl builds for it.
+template <class T, int ROT, class P>
+RDB_HD auto to_quat(const P& p) {
+    if constexpr (ROT == ROT_QUAT) return p;
+    else if constexpr (ROT == ROT_MRP) {
+        auto n2 = dot3(p, p);
+        auto i1 = T(1) / (T(1) + n2);
+        auto M = T(2) * i1;
+        return vec((T(1) - n2) * i1, M * get<0>(p), M * get<1>(p), M * get<2>(p));
+    } else {
+        auto M = rsqrt_(T(1) + dot3(p, p));
+        return vec(M, M * get<0>(p), M * get<1>(p), M * get<2>(p));
+    }
+}
+
+// Rotations.kinematics(R, w): time derivative of the attitude parameters for body rate w.
+template <class T, int ROT, class P, class W>
+RDB_HD auto rot_kinematics(const P& p, const W& w) {
+    if constexpr (ROT == ROT_QUAT) {   // 1/2 q (x) [0; w], bilinear, no normalisation (reference: test/liemodel.jl:13-20)
+        const auto& qw = get<0>(p); const auto& qx = get<1>(p); const auto& qy = get<2>(p); const auto& qz = get<3>(p);
+        const auto& w0 = get<0>(w); const auto& w1 = get<1>(w); const auto& w2 = get<2>(w);
+        return vec(T(-0.5) * (qx * w0 + qy * w1 + qz * w2),
+                   T(0.5) * (qw * w0 + qy * w2 - qz * w1),
+                   T(0.5) * (qw * w1 + qz * w0 - qx * w2),
+                   T(0.5) * (qw * w2 + qx * w1 - qy * w0));
+    } else {
+        auto pw = dot3(p, w);
+        auto c = cross3(p, w);
+        if constexpr (ROT == ROT_MRP) {  // 1/4 [(1-|p|^2) I + 2 skew(p) + 2 p p'] w
+            auto a = T(1) - dot3(p, p);
+            return vec(T(0.25) * (a * get<0>(w) + T(2) * (get<0>(c) + get<0>(p) * pw)),
+                       T(0.25) * (a * get<1>(w) + T(2) * (get<1>(c) + get<1>(p) * pw)),
+                       T(0.25) * (a * get<2>(w) + T(2) * (get<2>(c) + get<2>(p) * pw)));
+        } else {                          // 1/2 [I + skew(g) + g g'] w
+            return vec(T(0.5) * (get<0>(w) + get<0>(c) + get<0>(p) * pw),
+                       T(0.5) * (get<1>(w) + get<1>(c) + get<1>(p) * pw),
+                       T(0.5) * (get<2>(w) + get<2>(c) + get<2>(p) * pw));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RigidBody{R} with the Quadrotor or Body/Satellite wrench
+// ------------------------------------------------------------------------------------------------
+template <class T, int KIND, int ROT, int FRAME>
+struct RigidBody {
+    static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
+    static constexpr int n = 9 + np, m = (KIND == KIND_QUADROTOR) ? 4 : 6, nerr = 12, rot = ROT;
+    ModelParams<T> p;
+
+    template <class X, class U>
+    RDB_HD auto f(const X& x, const U& u) const {
+        auto att = slice<3, np>(x);
+        auto v = slice<3 + np, 3>(x);
+        auto w = slice<6 + np, 3>(x);
+        auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised)
+
+        // wrench: F in the world frame, tau in the body frame
+        auto wrench = [&]() {
+            if constexpr (KIND == KIND_QUADROTOR) {
+                auto F1 = relu_(p.kf * get<0>(u));
+                auto F2 = relu_(p.kf * get<1>(u));
+                auto F3 = relu_(p.kf * get<2>(u));
+                auto F4 = relu_(p.kf * get<3>(u));
+                auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, F1 + F2 + F3 + F4));
+                auto F = vec(p.mg[0] + get<0>(qF), p.mg[1] + get<1>(qF), p.mg[2] + get<2>(qF));
+                auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
+                               p.km * (get<0>(u) - get<1>(u) + get<2>(u) - get<3>(u)));
+                return cat(F, tau);
+            } else {
+                return cat(quat_rotate<T>(q, slice<0, 3>(u)), slice<3, 3>(u));
+            }
+        };
+        auto xi = wrench();
+        auto F = slice<0, 3>(xi);
+        auto tau = slice<3, 3>(xi);
+
+        auto qdot = rot_kinematics<T, ROT>(att, w);
+        // omega_dot = Jinv (tau - w x (J w))
+        auto wdot = mat3_mul(p.Jinv, vsub(tau, cross3(w, mat3_mul(p.J, w))));
+        if constexpr (FRAME == FRAME_WORLD) {
+            return cat(v, qdot, vscale(p.inv_mass, F), wdot);
+        } else {
+            auto rdot = quat_rotate<T>(q, v);
+            auto vdot = vsub(quat_rotate<T>(quat_conj(q), vscale(p.inv_mass, F)), cross3(w, v));
+            return cat(rdot, qdot, vdot, wdot);
+        }
+    }
+};
+
+}  // namespace rdb

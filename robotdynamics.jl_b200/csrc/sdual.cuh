@@ -1,0 +1,232 @@
+// sdual.cuh — compile-time-sparse forward-mode numbers and heterogeneous fixed vectors (device side).
+//
+// The reference's default Jacobian path is forward-mode AD over the whole [x;u] vector
+// (reference: src/jacobian_gen.jl:485-507, ForwardDiff.jacobian).  On the GPU we keep that meaning
+// but make the set of non-zero partials part of the TYPE: SD<T,MASK> carries a value and one partial
+// per set bit of MASK (bit j <-> column j of [x;u]).  Every operation returns the union mask, so
+// structural zeros of the stage Jacobians are never computed, never stored,
+// and never occupy a register — without anybody hand-deriving a sparsity pattern per model.
+// Because element types differ, vectors are heterogeneous tuples (Vec<...>) indexed at compile time.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <type_traits>
+
+#ifndef RDB_HD
+#define RDB_HD __host__ __device__ __forceinline__
+#endif
+
+namespace rdb {
+
+using mask_t = uint32_t;
+
+__host__ __device__ constexpr int cpopc(mask_t m) { int c = 0; while (m) { c += int(m & 1u); m >>= 1; } return c; }
+__host__ __device__ constexpr bool chas(mask_t m, int j) { return (m >> j) & 1u; }
+__host__ __device__ constexpr int cslot(mask_t m, int j) { return cpopc(m & ((mask_t(1) << j) - 1u)); }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+template <class T> struct ident { using type = T; };
+template <class T> using ident_t = typename ident<T>::type;
+
+// ---------------------------------------------------------------------------------------------
+// Structural zero: 0 * x == Zero, 0 + x == x.  Lets generic code (e.g. rotate([0,0,F])) prune itself.
+// ---------------------------------------------------------------------------------------------
+struct Zero {};
+
+// ---------------------------------------------------------------------------------------------
+// Sparse dual number.
+// ---------------------------------------------------------------------------------------------
+template <class T, mask_t M>
+struct SD {
+    static_assert(M != 0, "SD needs at least one partial; use plain T otherwise");
+    static constexpr mask_t mask = M;
+    T v;
+    T d[cpopc(M)];
+    template <int J> RDB_HD T part() const {
+        if constexpr (chas(M, J)) return d[cslot(M, J)]; else return T(0);
+    }
+};
+
+template <class X> struct is_sd : std::false_type {};
+template <class T, mask_t M> struct is_sd<SD<T, M>> : std::true_type {};
+template <class X> struct mask_of { static constexpr mask_t value = 0; };
+template <class T, mask_t M> struct mask_of<SD<T, M>> { static constexpr mask_t value = M; };
+
+template <class T> RDB_HD T val(const T& a) { return a; }
+template <class T, mask_t M> RDB_HD T val(const SD<T, M>& a) { return a.v; }
+
+// compile-time loop over the set bits of a mask:  f(std::integral_constant<int,j>)
+template <mask_t M, int J = 0, class F>
+RDB_HD void for_bits(F&& f) {
+    if constexpr ((M >> J) != 0) {
+        if constexpr (chas(M, J)) f(std::integral_constant<int, J>{});
+        for_bits<M, J + 1>(f);
+    }
+}
+
+// ---- SD (+,-) SD --------------------------------------------------------------------------------
+template <class T, mask_t A, mask_t B, int J = 0>
+RDB_HD void add_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
+    if constexpr (((A | B) >> J) != 0) {
+        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] + b.d[cslot(B, J)];
+        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)];
+        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = b.d[cslot(B, J)];
+        add_parts<T, A, B, J + 1>(r, a, b);
+    }
+}
+template <class T, mask_t A, mask_t B, int J = 0>
+RDB_HD void sub_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
+    if constexpr (((A | B) >> J) != 0) {
+        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] - b.d[cslot(B, J)];
+        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)];
+        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = -b.d[cslot(B, J)];
+        sub_parts<T, A, B, J + 1>(r, a, b);
+    }
+}
+// r.d = a.d * bv + b.d * av
+template <class T, mask_t A, mask_t B, int J = 0>
+RDB_HD void mul_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
+    if constexpr (((A | B) >> J) != 0) {
+        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * b.v + b.d[cslot(B, J)] * a.v;
+        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * b.v;
+        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = b.d[cslot(B, J)] * a.v;
+        mul_parts<T, A, B, J + 1>(r, a, b);
+    }
+}
+// r.d = (a.d - q * b.d) * ib        (q = a/b, ib = 1/b)
+template <class T, mask_t A, mask_t B, int J = 0>
+RDB_HD void div_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b, T q, T ib) {
+    if constexpr (((A | B) >> J) != 0) {
+        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = (a.d[cslot(A, J)] - q * b.d[cslot(B, J)]) * ib;
+        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * ib;
+        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = -(q * b.d[cslot(B, J)]) * ib;
+        div_parts<T, A, B, J + 1>(r, a, b, q, ib);
+    }
+}
+
+template <class T, mask_t A, mask_t B>
+RDB_HD SD<T, (A | B)> operator+(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A | B)> r; r.v = a.v + b.v; add_parts<T, A, B>(r, a, b); return r; }
+template <class T, mask_t A, mask_t B>
+RDB_HD SD<T, (A | B)> operator-(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A | B)> r; r.v = a.v - b.v; sub_parts<T, A, B>(r, a, b); return r; }
+template <class T, mask_t A, mask_t B>
+RDB_HD SD<T, (A | B)> operator*(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A | B)> r; r.v = a.v * b.v; mul_parts<T, A, B>(r, a, b); return r; }
+template <class T, mask_t A, mask_t B>
+RDB_HD SD<T, (A | B)> operator/(const SD<T, A>& a, const SD<T, B>& b) {
+    SD<T, (A | B)> r; const T ib = T(1) / b.v; r.v = a.v * ib; div_parts<T, A, B>(r, a, b, r.v, ib); return r;
+}
+
+// ---- SD with scalar -----------------------------------------------------------------------------
+template <class T, mask_t A> RDB_HD SD<T, A> operator-(const SD<T, A>& a) { SD<T, A> r; r.v = -a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = -a.d[i]; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator+(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r = a; r.v = a.v + b; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator+(ident_t<T> b, const SD<T, A>& a) { SD<T, A> r = a; r.v = b + a.v; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator-(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r = a; r.v = a.v - b; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator-(ident_t<T> b, const SD<T, A>& a) { SD<T, A> r; r.v = b - a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = -a.d[i]; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator*(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r; r.v = a.v * b; for (int i = 0; i < cpopc(A); ++i) r.d[i] = a.d[i] * b; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator*(ident_t<T> b, const SD<T, A>& a) { return a * b; }
+template <class T, mask_t A> RDB_HD SD<T, A> operator/(const SD<T, A>& a, ident_t<T> b) { return a * (T(1) / b); }
+template <class T, mask_t A> RDB_HD SD<T, A> operator/(ident_t<T> b, const SD<T, A>& a) {
+    SD<T, A> r; const T ib = T(1) / a.v; r.v = b * ib; const T s = -r.v * ib; for (int i = 0; i < cpopc(A); ++i) r.d[i] = a.d[i] * s; return r;
+}
+
+// ---- Zero algebra -------------------------------------------------------------------------------
+RDB_HD Zero operator+(Zero, Zero) { return {}; }
+RDB_HD Zero operator-(Zero, Zero) { return {}; }
+RDB_HD Zero operator*(Zero, Zero) { return {}; }
+RDB_HD Zero operator-(Zero) { return {}; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator+(Zero, const X& x) { return x; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator+(const X& x, Zero) { return x; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator-(const X& x, Zero) { return x; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD auto operator-(Zero, const X& x) { return -x; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD Zero operator*(Zero, const X&) { return {}; }
+template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD Zero operator*(const X&, Zero) { return {}; }
+
+// ---- elementary functions -----------------------------------------------------------------------
+RDB_HD void sincos_(float a, float& s, float& c) { sincosf(a, &s, &c); }
+RDB_HD void sincos_(double a, double& s, double& c) { sincos(a, &s, &c); }
+template <class T, mask_t A>
+RDB_HD void sincos_(const SD<T, A>& a, SD<T, A>& s, SD<T, A>& c) {
+    sincos_(a.v, s.v, c.v);
+    for (int i = 0; i < cpopc(A); ++i) { s.d[i] = c.v * a.d[i]; c.d[i] = -(s.v * a.d[i]); }
+}
+RDB_HD float rsqrt_(float a) { return 1.0f / sqrtf(a); }
+RDB_HD double rsqrt_(double a) { return 1.0 / sqrt(a); }
+template <class T, mask_t A>
+RDB_HD SD<T, A> rsqrt_(const SD<T, A>& a) {   // a^(-1/2);  d = -1/2 a^(-3/2) da
+    SD<T, A> r; r.v = rsqrt_(a.v); const T s = T(-0.5) * r.v / a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = s * a.d[i]; return r;
+}
+// max(0, a): ForwardDiff compares values; derivative is 0 when the clamp is active or at exactly 0
+// (reference: test/quadrotor.jl:67-70).
+RDB_HD float relu_(float a) { return a > 0.0f ? a : 0.0f; }
+RDB_HD double relu_(double a) { return a > 0.0 ? a : 0.0; }
+template <class T, mask_t A>
+RDB_HD SD<T, A> relu_(const SD<T, A>& a) {
+    SD<T, A> r; const bool on = a.v > T(0); r.v = on ? a.v : T(0); for (int i = 0; i < cpopc(A); ++i) r.d[i] = on ? a.d[i] : T(0); return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Heterogeneous fixed vector.
+// ---------------------------------------------------------------------------------------------
+template <int I, class E> struct Leaf { E e; };
+template <class Seq, class... Es> struct VecBase;
+template <size_t... Is, class... Es>
+struct VecBase<std::index_sequence<Is...>, Es...> : Leaf<int(Is), Es>... {
+    RDB_HD VecBase() {}
+    RDB_HD VecBase(const Es&... es) : Leaf<int(Is), Es>{es}... {}
+};
+template <class... Es>
+struct Vec : VecBase<std::index_sequence_for<Es...>, Es...> {
+    using Base = VecBase<std::index_sequence_for<Es...>, Es...>;
+    static constexpr int size = int(sizeof...(Es));
+    RDB_HD Vec() {}
+    RDB_HD Vec(const Es&... es) : Base(es...) {}
+};
+template <int I, class E> RDB_HD const E& get(const Leaf<I, E>& l) { return l.e; }
+template <int I, class E> RDB_HD E& get(Leaf<I, E>& l) { return l.e; }
+template <class... Es> RDB_HD Vec<Es...> vec(const Es&... es) { return Vec<Es...>(es...); }
+template <class V> using iseq = std::make_index_sequence<size_t(V::size)>;
+
+template <int S, class V, size_t... Is> RDB_HD auto slice_impl(const V& v, std::index_sequence<Is...>) { return vec(get<S + int(Is)>(v)...); }
+template <int S, int L, class V> RDB_HD auto slice(const V& v) { return slice_impl<S>(v, std::make_index_sequence<size_t(L)>{}); }
+
+template <class... As, class... Bs, size_t... Is, size_t... Js>
+RDB_HD auto cat_impl(const Vec<As...>& a, const Vec<Bs...>& b, std::index_sequence<Is...>, std::index_sequence<Js...>) { return vec(get<int(Is)>(a)..., get<int(Js)>(b)...); }
+template <class... As, class... Bs> RDB_HD auto cat(const Vec<As...>& a, const Vec<Bs...>& b) { return cat_impl(a, b, std::index_sequence_for<As...>{}, std::index_sequence_for<Bs...>{}); }
+template <class A, class B, class C, class... R> RDB_HD auto cat(const A& a, const B& b, const C& c, const R&... r) { return cat(cat(a, b), c, r...); }
+
+// elementwise a + s*b, a + b, s*a, a - b  (s scalar of any numeric kind)
+template <class A, class S, class B, size_t... Is> RDB_HD auto axpy_impl(const A& a, const S& s, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) + s * get<int(Is)>(b))...); }
+template <class A, class S, class B> RDB_HD auto axpy(const A& a, const S& s, const B& b) { return axpy_impl(a, s, b, iseq<A>{}); }
+template <class A, class B, size_t... Is> RDB_HD auto vadd_impl(const A& a, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) + get<int(Is)>(b))...); }
+template <class A, class B> RDB_HD auto vadd(const A& a, const B& b) { return vadd_impl(a, b, iseq<A>{}); }
+template <class A, class B, size_t... Is> RDB_HD auto vsub_impl(const A& a, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) - get<int(Is)>(b))...); }
+template <class A, class B> RDB_HD auto vsub(const A& a, const B& b) { return vsub_impl(a, b, iseq<A>{}); }
+template <class S, class A, size_t... Is> RDB_HD auto vscale_impl(const S& s, const A& a, std::index_sequence<Is...>) { return vec((s * get<int(Is)>(a))...); }
+template <class S, class A> RDB_HD auto vscale(const S& s, const A& a) { return vscale_impl(s, a, iseq<A>{}); }
+
+// 3-vector algebra on heterogeneous triples
+template <class A, class B> RDB_HD auto dot3(const A& a, const B& b) { return get<0>(a) * get<0>(b) + get<1>(a) * get<1>(b) + get<2>(a) * get<2>(b); }
+template <class A, class B> RDB_HD auto cross3(const A& a, const B& b) {
+    return vec(get<1>(a) * get<2>(b) - get<2>(a) * get<1>(b),
+               get<2>(a) * get<0>(b) - get<0>(a) * get<2>(b),
+               get<0>(a) * get<1>(b) - get<1>(a) * get<0>(b));
+}
+// y = M x for a row-major 3x3 of plain scalars
+template <class T, class A> RDB_HD auto mat3_mul(const T* M, const A& x) {
+    return vec(M[0] * get<0>(x) + M[1] * get<1>(x) + M[2] * get<2>(x),
+               M[3] * get<0>(x) + M[4] * get<1>(x) + M[5] * get<2>(x),
+               M[6] * get<0>(x) + M[7] * get<1>(x) + M[8] * get<2>(x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Seeding and extraction.
+// ---------------------------------------------------------------------------------------------
+// element I of [x;u]: a seeded dual if column I belongs to this thread's column chunk, a plain T otherwise
+template <class T, int I, mask_t CHUNK>
+RDB_HD auto seed(T z) {
+    if constexpr (chas(CHUNK, I)) { SD<T, (mask_t(1) << I)> r; r.v = z; r.d[0] = T(1); return r; }
+    else return z;
+}
+template <int J, class T> RDB_HD T partial(const T&) { return T(0); }
+template <int J, class T, mask_t M> RDB_HD T partial(const SD<T, M>& a) { return a.template part<J>(); }
+
+}  // namespace rdb

@@ -1,0 +1,76 @@
+"""Quick GPU sanity + timing sweep (development aid; not part of the test-suite)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import rdb200 as rd
+from oracle import rd_oracle as o
+
+def rand_inputs(model, N, rng, quat=True):
+    n, m = model.n, model.m
+    Z = rng.random((N, n + m))
+    if n >= 12:
+        np_ = n - 9
+        q = rng.standard_normal((N, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+        if np_ == 4: Z[:, 3:7] = q
+        else: Z[:, 3:6] = q[:, 1:] / (1 + np.abs(q[:, :1]))
+    return Z
+
+def check(name, gm, om, Q, dtype, N=5000, dt=0.01):
+    rng = np.random.default_rng(1)
+    Z = rand_inputs(gm._h, N, rng).astype(dtype)
+    Zd = torch.from_numpy(Z).cuda()
+    xn = torch.empty((N, gm._h.n), dtype=Zd.dtype, device='cuda')
+    J = gm._h.discrete_jacobian(Q, Zd, dt, xn=xn)
+    torch.cuda.synchronize()
+    Jo = o.discrete_jacobian(om, Q, Z.astype(np.float64), dt)
+    xo = o.discrete_dynamics(om, Q, Z.astype(np.float64), dt)
+    eJ = np.abs(J.cpu().numpy() - Jo).max(); ex = np.abs(xn.cpu().numpy() - xo).max()
+    # host path
+    Jh = gm._h.discrete_jacobian(Q, Z, dt)
+    eh = np.abs(Jh - Jo).max()
+    print(f"{name:28s} Q={Q} {np.dtype(dtype).name}: max|dJ|={eJ:.3e} max|dx+|={ex:.3e} host-path {eh:.3e}", flush=True)
+
+def bench(name, gm, Q, dtype, N, dt=0.01, iters=20):
+    rng = np.random.default_rng(2)
+    Z = torch.from_numpy(rand_inputs(gm._h, N, rng).astype(dtype)).cuda()
+    n, m = gm._h.n, gm._h.m
+    J = torch.empty((N, n + m, n), dtype=Z.dtype, device='cuda')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(3): gm._h.discrete_jacobian(Q, Z, dt, J=J)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gm._h.discrete_jacobian(Q, Z, dt, J=J); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = np.median(ts) * 1e-3
+    es = Z.element_size()
+    gbs = N * es * ((n + m) + n * (n + m)) / t / 1e9
+    print(f"BENCH {name:24s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    cp, cpo = rd.Cartpole(), o.cartpole()
+    qd, qdo = rd.Quadrotor(), o.quadrotor()
+    for Q in (0, 1, 2, 3):
+        check("cartpole", cp, cpo, Q, np.float64)
+    check("cartpole", cp, cpo, 3, np.float32)
+    check("cartpole ragged", cp, cpo, 3, np.float64, N=1000 + 37)
+    for Q in (0, 1, 2, 3):
+        check("quadrotor quat world", qd, qdo, Q, np.float32)
+    check("quadrotor quat world", qd, qdo, 3, np.float64)
+    check("quadrotor mrp world", rd.Quadrotor(rd.MRP), o.quadrotor(o.ROT_MRP), 3, np.float64)
+    check("quadrotor rp body", rd.Quadrotor(rd.RodriguesParam, bodyframe=True), o.quadrotor(o.ROT_RP, o.BODYFRAME), 3, np.float64)
+    check("body quat body", rd.Body(bodyframe=True), o.body(o.ROT_QUAT, o.BODYFRAME), 3, np.float64)
+    check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
+    check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
+    bench("cartpole", cp, 3, np.float64, 1 << 20)
+    bench("cartpole", cp, 3, np.float64, 1 << 23)
+    bench("cartpole", cp, 3, np.float32, 1 << 23)
+    bench("quadrotor", qd, 3, np.float32, 262144)
+    bench("quadrotor", qd, 3, np.float32, 1 << 21)
+    bench("quadrotor", qd, 3, np.float64, 262144)
+    bench("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float64, 1 << 20, dt=0.1)
+    bench("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float32, 1 << 20, dt=0.1)
