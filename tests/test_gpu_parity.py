@@ -1,0 +1,347 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI (librdb200.so via ctypes);
+the CPU oracle is only the checker.  Tolerances are the north_star's: 1e-10 (fp64) / 1e-4 (fp32) max-abs."""
+import numpy as np
+import pytest
+
+from oracle import rd_oracle as o
+from common import TOL, golden, rand_inputs, zoo
+
+pytestmark = pytest.mark.gpu
+
+QS = (o.EULER, o.RK2, o.RK3, o.RK4)
+
+
+@pytest.fixture(scope="module")
+def rd():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import rdb200
+    return rdb200
+
+
+@pytest.fixture(scope="module")
+def torch_():
+    import torch
+    return torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- every model x integrator x dtype against the oracle (device pointers, reference layout) ------------------------------
+@pytest.mark.parametrize("name", sorted(zoo()))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_discrete_jacobian_all_models(rd, torch_, name, dtype):
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    assert (gm.n, gm.m, rd.errstate_dim(gm)) == (om.n, om.m, om.nerr)
+    N = 777                                                   # several tiles + a ragged tail for every TILE in use
+    Z = rand_inputs(om.n, om.m, N, np.random.default_rng(21)).astype(dtype)
+    Z64 = Z.astype(np.float64)
+    Zd = dev(torch_, Z)
+    for Q in QS:
+        for dt in (0.01, 0.1):
+            xn = torch_.empty((N, om.n), dtype=Zd.dtype, device="cuda")
+            J = gm._h.discrete_jacobian(Q, Zd, dt, xn=xn)
+            torch_.cuda.synchronize()
+            assert np.abs(J.cpu().numpy() - o.discrete_jacobian(om, Q, Z64, dt)).max() < TOL[dtype]
+            assert np.abs(xn.cpu().numpy() - o.discrete_dynamics(om, Q, Z64, dt)).max() < TOL[dtype]
+    # continuous dynamics and Jacobian (dynamics / jacobian!)
+    xd = torch_.empty((N, om.n), dtype=Zd.dtype, device="cuda")
+    Jc = gm._h.jacobian(Zd, xdot=xd)
+    f = gm._h.dynamics(Zd)
+    xn2 = gm._h.discrete_dynamics(o.RK4, Zd, 0.05)
+    torch_.cuda.synchronize()
+    scale = max(1.0, np.abs(o.jacobian(om, Z64)).max())       # quadrotor d(wdot)/du ~ L/J ~ 76: relative for fp32
+    assert np.abs(Jc.cpu().numpy() - o.jacobian(om, Z64)).max() < TOL[dtype] * scale
+    fs = max(1.0, np.abs(o.dynamics(om, Z64)).max())
+    assert np.abs(xd.cpu().numpy() - o.dynamics(om, Z64)).max() < TOL[dtype] * fs
+    assert np.abs(f.cpu().numpy() - o.dynamics(om, Z64)).max() < TOL[dtype] * fs
+    assert np.abs(xn2.cpu().numpy() - o.discrete_dynamics(om, o.RK4, Z64, 0.05)).max() < TOL[dtype]
+
+
+# ---- layouts, pointer kinds, alignment, ragged sizes ----------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dtype", [("cartpole", np.float64), ("quad_quat_world", np.float32), ("satellite_mrp", np.float64)])
+def test_layouts_and_pointer_kinds_agree_bitwise(rd, torch_, name, dtype):
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    n, nz = om.n, om.n + om.m
+    for N in (1, 31, 64, 65, 1000, 70001):                    # 70001 > one host-pipeline chunk (65536)
+        Z = rand_inputs(om.n, om.m, N, np.random.default_rng(N)).astype(dtype)
+        dt = np.random.default_rng(N + 1).uniform(0.0, 0.1, N)
+        ref = o.discrete_jacobian(om, o.RK4, Z.astype(np.float64), dt)
+        Zd = dev(torch_, Z)
+        J_dev = gm._h.discrete_jacobian(o.RK4, Zd, dt).cpu().numpy()
+        assert np.abs(J_dev - ref).max() < TOL[dtype]
+        # host pointers (pinned pipeline inside the library)
+        xn_h = np.empty((N, n), dtype=dtype)
+        J_host = gm._h.discrete_jacobian(o.RK4, Z, dt, xn=xn_h)
+        assert np.array_equal(J_host, J_dev)
+        assert np.abs(xn_h - o.discrete_dynamics(om, o.RK4, Z.astype(np.float64), dt)).max() < TOL[dtype]
+        # component-major layout, device and host
+        Zs = np.ascontiguousarray(Z.T)
+        Js = gm._h.discrete_jacobian(o.RK4, dev(torch_, Zs), dt, layout=rd.SOA).cpu().numpy()
+        assert Js.shape == (n * nz, N) and np.array_equal(Js.T.reshape(N, nz, n), J_dev)
+        Jsh = gm._h.discrete_jacobian(o.RK4, Zs, dt, layout=rd.SOA)
+        assert np.array_equal(Jsh, Js)
+        # deliberately mis-aligned device buffers (element offset 1): cooperative-copy path instead of TMA
+        if N > 1:
+            esz = np.dtype(dtype).itemsize
+            raw = torch_.empty(N * nz + 1, dtype=Zd.dtype, device="cuda")
+            raw[1:].copy_(Zd.reshape(-1))
+            Zu = raw[1:].view(N, nz)
+            Jraw = torch_.empty(N * nz * n + 1, dtype=Zd.dtype, device="cuda")
+            Ju = Jraw[1:].view(N, nz, n)
+            assert Zu.data_ptr() % 16 == esz % 16 or esz == 16
+            gm._h.discrete_jacobian(o.RK4, Zu, dt, J=Ju)
+            assert np.array_equal(Ju.cpu().numpy(), J_dev)
+
+
+def test_empty_batch_and_argument_errors(rd, torch_):
+    gm = rd.Cartpole()
+    Z0 = np.empty((0, 5))
+    assert gm._h.discrete_jacobian(o.RK4, Z0, 0.01).shape == (0, 5, 4)
+    assert gm._h.discrete_jacobian(o.RK4, dev(torch_, Z0), 0.01).shape == (0, 5, 4)
+    with pytest.raises(ValueError):
+        gm._h.discrete_jacobian(o.RK4, np.zeros((3, 4)), 0.01)           # wrong width
+    with pytest.raises(rd.RDBError) as e:                                # host Z with device J
+        gm._h.discrete_jacobian(o.RK4, np.zeros((4, 5)), 0.01, J=torch_.empty((4, 5, 4), dtype=torch_.float64, device="cuda"))
+    assert e.value.code == rd._abi.ERR_POINTER_MIX
+    with pytest.raises(rd.RDBError):
+        gm._h.discrete_jacobian(7, np.zeros((4, 5)), 0.01)               # unknown integrator
+    with pytest.raises(TypeError):
+        gm._h.discrete_jacobian(o.RK4, np.zeros((4, 5), dtype=np.float16), 0.01)
+    with pytest.raises(rd.NotImplementedModelError):
+        rd.DoubleIntegrator(4)
+
+
+def test_terminal_knots_and_per_knot_dt(rd, torch_):
+    """dt == 0 (terminal knot point, src/knotpoint.jl:57-67) gives J = [I 0] and x+ = x."""
+    gm, om = rd.Quadrotor(), o.quadrotor()
+    N = 300
+    Z = rand_inputs(13, 4, N, np.random.default_rng(5))
+    dt = np.full(N, 0.02); dt[::7] = 0.0
+    xn = np.empty((N, 13))
+    J = gm._h.discrete_jacobian(o.RK4, Z, dt, xn=xn)
+    I0 = np.concatenate([np.eye(13), np.zeros((13, 4))], axis=1)
+    assert np.array_equal(o.as_matrix(J)[::7], np.broadcast_to(I0, (len(dt[::7]), 13, 17)))
+    assert np.array_equal(xn[::7], Z[::7, :13])
+    assert np.abs(J - o.discrete_jacobian(om, o.RK4, Z, dt)).max() < 1e-10
+
+
+def test_quadrotor_clamp_kink(rd):
+    """max(0, kf w): zero derivative when clamped and at exactly 0; yaw moment unclamped (test/quadrotor.jl:67-70,86-95)."""
+    gm, om = rd.Quadrotor(), o.quadrotor()
+    Z = rand_inputs(13, 4, 64, np.random.default_rng(6))
+    Z[:, 13] = -0.3; Z[:, 14] = 0.0
+    for dtype in (np.float64, np.float32):
+        J = gm._h.jacobian(Z.astype(dtype))
+        Jm = o.as_matrix(J)
+        assert np.all(Jm[:, 7:10, 13:15] == 0) and np.all(Jm[:, 10:12, 13:15] == 0)
+        assert np.abs(J - o.jacobian(om, Z.astype(dtype).astype(np.float64))).max() < TOL[dtype] * 100
+
+
+# ---- committed golden fixtures (BASELINE configs) ------------------------------------------------------------------------------
+def test_golden_c1_c2_cartpole(rd):
+    gm = rd.Cartpole()
+    g = golden("c1_cartpole_rk3")
+    assert np.abs(gm._h.discrete_jacobian(o.RK3, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-10
+    g = golden("c2_cartpole_rk4")
+    xn = np.empty_like(g["xn"])
+    assert np.abs(gm._h.discrete_jacobian(o.RK4, g["Z"], float(g["dt"]), xn=xn) - g["J"]).max() < 1e-10
+    assert np.abs(xn - g["xn"]).max() < 1e-10
+
+
+def test_golden_c3_quadrotor_fp32_and_liestate(rd):
+    gm = rd.Quadrotor()
+    g = golden("c3_quadrotor_rk4")
+    Z32 = g["Z"].astype(np.float32)
+    assert np.array_equal(Z32.astype(np.float64), g["Z"])           # fixture inputs are exactly representable in fp32
+    assert np.abs(gm._h.discrete_jacobian(o.RK4, Z32, float(g["dt"])) - g["J"]).max() < 1e-4
+    assert np.abs(gm._h.discrete_jacobian(o.RK4, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-10
+    X = np.ascontiguousarray(g["Z"][:, :13])
+    assert np.abs(gm._h.errstate_jacobian(g["Z"]) - g["G"]).max() < 1e-12          # ldx = n+m: states read in place
+    assert np.abs(gm._h.errstate_jacobian(X.astype(np.float32)) - g["G"]).max() < 1e-6
+    # Cayley error = vec/scalar of q0\\q: entries reach 1e2..1e3 for near-opposite random attitudes -> relative tolerance
+    assert np.abs(gm._h.state_diff(X, g["X0"]) - g["dX"]).max() < 1e-10 * max(1.0, np.abs(g["dX"]).max())
+    assert np.abs(gm._h.grad_errstate_jacobian(X, g["X0"]) - g["H"]).max() < 1e-12
+
+
+def test_golden_c4_satellite_and_c5_sweep_and_rollout(rd):
+    g = golden("c4_satellite_mrp_rk2")
+    gm = rd.Satellite(rd.MRP)
+    assert np.abs(gm._h.discrete_jacobian(o.RK2, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-10
+    assert np.abs(gm._h.discrete_jacobian(o.RK2, g["Z"].astype(np.float32), float(g["dt"])) - g["J"]).max() < 1e-4
+    assert np.abs(gm._h.errstate_jacobian(g["Z"]) - g["G"]).max() < 1e-12
+    g = golden("c5_mixed_sweep")
+    assert np.abs(rd.Cartpole()._h.discrete_jacobian(o.RK4, g["Zc"], g["dtc"]) - g["Jc"]).max() < 1e-10
+    assert np.abs(rd.Quadrotor()._h.discrete_jacobian(o.RK4, g["Zq"], g["dtq"]) - g["Jq"]).max() < 1e-10
+    g = golden("rollout_cartpole_rk4")
+    assert np.abs(rd.Cartpole()._h.rollout(o.RK4, g["x0"], g["U"], float(g["dt"])) - g["X"]).max() < 1e-10
+
+
+# ---- LieState maps and rollouts for every rotation ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["body_quat_world", "body_mrp_world", "body_rp_body", "cartpole"])
+def test_liestate_maps(rd, torch_, name):
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    rng = np.random.default_rng(31)
+    N = 1001
+    X = rand_inputs(om.n, om.m, N, rng)[:, :om.n].copy()
+    X0 = rand_inputs(om.n, om.m, N, rng)[:, :om.n].copy()
+    X[:, 3:7] *= 1.7 if om.n == 13 else 1.0                     # un-normalised quaternions: the maps normalise (Appendix A.2)
+    for dtype, tol in ((np.float64, 1e-12), (np.float32, 2e-5)):
+        Xt, X0t = X.astype(dtype), X0.astype(dtype)
+        Go, do_, Ho = o.errstate_jacobian(om, Xt.astype(np.float64)), o.state_diff(om, Xt.astype(np.float64), X0t.astype(np.float64)), \
+            o.grad_errstate_jacobian(om, Xt.astype(np.float64), X0t.astype(np.float64))
+        assert np.abs(gm._h.errstate_jacobian(Xt) - Go).max() < tol
+        assert np.abs(gm._h.errstate_jacobian(dev(torch_, Xt)).cpu().numpy() - Go).max() < tol
+        assert np.abs(gm._h.state_diff(Xt, X0t) - do_).max() < tol * max(1.0, np.abs(do_).max())
+        assert np.abs(gm._h.state_diff(dev(torch_, Xt), dev(torch_, X0t)).cpu().numpy() - do_).max() < tol * max(1.0, np.abs(do_).max())
+        assert np.abs(gm._h.grad_errstate_jacobian(Xt, X0t) - Ho).max() < tol * 10
+
+
+@pytest.mark.parametrize("name", ["cartpole", "quad_quat_world", "body_mrp_body", "di2"])
+def test_rollout(rd, torch_, name):
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    rng = np.random.default_rng(41)
+    ntraj, K = 130, 40
+    x0 = rand_inputs(om.n, om.m, ntraj, rng)[:, :om.n].copy()
+    U = rng.random((ntraj, K - 1, om.m))
+    dt = np.repeat(0.01 * (1 + np.arange(ntraj) % 4), K).reshape(ntraj, K)
+    for Q in (o.RK2, o.RK4):
+        ref = o.rollout(om, Q, x0, U, dt)
+        assert np.abs(gm._h.rollout(Q, x0, U, dt) - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+        Xd = gm._h.rollout(Q, dev(torch_, x0), dev(torch_, U), dt)
+        assert np.abs(Xd.cpu().numpy() - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+    X32 = gm._h.rollout(o.RK4, x0.astype(np.float32), U.astype(np.float32), 0.01)
+    ref = o.rollout(om, o.RK4, x0.astype(np.float32).astype(np.float64), U.astype(np.float32).astype(np.float64), 0.01)
+    assert np.abs(X32 - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
+# ---- BASELINE full sizes: size-independent properties + strided oracle sample -------------------------------------------------------
+def _full_size_check(rd, torch, gm, om, Q, N, dtype, dt, tol):
+    n, m = om.n, om.m
+    rng = np.random.default_rng(N % 1000 + n)
+    Z = rand_inputs(n, m, N, rng).astype(dtype)
+    Zd = dev(torch, Z)
+    xn = torch.empty((N, n), dtype=Zd.dtype, device="cuda")
+    J = gm._h.discrete_jacobian(Q, Zd, dt, xn=xn)
+    # (a) strided sample against the oracle
+    idx = np.arange(0, N, 997)
+    Jo = o.discrete_jacobian(om, Q, Z[idx].astype(np.float64), dt)
+    assert np.abs(J[torch.from_numpy(idx).cuda()].cpu().numpy() - Jo).max() < tol
+    # (b) directional finite difference of the GPU's own discrete_dynamics agrees with J d (fp64 arithmetic for the check)
+    Z64 = Zd.double()
+    d = torch.from_numpy(rng.standard_normal((N, n + m))).cuda()
+    eps = 1e-6
+    h64 = gm._h.discrete_dynamics
+    fd = (h64(Q, (Z64 + eps * d).contiguous(), dt) - h64(Q, (Z64 - eps * d).contiguous(), dt)) / (2 * eps)
+    Jd = torch.einsum("kji,kj->ki", J.double(), d)               # J stored (N, n+m, n)
+    assert float((fd - Jd).abs().max()) < max(tol * 20, 1e-7) * max(1.0, float(Jd.abs().max()))
+    # (c) x+ from the Jacobian call equals discrete_dynamics bit-for-bit; (d) a second call is bit-identical (no races)
+    assert torch.equal(xn, gm._h.discrete_dynamics(Q, Zd, dt))
+    assert torch.equal(J, gm._h.discrete_jacobian(Q, Zd, dt))
+    # (e) structural facts of the reference map
+    if n == 4:                                                   # cartpole: column 1 of J is e1; d x1+/d x3 = dt
+        Jm = J.transpose(1, 2)
+        assert torch.all(Jm[:, :, 0] == torch.tensor([1.0, 0, 0, 0], dtype=J.dtype, device="cuda"))
+    return J
+
+
+def test_full_size_c2_cartpole_rk4_fp64(rd, torch_):
+    _full_size_check(rd, torch_, rd.Cartpole(), o.cartpole(), o.RK4, 1 << 20, np.float64, 0.01, 1e-10)
+
+
+def test_full_size_c3_quadrotor_rk4_fp32(rd, torch_):
+    J = _full_size_check(rd, torch_, rd.Quadrotor(), o.quadrotor(), o.RK4, 262144, np.float32, 0.01, 1e-4)
+    Jm = J.transpose(1, 2)                                         # position columns are unit vectors; omega rows ignore r, q, v
+    assert torch.all(Jm[:, :, 0:3] == torch.eye(13, dtype=J.dtype, device="cuda")[:, 0:3])
+    assert torch.all(Jm[:, 10:13, 0:10] == 0)
+
+
+def test_full_size_c4_satellite_mrp_rk2(rd, torch_):
+    for dtype, tol in ((np.float64, 1e-10), (np.float32, 1e-4)):
+        _full_size_check(rd, torch_, rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), o.RK2, 1 << 20, dtype, 0.1, tol)
+
+
+def test_full_size_c5_mixed_sweep(rd, torch_):
+    """4096 trajectories x 256 knots, first half Cartpole, second half Quadrotor, per-trajectory dt; this rank's shard only
+    differs from the whole by the partition, so the single-GPU sweep checks the union of all shards."""
+    from rdb200 import sharding as sh
+    ntraj, K = 4096, 256
+    segs = {"cartpole": ntraj // 2, "quadrotor": ntraj // 2}
+    models = {"cartpole": (rd.Cartpole(), o.cartpole(), np.float64, 1e-10), "quadrotor": (rd.Quadrotor(), o.quadrotor(), np.float32, 1e-4)}
+    rng = np.random.default_rng(5)
+    for name, (gm, om, dtype, tol) in models.items():
+        Z = rand_inputs(om.n, om.m, segs[name] * K, rng).astype(dtype)
+        dt = np.repeat(0.01 * (1 + np.arange(segs[name]) % 4), K)
+        whole = gm._h.discrete_jacobian(o.RK4, dev(torch_, Z), dt)
+        parts = []
+        for r in range(8):                                       # the 8-GPU partition, evaluated shard by shard
+            lo, hi = sh.partition_segments(segs, 8, r)[name]
+            parts.append(gm._h.discrete_jacobian(o.RK4, dev(torch_, Z[lo * K:hi * K]), dt[lo * K:hi * K]))
+        assert torch_.equal(torch_.cat(parts), whole)
+        idx = np.arange(0, Z.shape[0], 1499)
+        assert np.abs(whole[torch_.from_numpy(idx).cuda()].cpu().numpy() - o.discrete_jacobian(om, o.RK4, Z[idx].astype(np.float64), dt[idx])).max() < tol
+
+
+# ---- the reference-facing API mirror ---------------------------------------------------------------------------------------------------
+def test_reference_api_single_knot_and_trajectory(rd):
+    """Mirrors test/cartpole_test.jl:48-72 and test/integration_tests.jl:7-18 through the drop-in names."""
+    model = rd.Cartpole()
+    dmodel = rd.DiscretizedDynamics(model, rd.RK4)
+    om = o.cartpole()
+    rng = np.random.default_rng(51)
+    x, u = rng.random(4), rng.random(1)
+    z = rd.KnotPoint(x, u, 0.0, 0.01)
+    zz = np.r_[x, u][None]
+    assert rd.dims(dmodel) == (4, 1, 4) and isinstance(rd.default_diffmethod(dmodel), rd.ForwardAD)
+    assert np.abs(rd.dynamics(model, z) - o.dynamics(om, zz)[0]).max() < 1e-12
+    assert np.abs(rd.dynamics(model, x, u) - o.dynamics(om, zz)[0]).max() < 1e-12
+    assert np.abs(rd.discrete_dynamics(dmodel, z) - o.discrete_dynamics(om, o.RK4, zz, 0.01)[0]).max() < 1e-12
+    assert np.abs(rd.discrete_dynamics(dmodel, x, u, 0.0, 0.01) - rd.discrete_dynamics(rd.RK4, model, z)).max() == 0
+    Jref = o.as_matrix(o.discrete_jacobian(om, o.RK4, zz, 0.01))[0]
+    for J in (np.zeros((4, 5)), rd.DynamicsJacobian(model)):
+        for sig in (rd.StaticReturn(), rd.InPlace()):
+            for diff in (rd.ForwardAD(), rd.UserDefined(), rd.B200()):
+                y = np.zeros(4)
+                assert rd.jacobian_(sig, diff, dmodel, J, y, z) is None
+                assert np.abs(np.asarray(J) - Jref).max() < 1e-10
+                assert np.abs(y - o.discrete_dynamics(om, o.RK4, zz, 0.01)[0]).max() < 1e-12
+    D = rd.DynamicsJacobian(model)
+    rd.discrete_jacobian_(rd.RK3, D, model, z)                     # v0.3 spelling
+    assert np.abs(D.A - o.as_matrix(o.discrete_jacobian(om, o.RK3, zz, 0.01))[0][:, :4]).max() < 1e-10
+    with pytest.raises(rd.NotImplementedModelError):
+        rd.jacobian_(rd.StaticReturn(), rd.FiniteDifference(), dmodel, D, None, z)
+    Jc = np.zeros((4, 5))
+    rd.jacobian_(rd.StaticReturn(), rd.UserDefined(), model, Jc, np.zeros(4), z)       # continuous Jacobian, test/integration_tests.jl:27-33
+    assert np.abs(Jc - o.as_matrix(o.jacobian(om, zz))[0]).max() < 1e-10
+    # whole trajectory in one call
+    Z = rd.SampledTrajectory(rng.random((101, 4)), rng.random((100, 1)), dt=0.02)
+    Js, ys = np.zeros((101, 5, 4)), np.zeros((101, 4))
+    rd.jacobian_(rd.StaticReturn(), rd.B200(), dmodel, Js, ys, Z)
+    assert np.abs(Js - o.discrete_jacobian(om, o.RK4, Z.data, Z.dts)).max() < 1e-10
+    assert np.array_equal(Js[-1].T, np.concatenate([np.eye(4), np.zeros((4, 1))], axis=1))       # terminal knot
+    x0 = rd.states(Z)[0].copy()
+    rd.rollout_(rd.StaticReturn(), dmodel, Z)
+    assert np.abs(rd.states(Z) - o.rollout(om, o.RK4, x0[None], rd.controls(Z)[None, :-1], Z.dts[None])[0]).max() < 1e-10
+
+
+def test_reference_api_rigid_body_liestate(rd):
+    """Mirrors test/rigid_body_jacobians.jl:55-83."""
+    model = rd.Quadrotor()
+    om = o.quadrotor()
+    rng = np.random.default_rng(52)
+    zz = rand_inputs(13, 4, 1, rng)
+    z = rd.KnotPoint(zz[0, :13], zz[0, 13:], 0.0, 0.1)
+    assert rd.errstate_dim(model) == 12 and rd.jacobian_width(model) == 16 and model.statevectortype is rd.RotationState
+    J = rd.DynamicsJacobian(model)
+    rd.jacobian_(rd.StaticReturn(), rd.ForwardAD(), rd.DiscretizedDynamics(model, rd.RK4), J, np.zeros(13), z)
+    assert np.abs(np.asarray(J) - o.as_matrix(o.discrete_jacobian(om, o.RK4, zz, 0.1))[0]).max() < 1e-10
+    G = np.zeros((13, 12))
+    rd.errstate_jacobian_(model, G, z)
+    assert np.abs(G - o.errstate_jacobian(om, zz[:, :13])[0].T).max() < 1e-12
+    x0 = rand_inputs(13, 4, 1, rng)[0, :13]
+    assert np.abs(rd.state_diff(model, zz[0, :13], x0) - o.state_diff(om, zz[:, :13], x0[None])[0]).max() < 1e-12
+    dG = np.zeros((12, 12))
+    rd.grad_errstate_jacobian_(model, dG, zz[0, :13], x0)
+    assert np.abs(dG - o.grad_errstate_jacobian(om, zz[:, :13], x0[None])[0].T).max() < 1e-12

@@ -1,0 +1,233 @@
+"""Pins the CPU oracle (test infrastructure) — runs without a GPU.
+
+The reference ships no golden vectors and Julia is unavailable, so the oracle is pinned by
+ (1) the relational assertions the reference's own tests make on this path, re-run here on the oracle;
+ (2) an independent numpy complex-step restatement (oracle/independent.py) that shares no code with it;
+ (3) the hand-verified known answers of SURVEY.md Appendix C;
+ (4) the committed fixtures in tests/golden/ (regression pin).
+"""
+import numpy as np
+import pytest
+
+from oracle import rd_oracle as o
+from oracle import independent as ind
+from common import golden, rand_inputs, zoo
+
+QS = {o.EULER: "euler", o.RK2: "rk2", o.RK3: "rk3", o.RK4: "rk4"}
+
+
+def ind_model(name):
+    if name == "cartpole":
+        return ind.Cartpole()
+    if name.startswith("di"):
+        return ind.DoubleIntegrator(int(name[2]))
+    if name == "satellite_mrp":
+        return ind.RigidBody("body", rot="mrp", mass=1.0, J=np.eye(3))
+    kind, rot, frame = name.split("_")
+    if kind == "quad":
+        return ind.RigidBody("quadrotor", rot=rot, frame=frame, mass=0.5, J=np.diag([0.0023, 0.0023, 0.004]))
+    return ind.RigidBody("body", rot=rot, frame=frame)
+
+
+# ---- (3) known answers, SURVEY.md Appendix C ------------------------------------------------------------------------
+def test_cartpole_known_answers():
+    m = o.cartpole()
+    z = np.array([[0.1, 0.2, 0.3, 0.4, 0.5]])
+    assert np.allclose(o.dynamics(m, z)[0], [0.3, 0.4, 0.8782651651833607, -5.619408939955959], atol=1e-14)
+    xn = {o.EULER: [0.103, 0.204, 0.3087826516518336, 0.3438059106004404],
+          o.RK2: [0.10304391325825918, 0.20371902955300222, 0.30881310601518436, 0.34336875420270035],
+          o.RK3: [0.10304401477280367, 0.20371757236500976, 0.308811491738707, 0.34338962242102583],
+          o.RK4: [0.10304401065773387, 0.2037176246055777, 0.3088114828472635, 0.3433897139235887]}
+    for Q, ref in xn.items():
+        assert np.allclose(o.discrete_dynamics(m, Q, z, 0.01)[0], ref, atol=1e-14)
+    J = o.as_matrix(o.discrete_jacobian(m, o.RK4, z, 0.01))[0]
+    Jref = np.array([[1, 8.6756343027589333e-05, 9.9999999999999985e-03, 1.0448126477784444e-06, 4.9597243518762175e-05],
+                     [0, 9.9888657059330599e-01, 0, 9.9948082258736765e-03, -9.7176440940498530e-05],
+                     [0, 1.7323086579775784e-02, 1, 2.3441048181776361e-04, 9.9182435944503398e-03],
+                     [0, -2.2255256446242244e-01, 0, 9.9859778390010401e-01, -1.9427409451867484e-02]])
+    assert np.abs(J - Jref).max() < 1e-13
+    inv = {o.EULER: (2.012474668101985, 3.804810437010853, 3.999690905289077),
+           o.RK2: (2.011344109181849, 3.802943360695978, 3.997482116503141),
+           o.RK3: (2.011337012474398, 3.803014784739832, 3.997483940351493),
+           o.RK4: (2.011337220498831, 3.803015151419291, 3.997484354493410)}
+    for Q, (fro, tot, tr) in inv.items():
+        J = o.as_matrix(o.discrete_jacobian(m, Q, z, 0.01))[0]
+        assert np.allclose([np.linalg.norm(J), J.sum(), np.trace(J[:, :4])], [fro, tot, tr], atol=1e-12)
+
+
+def test_quadrotor_known_answers():
+    m = o.quadrotor()
+    z = np.array([[.1, .2, .3, .8, .2, -.4, .4, .4, -.5, .6, .7, .8, -.9, 1, 1.5, 1.25, 1.75]])
+    xd = [0.4, -0.5, 0.6, 0.27, 0.3, 0.55, -0.14, -5.28, -7.04, -3.21, -18.489565217391302, 18.55608695652174, -6.125]
+    assert np.allclose(o.dynamics(m, z)[0], xd, atol=1e-13)
+    xn = [0.1037375220479742, 0.19464802561115327, 0.30584073621895413, 0.8030187350157577, 0.20250115547279274,
+          -0.394271190376744, 0.3983772355640589, 0.3476534470164253, -0.5703831897018942, 0.5682771583095719,
+          0.5159317379858185, 0.9860433879861684, -0.96125]
+    assert np.allclose(o.discrete_dynamics(m, o.RK4, z, 0.01)[0], xn, atol=1e-13)
+    J = o.as_matrix(o.discrete_jacobian(m, o.RK4, z, 0.01))[0]
+    assert np.allclose([np.linalg.norm(J), J.sum(), np.trace(J[:, :13])], [3.934201769388178, 13.31063583261720, 12.99985104390944], atol=1e-11)
+    assert np.allclose(J[12, 13:], [0.06125, -0.06125, 0.06125, -0.06125], atol=1e-14)      # km dt / J33
+    G = o.errstate_jacobian(m, z[:, :13])[0].T
+    assert np.allclose(G[3:7, 3:6], [[-.2, .4, -.4], [.8, -.4, -.4], [.4, .8, -.2], [.4, .2, .8]], atol=1e-14)
+
+
+def test_satellite_mrp_known_answers():
+    m = o.satellite(o.ROT_MRP)
+    z = np.array([[.1, .2, .3, 1 / 9, -2 / 9, 2 / 9, .4, -.5, .6, .7, .8, -.9, .1, .2, .3, .4, .5, .6]])
+    xd = [0.4, -0.5, 0.6, 0.15, 0.3388888888888889, -0.1111111111111111, -0.268, -0.024, 0.26, 0.4, 0.5, 0.6]
+    assert np.allclose(o.dynamics(m, z)[0], xd, atol=1e-14)
+    xn = [0.13866, 0.14988, 0.3613, 0.1256306537615741, -0.18796870972222224, 0.2120468998842593, 0.37508276490760817,
+          -0.5024963801754104, 0.6278010697882347, 0.74, 0.85, -0.84]
+    assert np.allclose(o.discrete_dynamics(m, o.RK2, z, 0.1)[0], xn, atol=1e-13)
+    J = o.as_matrix(o.discrete_jacobian(m, o.RK2, z, 0.1))[0]
+    assert np.allclose([np.linalg.norm(J), J.sum(), np.trace(J[:, :12])], [3.471030047880510, 12.80119860912479, 11.95425437702546], atol=1e-11)
+
+
+# ---- (1) the reference's relational assertions ----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(zoo()))
+def test_forward_ad_equals_chain_rule(name):
+    """test/integration_tests.jl:7-18: all sig x diff paths agree to atol 1e-10."""
+    m = zoo()[name][0]()
+    Z = rand_inputs(m.n, m.m, 64, np.random.default_rng(7))
+    for Q in QS:
+        for dt in (0.01, 0.1):
+            a = o.discrete_jacobian(m, Q, Z, dt, method=o.AD)
+            b = o.discrete_jacobian(m, Q, Z, dt, method=o.CHAIN)
+            assert np.abs(a - b).max() < 1e-11
+    assert np.abs(o.jacobian(m, Z, method=o.AD) - o.jacobian(m, Z, method=o.CHAIN)).max() < 1e-11   # :27-33
+
+
+def test_rk_stage_formulas():
+    """test/integration_tests.jl:35-38,47-59,80-99 — steps equal the hand-written stage formulas."""
+    for name in ("cartpole", "quad_quat_world", "body_mrp_body"):
+        m = zoo()[name][0]()
+        Z = rand_inputs(m.n, m.m, 16, np.random.default_rng(8))
+        x, u, h = Z[:, :m.n], Z[:, m.n:], 0.05
+        f = lambda xx: o.dynamics(m, np.concatenate([xx, u], axis=1))
+        k1 = f(x) * h
+        assert np.abs(o.discrete_dynamics(m, o.EULER, Z, h) - (x + k1)).max() < 1e-14
+        k2 = f(x + k1 / 2) * h
+        assert np.abs(o.discrete_dynamics(m, o.RK2, Z, h) - (x + k2)).max() < 1e-14
+        k3 = f(x - k1 + 2 * k2) * h
+        assert np.abs(o.discrete_dynamics(m, o.RK3, Z, h) - (x + (k1 + 4 * k2 + k3) / 6)).max() < 1e-14
+        k3 = f(x + k2 / 2) * h
+        k4 = f(x + k3) * h
+        assert np.abs(o.discrete_dynamics(m, o.RK4, Z, h) - (x + (k1 + 2 * k2 + 2 * k3 + k4) / 6)).max() < 1e-14
+
+
+def test_rk2_linear_known_answer():
+    """test/old_tests/linear_tests.jl:135-145 (disabled v0.3 test): A = I + A_(I + A_ dt/2) dt, B = (A_ B_ dt/2 + B_) dt."""
+    D, dt = 2, 0.1
+    m = o.double_integrator(D)
+    A_ = np.block([[np.zeros((D, D)), np.eye(D)], [np.zeros((D, 2 * D))]])
+    B_ = np.vstack([np.zeros((D, D)), np.eye(D)])
+    J = o.as_matrix(o.discrete_jacobian(m, o.RK2, np.random.default_rng(0).random((1, 3 * D)), dt))[0]
+    assert np.allclose(J[:, :2 * D], np.eye(2 * D) + A_ @ (np.eye(2 * D) + A_ * dt / 2) * dt, atol=1e-15)
+    assert np.allclose(J[:, 2 * D:], (A_ @ B_ * dt / 2 + B_) * dt, atol=1e-15)
+
+
+def test_rigid_body_first_principles():
+    """test/rigidbody_test.jl:135-162: xdot re-derived from Newton-Euler with rotation matrices."""
+    rng = np.random.default_rng(9)
+    for frame in (o.WORLD, o.BODYFRAME):
+        m = o.body(o.ROT_QUAT, frame)
+        Z = rand_inputs(13, 6, 8, rng)
+        xd = o.dynamics(m, Z)
+        for k in range(8):
+            r, q, v, w, u = Z[k, :3], Z[k, 3:7], Z[k, 7:10], Z[k, 10:13], Z[k, 13:]
+            R = ind.quat_matrix(q)           # unit q -> rotation matrix
+            assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+            F, tau, J = R @ u[:3], u[3:], np.diag([2.0, 3.0, 1.0])
+            assert np.allclose(xd[k, 3:7], 0.5 * ind.lmult(q) @ np.r_[0, w], atol=1e-13)
+            assert np.allclose(xd[k, 10:], np.linalg.solve(J, tau - np.cross(w, J @ w)), atol=1e-13)
+            if frame == o.WORLD:
+                assert np.allclose(xd[k, :3], v) and np.allclose(xd[k, 7:10], F / 2.0, atol=1e-13)
+            else:
+                assert np.allclose(xd[k, :3], R @ v, atol=1e-13)
+                assert np.allclose(xd[k, 7:10], R.T @ (F / 2.0) - np.cross(w, v), atol=1e-13)
+
+
+def test_errstate_structure_and_state_diff():
+    """test/liestate.jl:73-99, test/rigid_body_jacobians.jl:64-83: G = cat(I3, ∇differential(q), I6); state_diff = ⊖."""
+    rng = np.random.default_rng(10)
+    for rn, rc in (("quat", o.ROT_QUAT), ("mrp", o.ROT_MRP), ("rp", o.ROT_RP)):
+        m = o.body(rc)
+        Z = rand_inputs(m.n, m.m, 8, rng)
+        X, X0 = Z[:, :m.n], rand_inputs(m.n, m.m, 8, rng)[:, :m.n]
+        G = o.errstate_jacobian(m, X)
+        d = o.state_diff(m, X, X0)
+        for k in range(8):
+            assert np.allclose(G[k].T, ind.errstate_jacobian(rn, X[k]), atol=1e-14)
+            assert np.allclose(d[k], ind.state_diff(rn, X[k], X0[k]), atol=1e-13)
+        assert np.abs(o.state_diff(m, X, X)).max() < 1e-15
+    m = o.cartpole()                                   # Euclidean: G = I, dx = x - x0 (src/statevectortype.jl:144-155)
+    X = rng.random((4, 4))
+    assert np.allclose(o.errstate_jacobian(m, X), np.eye(4)[None])
+    assert np.allclose(o.state_diff(m, X, X[::-1]), X - X[::-1])
+
+
+def test_grad_errstate_is_derivative_of_Gt_b():
+    """∇errstate_jacobian = d/dδ [G(x ⊕ δ)ᵀ b] at δ = 0, checked by central differences through the oracle's own G."""
+    rng = np.random.default_rng(11)
+    m = o.body(o.ROT_QUAT)
+    X = rand_inputs(13, 6, 4, rng)[:, :13]
+    B = rng.random((4, 13))
+    H = o.grad_errstate_jacobian(m, X, B)
+    for k in range(4):
+        q = X[k, 3:7]
+        assert np.allclose(H[k].T[3:6, 3:6], -(q @ B[k, 3:7]) * np.eye(3), atol=1e-13)      # -(q.b) I3, test/liestate.jl:96-99
+        assert np.abs(H[k]).sum() - np.abs(H[k].T[3:6, 3:6]).sum() < 1e-15
+
+
+# ---- (2) independent complex-step restatement -------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(zoo()))
+def test_oracle_vs_independent_complex_step(name):
+    m = zoo()[name][0]()
+    im = ind_model(name)
+    Z = rand_inputs(m.n, m.m, 6, np.random.default_rng(12))
+    for Q, qn in QS.items():
+        J = o.as_matrix(o.discrete_jacobian(m, Q, Z, 0.05))
+        xn = o.discrete_dynamics(m, Q, Z, 0.05)
+        for k in range(Z.shape[0]):
+            assert np.abs(J[k] - ind.discrete_jacobian(im, qn, Z[k], 0.05)).max() < 1e-11
+            assert np.abs(xn[k] - np.real(ind.step(im, qn, Z[k, :m.n], Z[k, m.n:], 0.05))).max() < 1e-13
+    Jc = o.as_matrix(o.jacobian(m, Z))
+    for k in range(Z.shape[0]):
+        assert np.abs(Jc[k] - ind.continuous_jacobian(im, Z[k])).max() < 1e-11
+
+
+def test_quadrotor_thrust_clamp_derivative():
+    """max(0, kf w): zero derivative when clamped or exactly 0 (test/quadrotor.jl:67-70);
+    the yaw moment km*w is NOT clamped."""
+    m = o.quadrotor()
+    z = rand_inputs(13, 4, 1, np.random.default_rng(13))
+    z[0, 13:] = [-0.5, 0.0, 0.7, 0.9]
+    J = o.as_matrix(o.jacobian(m, z))[0]
+    assert np.all(J[7:10, 13] == 0) and np.all(J[7:10, 14] == 0) and np.any(J[7:10, 15] != 0)
+    assert np.allclose(J[12, 13:], np.array([1, -1, 1, -1]) * 0.0245 / 0.004)
+
+
+def test_terminal_knot_is_identity():
+    m = o.cartpole()
+    J = o.as_matrix(o.discrete_jacobian(m, o.RK4, np.random.default_rng(0).random((3, 5)), 0.0))
+    assert np.allclose(J, np.concatenate([np.eye(4), np.zeros((4, 1))], axis=1)[None])
+
+
+# ---- (4) committed fixtures -----------------------------------------------------------------------------------------------------
+def test_golden_fixtures_reproduce():
+    g = golden("c1_cartpole_rk3")
+    assert np.abs(o.discrete_jacobian(o.cartpole(), o.RK3, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-13
+    g = golden("c2_cartpole_rk4")
+    assert np.abs(o.discrete_jacobian(o.cartpole(), o.RK4, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-13
+    g = golden("c3_quadrotor_rk4")
+    m = o.quadrotor()
+    assert np.abs(o.discrete_jacobian(m, o.RK4, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-13
+    assert np.abs(o.errstate_jacobian(m, g["Z"][:, :13]) - g["G"]).max() < 1e-14
+    assert np.abs(o.state_diff(m, g["Z"][:, :13], g["X0"]) - g["dX"]).max() < 1e-13
+    g = golden("c4_satellite_mrp_rk2")
+    assert np.abs(o.discrete_jacobian(o.satellite(o.ROT_MRP), o.RK2, g["Z"], float(g["dt"])) - g["J"]).max() < 1e-13
+    g = golden("c5_mixed_sweep")
+    assert np.abs(o.discrete_jacobian(o.cartpole(), o.RK4, g["Zc"], g["dtc"]) - g["Jc"]).max() < 1e-13
+    assert np.abs(o.discrete_jacobian(m, o.RK4, g["Zq"], g["dtq"]) - g["Jq"]).max() < 1e-13
+    g = golden("rollout_cartpole_rk4")
+    assert np.abs(o.rollout(o.cartpole(), o.RK4, g["x0"], g["U"], float(g["dt"])) - g["X"]).max() < 1e-13
