@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librdb200.so")
+LIB_PATH = os.environ.get("RDB200_LIB") or os.path.join(_PKG, "librdb200.so")   # RDB200_LIB: tuning builds (scripts/tune.py)
 
 F32, F64 = 0, 1
 AOS, SOA = 0, 1

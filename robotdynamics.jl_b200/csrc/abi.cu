@@ -28,6 +28,7 @@ struct Slot {
 struct rdb_context {
     int device = 0;
     int sm_count = 0;
+    int pdl = 1;     // programmatic dependent launch of the knot kernels (RDB200_PDL=0 disables)
     Slot slot[NSLOT];
     std::mutex mu;   // the staging slots are shared by all host-pointer calls on this context
 };
@@ -124,7 +125,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
     r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.params = M->p;
-    r.dt0 = dt0; r.layout = layout; r.dev = DeviceInfo{c->device, c->sm_count};
+    r.dt0 = dt0; r.layout = layout; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.Z = Z; r.dt = dt; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
         return fn(&r);
@@ -199,6 +200,7 @@ int rdb_create(int device, rdb_context** ctx) {
     if (!c) return RDB_ERR_ARG;
     c->device = device;
     RDB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = std::getenv("RDB200_PDL")) c->pdl = (e[0] != '0');
     for (auto& s : c->slot) RDB_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     *ctx = c;
     return 0;
@@ -371,7 +373,7 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
     r.op = OP_ROLLOUT; r.Q = Q; r.dtype = dtype; r.params = M->p; r.dt0 = dt0; r.ntraj = ntraj; r.K = K;
-    r.dev = DeviceInfo{c->device, c->sm_count};
+    r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.x0 = x0; r.U = U; r.dt = dt; r.X = X; r.stream = (cudaStream_t)stream;
         return fn(&r);

@@ -95,11 +95,11 @@ __device__ __forceinline__ void images_free_barrier(int tid) {
 }
 
 // One role: evaluate the map for one knot with partials for the columns in CHUNK; write this role's share.
-template <class Model, int Q, class T, bool WITH_J, mask_t CHUNK, bool WRITE_OUT, int NTHR>
+template <class Model, int Q, class T, bool WITH_J, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL>
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
     auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, std::make_index_sequence<size_t(NZ)>{});
-    auto xn = integrate<Q, T>(model, slice<0, n>(zz), slice<n, m>(zz), h);
+    auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
     images_free_barrier<NTHR>(tid);
     if constexpr (WITH_J) put_cols<n, CHUNK>(xn, jrow, std::make_index_sequence<size_t(NZ)>{});
     if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
@@ -109,13 +109,13 @@ template <int R, class L> struct list_at;
 template <int R, mask_t M0, mask_t... Ms> struct list_at<R, MaskList<M0, Ms...>> { static constexpr mask_t value = list_at<R - 1, MaskList<Ms...>>::value; };
 template <mask_t M0, mask_t... Ms> struct list_at<0, MaskList<M0, Ms...>> { static constexpr mask_t value = M0; };
 
-template <class Model, int Q, class T, bool WITH_J, class Chunks, int NTHR, int R = 0>
+template <class Model, int Q, class T, bool WITH_J, class Chunks, int NTHR, int ROLL, int R = 0>
 __device__ __forceinline__ void dispatch_role(int role, const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     if constexpr (R + 1 == Chunks::count) {
-        role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR>(model, zrow, h, jrow, orow, tid);
+        role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR, ROLL>(model, zrow, h, jrow, orow, tid);
     } else {
-        if (role == R) role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR>(model, zrow, h, jrow, orow, tid);
-        else dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR, R + 1>(role, model, zrow, h, jrow, orow, tid);
+        if (role == R) role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR, ROLL>(model, zrow, h, jrow, orow, tid);
+        else dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR, ROLL, R + 1>(role, model, zrow, h, jrow, orow, tid);
     }
 }
 
@@ -156,7 +156,7 @@ struct KnotSmem {
     static constexpr size_t total = off_bar + 16;
 };
 
-template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB>
+template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL>
 __global__ void __launch_bounds__(TILE * Chunks::count, MINB)
 knot_kernel(const Model model, const KnotArgs<T> a) {
     constexpr int n = Model::n, NZ = Model::n + Model::m, E = n * NZ;
@@ -182,6 +182,10 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
 
     if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
     __syncthreads();
+    // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; nothing
+    // below (first global access) may start before that kernel's memory is visible.  No-ops without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     long long tile = blockIdx.x;
     if (tile < ntiles && tile_tma(tile) && tid == 0) {
@@ -210,7 +214,7 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
         (void)cnt;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
-        dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR>(role, model, zrow, h, j_img + kt * E, want_o ? o_img + kt * n : nullptr, tid);
+        dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR, ROLL>(role, model, zrow, h, j_img + kt * E, want_o ? o_img + kt * n : nullptr, tid);
         // (5) publish
         if (tma) {
             fence_proxy_async();

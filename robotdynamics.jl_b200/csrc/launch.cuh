@@ -13,39 +13,113 @@ template <int NZ, int CPR, size_t... Rs> struct gen_chunks<NZ, CPR, std::index_s
 template <int NZ, int CPR> using uniform_chunks = typename gen_chunks<NZ, CPR, std::make_index_sequence<size_t((NZ + CPR - 1) / CPR)>>::type;
 
 // ---- tiling configuration ---------------------------------------------------------------------------------------
-// TILE  knots per CTA tile (multiple of 32);  Chunks  column chunks = roles;  MINB  CTAs/SM promised to ptxas.
-template <class Model, class T, bool WITH_J, class Enable = void>
-struct KnotConfig {   // small models (Cartpole, double integrators) and every value-only kernel: one role
-    static constexpr int TILE = 128, MINB = (sizeof(T) == 8 ? 3 : 4);
+// TILE   knots per CTA tile (multiple of 32)
+// Chunks column chunks = roles (one warp-uniform code path each)
+// MINB   CTAs/SM promised to ptxas (register cap = 65536 / (threads * MINB))
+// ROLL   RK4 stage loop: 0 fully unrolled, 1 stage 1 sparse + stages 2..4 rolled, 2 all four rolled (integrators.cuh)
+// Tuning overrides for experiments (scripts/tune.py): -DRDB_TUNE_TILE / _MINB / _ROLL / _C0.._C8 (chunk masks) apply to the
+// Jacobian kernels of the unit being compiled.
+template <class Model, class T, bool WITH_J, int Q, class Enable = void>
+struct KnotConfigDefault {   // small models (Cartpole, double integrators) and every value-only kernel: one role
+    static constexpr int TILE = 128, MINB = 4, ROLL = 0;
     using Chunks = MaskList<WITH_J ? range_mask(0, Model::n + Model::m) : mask_t(0)>;
 };
-// rigid bodies with Jacobians, fp32
-template <class Model>
-struct KnotConfig<Model, float, true, std::enable_if_t<(Model::n >= 12)>> {
-    static constexpr int NZ = Model::n + Model::m;
-    static constexpr int TILE = 64, MINB = 2;
-    using Chunks = std::conditional_t<NZ == 17, MaskList<0x7Fu, 0x1F80u, 0x1E000u>,            // {r,q} {v,w} {u}
-                   std::conditional_t<NZ == 16, MaskList<0x3Fu, 0xFC0u, 0xF000u>,             // {r,p} {v,w} {u}
-                   std::conditional_t<NZ == 19, MaskList<0x7Fu, 0x1F80u, 0xE000u, 0x70000u>,  // {r,q} {v,w} {u0-2} {u3-5}
-                                                MaskList<0x3Fu, 0xFC0u, 0x7000u, 0x38000u>>>>; // NZ == 18
+// Rigid bodies with Jacobians.  Measured on B200 (profiles/tuning_r01.md): few wide roles beat many narrow ones (every role
+// recomputes the stage values), as long as the role's live partials fit the register file; RK4 is rolled (ROLL=1).
+template <class Model, int Q>
+struct KnotConfigDefault<Model, float, true, Q, std::enable_if_t<(Model::n >= 12)>> {
+    static constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    static constexpr bool heavy = (Q == Q_RK3 || Q == Q_RK4);
+    static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
+    static constexpr int TILE = (heavy && m == 4) ? 128 : 64;
+    static constexpr int MINB = (heavy && m == 4) ? 1 : 2;
+    using Heavy = std::conditional_t<m == 4, MaskList<range_mask(0, n - 1), range_mask(n - 1, NZ)>,                    // {r,att,v,w0,w1} {w2,u}
+                                              MaskList<range_mask(0, n - 3), range_mask(n - 3, n + 2), range_mask(n + 2, NZ)>>;  // {r,att,v} {w,u0,u1} {u2..u5}
+    using Light = std::conditional_t<m == 4, MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, NZ)>,            // {r,att} {v,w} {u}
+                                              MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + 3), range_mask(n + 3, NZ)>>;
+    using Chunks = std::conditional_t<heavy, Heavy, Light>;
 };
-// rigid bodies with Jacobians, fp64 (twice the registers per value: narrower chunks)
-template <class Model>
-struct KnotConfig<Model, double, true, std::enable_if_t<(Model::n >= 12)>> {
-    static constexpr int NZ = Model::n + Model::m;
-    static constexpr int TILE = 32, MINB = 1;
-    using Chunks = uniform_chunks<NZ, 3>;
+// fp64: twice the registers per value -> narrower roles for the long RK3/RK4 chains
+template <class Model, int Q>
+struct KnotConfigDefault<Model, double, true, Q, std::enable_if_t<(Model::n >= 12)>> {
+    static constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    static constexpr bool heavy = (Q == Q_RK3 || Q == Q_RK4);
+    static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
+    static constexpr int TILE = 64;
+    static constexpr int MINB = heavy ? 1 : 2;
+    using Heavy = MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + m / 2), range_mask(n + m / 2, NZ)>;   // {r,att} {v,w} {u lo} {u hi}
+    using Light = MaskList<range_mask(0, NZ / 2), range_mask(NZ / 2, NZ)>;
+    using Chunks = std::conditional_t<heavy, Heavy, Light>;
 };
 
-struct DeviceInfo { int device; int sm_count; };
+template <class Model, class T, bool WITH_J, int Q>
+struct KnotConfig : KnotConfigDefault<Model, T, WITH_J, Q> {};
+
+template <mask_t... Acc> struct nz_build {
+    template <mask_t M> using add = std::conditional_t<M != 0, nz_build<Acc..., M>, nz_build<Acc...>>;
+    using type = MaskList<Acc...>;
+};
+#ifndef RDB_TUNE_C1
+#define RDB_TUNE_C1 0
+#endif
+#ifndef RDB_TUNE_C2
+#define RDB_TUNE_C2 0
+#endif
+#ifndef RDB_TUNE_C3
+#define RDB_TUNE_C3 0
+#endif
+#ifndef RDB_TUNE_C4
+#define RDB_TUNE_C4 0
+#endif
+#ifndef RDB_TUNE_C5
+#define RDB_TUNE_C5 0
+#endif
+#ifndef RDB_TUNE_C6
+#define RDB_TUNE_C6 0
+#endif
+#ifndef RDB_TUNE_C7
+#define RDB_TUNE_C7 0
+#endif
+#ifndef RDB_TUNE_C8
+#define RDB_TUNE_C8 0
+#endif
+#if defined(RDB_TUNE_TILE) || defined(RDB_TUNE_MINB) || defined(RDB_TUNE_ROLL) || defined(RDB_TUNE_C0)
+template <class Model, class T, int Q>
+struct KnotConfig<Model, T, true, Q> {
+    using D = KnotConfigDefault<Model, T, true, Q>;
+#ifdef RDB_TUNE_TILE
+    static constexpr int TILE = RDB_TUNE_TILE;
+#else
+    static constexpr int TILE = D::TILE;
+#endif
+#ifdef RDB_TUNE_MINB
+    static constexpr int MINB = RDB_TUNE_MINB;
+#else
+    static constexpr int MINB = D::MINB;
+#endif
+#ifdef RDB_TUNE_ROLL
+    static constexpr int ROLL = RDB_TUNE_ROLL;
+#else
+    static constexpr int ROLL = D::ROLL;
+#endif
+#ifdef RDB_TUNE_C0
+    using Chunks = typename nz_build<>::add<RDB_TUNE_C0>::add<RDB_TUNE_C1>::add<RDB_TUNE_C2>::add<RDB_TUNE_C3>::add<RDB_TUNE_C4>
+        ::add<RDB_TUNE_C5>::add<RDB_TUNE_C6>::add<RDB_TUNE_C7>::add<RDB_TUNE_C8>::type;
+#else
+    using Chunks = typename D::Chunks;
+#endif
+};
+#endif
+
+struct DeviceInfo { int device; int sm_count; int pdl; };   // pdl: launch with programmatic stream serialization
 
 template <class Model, int Q, class T, bool WITH_J>
 struct KnotLaunch {
-    using Cfg = KnotConfig<Model, T, WITH_J>;
+    using Cfg = KnotConfig<Model, T, WITH_J, Q>;
     using S = KnotSmem<Model, Cfg::TILE, WITH_J, T>;
     static constexpr int NTHR = Cfg::TILE * Cfg::Chunks::count;
     static int run(const Model& model, const KnotArgs<T>& a, const DeviceInfo& dev, cudaStream_t st) {
-        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB>;
+        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL>;
         static int occ_cache[64];   // CTAs/SM per device id; 0 = not yet configured on that device
         const int d = dev.device & 63;
         if (occ_cache[d] == 0) {
@@ -60,8 +134,13 @@ struct KnotLaunch {
         const long long ntiles = (a.N + Cfg::TILE - 1) / Cfg::TILE;
         const long long cap = (long long)dev.sm_count * occ_cache[d];
         const unsigned grid = unsigned(ntiles < cap ? ntiles : cap);
-        kern<<<grid, NTHR, S::total, st>>>(model, a);
-        return int(cudaGetLastError());
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = S::total; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = dev.pdl ? 1 : 0;
+        return int(cudaLaunchKernelEx(&cfg, kern, model, a));
     }
 };
 

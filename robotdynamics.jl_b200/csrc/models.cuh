@@ -109,11 +109,12 @@ template <class T, int ROT, class P, class W>
 RDB_HD auto rot_kinematics(const P& p, const W& w) {
     if constexpr (ROT == ROT_QUAT) {   // 1/2 q (x) [0; w], bilinear, no normalisation (reference: test/liemodel.jl:13-20)
         const auto& qw = get<0>(p); const auto& qx = get<1>(p); const auto& qy = get<2>(p); const auto& qz = get<3>(p);
-        const auto& w0 = get<0>(w); const auto& w1 = get<1>(w); const auto& w2 = get<2>(w);
-        return vec(T(-0.5) * (qx * w0 + qy * w1 + qz * w2),
-                   T(0.5) * (qw * w0 + qy * w2 - qz * w1),
-                   T(0.5) * (qw * w1 + qz * w0 - qx * w2),
-                   T(0.5) * (qw * w2 + qx * w1 - qy * w0));
+        // the factor 1/2 is applied to w once (3 scalars) rather than to the 4 results (exact: a power of two)
+        auto w0 = T(0.5) * get<0>(w); auto w1 = T(0.5) * get<1>(w); auto w2 = T(0.5) * get<2>(w);
+        return vec(-(qx * w0 + qy * w1 + qz * w2),
+                   qw * w0 + qy * w2 - qz * w1,
+                   qw * w1 + qz * w0 - qx * w2,
+                   qw * w2 + qx * w1 - qy * w0);
     } else {
         auto pw = dot3(p, w);
         auto c = cross3(p, w);
@@ -130,6 +131,9 @@ RDB_HD auto rot_kinematics(const P& p, const W& w) {
     }
 }
 
+// y = diag(d) x
+template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) { return vec(d0 * get<0>(x), d1 * get<1>(x), d2 * get<2>(x)); }
+
 // ------------------------------------------------------------------------------------------------
 // RigidBody{R} with the Quadrotor or Body/Satellite wrench
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +141,17 @@ template <class T, int KIND, int ROT, int FRAME>
 struct RigidBody {
     static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
     static constexpr int n = 9 + np, m = (KIND == KIND_QUADROTOR) ? 4 : 6, nerr = 12, rot = ROT;
+    // The reference Quadrotor stores its inertia as Diagonal{Float64} (test/quadrotor.jl:25-26): only the diagonal exists.
+    // Body/Satellite carry a full SMatrix{3,3} (test/rigidbody_test.jl:24, examples/single_satellite.jl:9).
+    static constexpr bool diag_inertia = (KIND == KIND_QUADROTOR);
     ModelParams<T> p;
+
+    template <class W> RDB_HD auto inertia_mul(const W& w) const {
+        if constexpr (diag_inertia) return diag3_mul(p.J[0], p.J[4], p.J[8], w); else return mat3_mul(p.J, w);
+    }
+    template <class W> RDB_HD auto inertia_inv_mul(const W& w) const {
+        if constexpr (diag_inertia) return diag3_mul(p.Jinv[0], p.Jinv[4], p.Jinv[8], w); else return mat3_mul(p.Jinv, w);
+    }
 
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const {
@@ -146,34 +160,36 @@ struct RigidBody {
         auto w = slice<6 + np, 3>(x);
         auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised)
 
-        // wrench: F in the world frame, tau in the body frame
+        // wrench: F/m in the world frame (the 1/m of vdot = F/m is folded into the few scalars that build F, instead of
+        // scaling every partial of the rotated vector), tau in the body frame
         auto wrench = [&]() {
             if constexpr (KIND == KIND_QUADROTOR) {
                 auto F1 = relu_(p.kf * get<0>(u));
                 auto F2 = relu_(p.kf * get<1>(u));
                 auto F3 = relu_(p.kf * get<2>(u));
                 auto F4 = relu_(p.kf * get<3>(u));
-                auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, F1 + F2 + F3 + F4));
-                auto F = vec(p.mg[0] + get<0>(qF), p.mg[1] + get<1>(qF), p.mg[2] + get<2>(qF));
+                auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, p.inv_mass * (F1 + F2 + F3 + F4)));
+                const T g0 = p.mg[0] * p.inv_mass, g1 = p.mg[1] * p.inv_mass, g2 = p.mg[2] * p.inv_mass;
+                auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
                                p.km * (get<0>(u) - get<1>(u) + get<2>(u) - get<3>(u)));
-                return cat(F, tau);
+                return cat(Fm, tau);
             } else {
-                return cat(quat_rotate<T>(q, slice<0, 3>(u)), slice<3, 3>(u));
+                return cat(quat_rotate<T>(q, vscale(p.inv_mass, slice<0, 3>(u))), slice<3, 3>(u));
             }
         };
         auto xi = wrench();
-        auto F = slice<0, 3>(xi);
+        auto Fm = slice<0, 3>(xi);
         auto tau = slice<3, 3>(xi);
 
         auto qdot = rot_kinematics<T, ROT>(att, w);
         // omega_dot = Jinv (tau - w x (J w))
-        auto wdot = mat3_mul(p.Jinv, vsub(tau, cross3(w, mat3_mul(p.J, w))));
+        auto wdot = inertia_inv_mul(vsub(tau, cross3(w, inertia_mul(w))));
         if constexpr (FRAME == FRAME_WORLD) {
-            return cat(v, qdot, vscale(p.inv_mass, F), wdot);
+            return cat(v, qdot, Fm, wdot);
         } else {
             auto rdot = quat_rotate<T>(q, v);
-            auto vdot = vsub(quat_rotate<T>(quat_conj(q), vscale(p.inv_mass, F)), cross3(w, v));
+            auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3(w, v));
             return cat(rdot, qdot, vdot, wdot);
         }
     }

@@ -229,4 +229,37 @@ RDB_HD auto seed(T z) {
 template <int J, class T> RDB_HD T partial(const T&) { return T(0); }
 template <int J, class T, mask_t M> RDB_HD T partial(const SD<T, M>& a) { return a.template part<J>(); }
 
+// ---------------------------------------------------------------------------------------------
+// Widening: re-type an element / vector to a superset mask (new partials are explicit zeros), so that a rolled
+// loop over integrator stages can carry ONE type (see integrators.cuh: saturated stage types).
+// ---------------------------------------------------------------------------------------------
+template <class To> struct widen_to;
+template <class T> struct widen_to {   // plain target
+    RDB_HD static T from(const T& a) { return a; }
+};
+template <class T, mask_t B> struct widen_to<SD<T, B>> {
+    RDB_HD static SD<T, B> from(const T& a) { SD<T, B> r; r.v = a; for (int i = 0; i < cpopc(B); ++i) r.d[i] = T(0); return r; }
+    template <mask_t A, int J = 0>
+    RDB_HD static void fill(SD<T, B>& r, const SD<T, A>& a) {
+        if constexpr ((B >> J) != 0) {
+            if constexpr (chas(B, J)) { if constexpr (chas(A, J)) r.d[cslot(B, J)] = a.d[cslot(A, J)]; else r.d[cslot(B, J)] = T(0); }
+            fill<A, J + 1>(r, a);
+        }
+    }
+    template <mask_t A> RDB_HD static SD<T, B> from(const SD<T, A>& a) {
+        static_assert((A & ~B) == 0, "widen: target mask must contain the source mask");
+        SD<T, B> r; r.v = a.v; fill<A>(r, a); return r;
+    }
+};
+template <class To, class From, size_t... Is>
+RDB_HD To widen_vec_impl(const From& a, std::index_sequence<Is...>) {
+    return To(widen_to<std::remove_cv_t<std::remove_reference_t<decltype(get<int(Is)>(std::declval<const To&>()))>>>::from(get<int(Is)>(a))...);
+}
+template <class To, class From> RDB_HD To widen_vec(const From& a) { return widen_vec_impl<To>(a, iseq<To>{}); }
+template <class To, class T, size_t... Is>
+RDB_HD To zero_vec_impl(std::index_sequence<Is...>) {
+    return To(widen_to<std::remove_cv_t<std::remove_reference_t<decltype(get<int(Is)>(std::declval<const To&>()))>>>::from(T(0))...);
+}
+template <class To, class T> RDB_HD To zero_vec() { return zero_vec_impl<To, T>(iseq<To>{}); }
+
 }  // namespace rdb

@@ -68,9 +68,17 @@ if __name__ == "__main__":
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
     bench("cartpole", cp, 3, np.float64, 1 << 20)
     bench("cartpole", cp, 3, np.float64, 1 << 23)
-    bench("cartpole", cp, 3, np.float32, 1 << 23)
+    bench("cartpole", cp, 3, np.float32, 1 << 22)
+    bench("cartpole rk3", cp, 2, np.float64, 1 << 20)
     bench("quadrotor", qd, 3, np.float32, 262144)
     bench("quadrotor", qd, 3, np.float32, 1 << 21)
     bench("quadrotor", qd, 3, np.float64, 262144)
+    bench("quadrotor rk3", qd, 2, np.float32, 262144)
+    bench("quadrotor rk2", qd, 1, np.float32, 262144)
+    bench("quadrotor mrp", rd.Quadrotor(rd.MRP), 3, np.float32, 262144)
+    bench("quadrotor body-frame", rd.Quadrotor(bodyframe=True), 3, np.float32, 262144)
+    bench("body quat", rd.Body(), 3, np.float32, 262144)
+    bench("body quat", rd.Body(), 3, np.float64, 262144)
     bench("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float64, 1 << 20, dt=0.1)
     bench("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float32, 1 << 20, dt=0.1)
+    bench("satellite mrp rk4", rd.Satellite(rd.MRP), 3, np.float64, 1 << 18, dt=0.1)

@@ -1,0 +1,162 @@
+"""Tuning harness (development aid): build variants of ONE unit with different tiling / role / roll settings into small
+libraries (tune_libs/, git-ignored), then time them on the GPU.
+
+    python scripts/tune.py build  <workload>      # here (no GPU): compiles all variants in parallel
+    python scripts/tune.py run    <workload>      # on the GPU box: times every tune_libs/<workload>_*.so and checks parity
+"""
+import concurrent.futures as cf
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "robotdynamics.jl_b200", "csrc")
+OUT = os.path.join(ROOT, "tune_libs")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, CSRC)
+
+UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
+    "quadrotor": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
+    "cartpole": ("cartpole_f64", dict(RDB_KIND=0, RDB_DTYPE=1)),
+    "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
+    "satellite": ("body_mrp_world_f64", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
+    "satellite32": ("body_mrp_world_f32", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=0)),
+}
+
+VARIANTS = {
+    "quadrotor": {
+        "base": {},
+        "roll1": dict(RDB_TUNE_ROLL=1),
+        "roll2": dict(RDB_TUNE_ROLL=2),
+        "roll1_2r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+        "roll2_2r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+        "roll1_2rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0x1F800u"),
+        "roll2_2rb": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0x1F800u"),
+        "roll1_2r_t128": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+        "roll2_2r_t32": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=32, RDB_TUNE_MINB=4, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+        "roll1_3rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x3C00u", RDB_TUNE_C2="0x1C000u"),
+        "roll2_1r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=4, RDB_TUNE_C0="0x1FFFFu"),
+    },
+    "quadrotor64": {
+        "base": {},
+        "roll1_c3": dict(RDB_TUNE_ROLL=1),
+        "roll1_2r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+        "roll1_3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+        "roll2_3r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+        "roll1_4r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
+    },
+    "cartpole": {
+        "base": {},
+        "minb4": dict(RDB_TUNE_MINB=4),
+        "minb5": dict(RDB_TUNE_MINB=5),
+        "minb6": dict(RDB_TUNE_MINB=6),
+        "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
+        "t64_minb10": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=10),
+        "t256_minb2": dict(RDB_TUNE_TILE=256, RDB_TUNE_MINB=2),
+        "2r_minb3": dict(RDB_TUNE_C0="0x7u", RDB_TUNE_C1="0x18u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=4),
+    },
+    "satellite": {
+        "base": {},
+        "t64_3c": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=1),
+        "c2": dict(RDB_TUNE_C0="0x3u", RDB_TUNE_C1="0xCu", RDB_TUNE_C2="0x30u", RDB_TUNE_C3="0xC0u", RDB_TUNE_C4="0x300u", RDB_TUNE_C5="0xC00u", RDB_TUNE_C6="0x3000u", RDB_TUNE_C7="0xC000u", RDB_TUNE_C8="0x30000u", RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
+        "c6": dict(RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0x3F000u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
+        "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
+        "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
+    },
+}
+VARIANTS["satellite32"] = {"base": {}, "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=3),
+                           "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2)}
+
+
+def build_variants(workload):
+    import build as B
+    os.makedirs(OUT, exist_ok=True)
+    B.build()   # make sure abi.o / lie.o exist
+    unit, defs = UNIT[workload]
+    # stub object: every other unit symbol returns RDB_ERR_NOT_IMPLEMENTED
+    stub_src = os.path.join(OUT, f"stubs_{workload}.cu")
+    with open(stub_src, "w") as f:
+        f.write('namespace rdb { struct KnotRequest; }\n')
+        for name, _ in B.units():
+            if name != unit:
+                f.write(f'extern "C" int rdb_unit_{name}(const rdb::KnotRequest*) {{ return -2; }}\n')
+    stub_obj = stub_src.replace(".cu", ".o")
+    subprocess.check_call([B.NVCC] + B.ARCH + ["-Xcompiler", "-fPIC", "-c", "-o", stub_obj, stub_src])
+
+    def one(tag, extra):
+        obj = os.path.join(OUT, f"{workload}_{tag}.o")
+        lib = os.path.join(OUT, f"{workload}_{tag}.so")
+        flags = [f"-D{k}={v}" for k, v in {**defs, **extra}.items()] + [f"-DRDB_UNIT_NAME={unit}"]
+        p = subprocess.run([B.NVCC] + B.ARCH + B.COMMON + ["-Xptxas", "-v"] + flags + ["-c", "-o", obj, os.path.join(CSRC, "unit.cu")],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            return tag, "COMPILE FAILED: " + p.stdout[-1500:]
+        # resource line of the RK4 (or RK2 for satellite) Jacobian kernel
+        want = "Li1E" if workload.startswith("satellite") else "Li3E"
+        lines = p.stdout.splitlines()
+        info = ""
+        for i, l in enumerate(lines):
+            if "Compiling entry function" in l and "knot_kernel" in l and want in l and "ELb1E" in l:
+                info = " ".join(x.strip() for x in lines[i + 1:i + 4] if "registers" in x or "spill" in x)
+        subprocess.check_call([B.NVCC] + B.ARCH + ["-shared", "-o", lib, obj, stub_obj, os.path.join(B.OBJ, "abi.o"), os.path.join(B.OBJ, "lie.o"),
+                               "-cudart", "static"])
+        os.remove(obj)
+        return tag, info
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
+        for tag, info in ex.map(lambda kv: one(*kv), VARIANTS[workload].items()):
+            print(f"{workload}_{tag}: {info}", flush=True)
+
+
+_RUN_ONE = r"""
+import sys, os, json
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+import rdb200 as rd
+import bench
+from oracle import rd_oracle as o
+name = sys.argv[2]
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor"}.get(name, name)
+desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
+if name == "satellite32": dtn = "float32"
+if name == "quadrotor64": dtn = "float64"
+if len(sys.argv) > 3: N = int(sys.argv[3])
+mk, Q = bench.gpu_model(wl, rd)
+model = mk(); h = model._h
+nsets = 4
+Zs = [torch.from_numpy(bench.make_inputs(n, m, N, dtn, i)).cuda() for i in range(nsets)]
+Js = [torch.empty((N, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
+for i in range(5): h.discrete_jacobian(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
+torch.cuda.synchronize()
+steps = 100
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(steps): h.discrete_jacobian(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / steps * 1e3
+omk, oQ = bench.oracle_model(wl)
+idx = np.arange(0, N, 4099)
+ref = o.discrete_jacobian(omk(), oQ, Zs[0].cpu().numpy()[idx].astype(np.float64), dt)
+err = float(np.abs(Js[0].cpu().numpy()[idx] - ref).max())
+es = Zs[0].element_size()
+gbs = N * es * ((n + m) + n * (n + m)) / (us * 1e-6) / 1e9
+print(json.dumps({"us": us, "evals_per_s": N / (us * 1e-6), "GBs": gbs, "frac": gbs / 6551.4, "err": err}))
+"""
+
+
+def run_variants(workload, extra):
+    libs = sorted(f for f in os.listdir(OUT) if f.startswith(workload + "_") and f.endswith(".so"))
+    for lib in libs:
+        env = dict(os.environ, RDB200_LIB=os.path.join(OUT, lib))
+        p = subprocess.run([sys.executable, "-c", _RUN_ONE, ROOT, workload] + extra, capture_output=True, text=True, env=env, timeout=600)
+        last = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-300:]
+        print(f"{lib:40s} {last}", flush=True)
+
+
+if __name__ == "__main__":
+    cmd, workload = sys.argv[1], sys.argv[2]
+    if cmd == "build":
+        build_variants(workload)
+    else:
+        run_variants(workload, sys.argv[3:])
