@@ -86,6 +86,13 @@ int rdb_jacobian(const rdb_model* model, int dtype, int layout, int64_t N, const
  * src/discretized_dynamics.jl:169-219, src/integration.jl:85-93,149-177,302-337.  xn (= x+) may be NULL. */
 int rdb_discrete_jacobian(const rdb_model* model, int integrator, int dtype, int layout, int64_t N, const void* Z,
                           const double* t, const double* dt, double dt0, void* J, void* xn, void* stream);
+/* Error-state ("LieState") discrete Jacobian, what Altro / TrajectoryOptimization consume for RotationState models:
+ *   Jbar = G(x+)' [A B] blkdiag(G(x), I),  G = errstate_jacobian (src/liestate.jl:262-298), nerr x (nerr + m) column-major per
+ * knot (jacobian_width = errstate_dim + control_dim, src/functionbase.jl:135).  Computed in one pass by seeding forward mode with
+ * the columns of G(x); never forms the n x (n+m) Jacobian.  For EuclideanState models G = I and this equals
+ * rdb_discrete_jacobian.  Layouts as for J with (nerr, nerr+m) in place of (n, n+m); xn (= x+, n values) may be NULL. */
+int rdb_discrete_error_jacobian(const rdb_model* model, int integrator, int dtype, int layout, int64_t N, const void* Z,
+                                const double* t, const double* dt, double dt0, void* Jbar, void* xn, void* stream);
 /* errstate_jacobian!(model, G, x)                            src/statevectortype.jl:119-122, src/liestate.jl:262-298
  * X: N states with leading dimension ldx (>= n; pass n+m to read the states straight out of Z).
  * G: (n, nerr, N) column-major per knot, fully written (zeros included). */

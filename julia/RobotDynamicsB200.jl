@@ -122,6 +122,14 @@ end
 discrete_jacobian!(::Type{Q}, ∇f, model::RD.AbstractModel, z) where {Q<:RD.QuadratureRule} =
     RD.jacobian!(RD.StaticReturn(), B200(), RD.DiscretizedDynamics{Q}(model), ∇f, zeros(RD.state_dim(model)), z)
 
+"Error-state expansion `Jbar[:, :, k] = G(x⁺)' [A B] blkdiag(G(x), I)` (n̄ × (n̄+m)) for every knot point, one pass."
+function discrete_error_jacobian_batch!(dmodel::RD.DiscretizedDynamics{L,Q}, Jbar::Array{T,3}, y, data::Matrix{T}, dts; stream=C_NULL) where {L,Q,T}
+    check(ccall((:rdb_discrete_error_jacobian, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                gethandle(dmodel.continuous_dynamics).ptr, INTEGRATOR[Q], dtypecode(T), 0, size(data, 2), pointer(data), C_NULL, pointer(dts), 0.0,
+                pointer(Jbar), y === nothing ? C_NULL : pointer(y), stream), "rdb_discrete_error_jacobian")
+end
+
 "`errstate_jacobian!` for every knot point: `G[:, :, k]` is `n×n̄`, fully written (src/liestate.jl:262-298 writes non-zeros only)."
 function errstate_jacobian_batch!(model::RD.AbstractModel, G::Array{T,3}, X::Matrix{T}; stream=C_NULL) where T
     check(ccall((:rdb_errstate_jacobian, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),

@@ -31,7 +31,7 @@ ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE = -1, -2, -3, -4
 SYMBOLS = (
     "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free",
     "rdb_model_create", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
-    "rdb_jacobian", "rdb_discrete_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
+    "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
 )
 
@@ -73,6 +73,7 @@ def lib():
         L.rdb_discrete_dynamics.argtypes = [vp, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp]
         L.rdb_jacobian.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
         L.rdb_discrete_jacobian.argtypes = [vp, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp, vp]
+        L.rdb_discrete_error_jacobian.argtypes = [vp, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp, vp]
         L.rdb_errstate_jacobian.argtypes = [vp, i32, i64, vp, i32, vp, vp]
         L.rdb_grad_errstate_jacobian.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
         L.rdb_state_diff.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
@@ -282,6 +283,17 @@ class ModelHandle:
         pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv)
         check(lib().rdb_discrete_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, None, pd, dt0, pj, po,
                                           current_stream(Z)), "rdb_discrete_jacobian")
+        return J
+
+    def discrete_error_jacobian(self, Q, Z, dt, t=None, J=None, xn=None, layout=AOS):
+        """Jbar = G(x+)' [A B] blkdiag(G(x), I): AOS (N, nerr+m, nerr) C-order, i.e. per knot a column-major nerr x (nerr+m)."""
+        N = self._count(Z, layout)
+        nc = self.nerr + self.m
+        J = empty_like_kind(Z, (N, nc, self.nerr) if layout == AOS else (self.nerr * nc, N)) if J is None else J
+        dtv, dt0 = self._dt(dt, Z)
+        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv)
+        check(lib().rdb_discrete_error_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, None, pd, dt0, pj, po,
+                                                current_stream(Z)), "rdb_discrete_error_jacobian")
         return J
 
     def errstate_jacobian(self, X, G=None):

@@ -315,6 +315,21 @@ def discrete_jacobian_(Q, J, model, z):
     return jacobian_(StaticReturn(), B200(), DiscretizedDynamics(model, Q), J, None, z)
 
 
+def discrete_error_jacobian_(dmodel, Jbar, y, z):
+    """Error-state expansion of the discrete dynamics for RotationState models:  Jbar <- G(x+)' [A B] blkdiag(G(x), I)
+    (nerr x (nerr+m)), y <- x+.  The product Altro / TrajectoryOptimization build from jacobian! and errstate_jacobian!
+    (src/liestate.jl:262-298, src/functionbase.jl:135), fused into the Jacobian kernel."""
+    Z, _, dt, single = _batch(z)
+    h = dmodel._h
+    yb = None if y is None else (np.empty((Z.shape[0], h.n), dtype=Z.dtype) if single else y)
+    Jb = h.discrete_error_jacobian(_qcode(dmodel.integrator), Z, dt, J=None if single else Jbar, xn=yb)
+    if single:
+        Jbar[...] = Jb[0].T
+        if y is not None:
+            y[...] = yb[0]
+    return None
+
+
 def _states_of(model, x):
     """x: KnotPoint | SampledTrajectory | (n,) | (N, >=n) -> (X (N, ld), single?)."""
     if isinstance(x, KnotPoint):

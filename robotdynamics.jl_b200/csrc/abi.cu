@@ -111,7 +111,7 @@ int map_q(int integrator) {
 
 // The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
 int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* dt,
-            double dt0, void* J, void* out, void* stream) {
+            double dt0, void* J, void* out, void* stream, int err = 0) {
     if (!M || N < 0 || (dtype != RDB_F32 && dtype != RDB_F64) || (layout != RDB_AOS && layout != RDB_SOA)) return RDB_ERR_ARG;
     if (N == 0) return 0;
     if (!Z || (with_j && !J) || (!with_j && !out)) return RDB_ERR_ARG;
@@ -124,7 +124,8 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
 
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
-    r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.params = M->p;
+    if (M->rot == RDB_ROT_NONE) err = 0;     // EuclideanState: G = I (src/statevectortype.jl:149-155)
+    r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.err = err; r.params = M->p;
     r.dt0 = dt0; r.layout = layout; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.Z = Z; r.dt = dt; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
@@ -133,7 +134,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     // host pointers: H2D -> kernel -> D2H per chunk, chunks round-robin over NSLOT streams so the three overlap
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t es = esize(dtype);
-    const int n = M->n, NZ = M->n + M->m, E = n * NZ;
+    const int n = M->n, NZ = M->n + M->m, E = err ? M->nerr * (M->nerr + M->m) : n * NZ;
     int rc = 0;
     long long ci = 0;
     const long long cap_knots = N < HOST_CHUNK ? N : HOST_CHUNK;
@@ -296,6 +297,13 @@ int rdb_discrete_jacobian(const rdb_model* M, int integrator, int dtype, int lay
     const int Q = map_q(integrator);
     if (Q < 0) return RDB_ERR_ARG;
     return knot_op(M, Q, dtype, layout, 1, N, Z, dt, dt0, J, xn, stream);
+}
+
+int rdb_discrete_error_jacobian(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/,
+                                const double* dt, double dt0, void* Jbar, void* xn, void* stream) {
+    const int Q = map_q(integrator);
+    if (Q < 0) return RDB_ERR_ARG;
+    return knot_op(M, Q, dtype, layout, 1, N, Z, dt, dt0, Jbar, xn, stream, 1);
 }
 
 int rdb_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const void* X, int ldx, void* G, void* stream) {

@@ -31,6 +31,7 @@ struct KnotArgs {
     const double* dt;    // per-knot step (N) or nullptr -> dt0      (KnotPoint.dt is Float64: src/knotpoint.jl:148-153)
     double dt0;
     T* J;                // AOS (N, n+m, n) == per knot n x (n+m) column-major | SOA (n*(n+m), N);  may be nullptr
+                         // (error-state mode: nerr x (nerr+m) per knot instead)
     T* out;              // xdot or x+ : AOS (N, n) | SOA (n, N);  may be nullptr
     long long N;
     int layout;
@@ -73,79 +74,192 @@ __device__ __forceinline__ auto load_seeded(const T* zrow, std::index_sequence<I
 template <class T> __device__ __forceinline__ T plain(const T& a) { return a; }
 template <class T, mask_t M> __device__ __forceinline__ T plain(const SD<T, M>& a) { return a.v; }
 
-template <int N_, mask_t CHUNK, int J, class T, class XN, size_t... Is>
-__device__ __forceinline__ void put_col(const XN& xn, T* jrow, std::index_sequence<Is...>) {
-    if constexpr (chas(CHUNK, J)) { ((jrow[int(Is) + N_ * J] = partial<J>(get<int(Is)>(xn))), ...); }
+// 16-byte shared-memory stores of 4 floats / 2 doubles (used when a Jacobian column is a whole number of 16-byte units)
+__device__ __forceinline__ void st16(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void st16(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+template <int N_, int J, class XN, size_t... Ks>
+__device__ __forceinline__ void put_col_v(const XN& xn, float* col, std::index_sequence<Ks...>) {
+    (st16(col + 4 * int(Ks), partial<J>(get<4 * int(Ks)>(xn)), partial<J>(get<4 * int(Ks) + 1>(xn)), partial<J>(get<4 * int(Ks) + 2>(xn)),
+          partial<J>(get<4 * int(Ks) + 3>(xn))), ...);
 }
-template <int N_, mask_t CHUNK, class T, class XN, size_t... Js>
+template <int N_, int J, class XN, size_t... Ks>
+__device__ __forceinline__ void put_col_v(const XN& xn, double* col, std::index_sequence<Ks...>) {
+    (st16(col + 2 * int(Ks), partial<J>(get<2 * int(Ks)>(xn)), partial<J>(get<2 * int(Ks) + 1>(xn))), ...);
+}
+template <int N_, mask_t CHUNK, int J, bool VEC, class T, class XN, size_t... Is>
+__device__ __forceinline__ void put_col(const XN& xn, T* jrow, std::index_sequence<Is...>) {
+    if constexpr (chas(CHUNK, J)) {
+        if constexpr (VEC) put_col_v<N_, J>(xn, jrow + N_ * J, std::make_index_sequence<size_t(N_ * sizeof(T) / 16)>{});
+        else ((jrow[int(Is) + N_ * J] = partial<J>(get<int(Is)>(xn))), ...);
+    }
+}
+template <int N_, mask_t CHUNK, bool VEC, class T, class XN, size_t... Js>
 __device__ __forceinline__ void put_cols(const XN& xn, T* jrow, std::index_sequence<Js...>) {
-    (put_col<N_, CHUNK, int(Js)>(xn, jrow, std::make_index_sequence<size_t(N_)>{}), ...);
+    (put_col<N_, CHUNK, int(Js), VEC>(xn, jrow, std::make_index_sequence<size_t(N_)>{}), ...);
 }
 template <class T, class XN, size_t... Is>
 __device__ __forceinline__ void put_vals(const XN& xn, T* orow, std::index_sequence<Is...>) {
     ((orow[Is] = plain(get<int(Is)>(xn))), ...);
 }
 
+// ---- error-state ("LieState") mode --------------------------------------------------------------------------------------
+// Altro / TrajectoryOptimization consume  Abar = G(x+)' A G(x),  Bbar = G(x+)' B  for RotationState models, with
+// G = errstate_jacobian (reference: src/liestate.jl:262-298; jacobian_width = errstate_dim + m, src/functionbase.jl:135).
+// Here the product never exists as a product: the attitude entries of x are SEEDED with the rows of the attitude block of
+// G(x) (3 tangent directions instead of 4 unit vectors), forward mode then yields [A G(x), B] directly, and the attitude rows
+// of the result are contracted with G(x+)'.  Output: nerr x (nerr + m), column-major.
+template <class T, int ROT>
+__device__ __forceinline__ void att_grad(const T* p, T (&G)[4][3]) {   // Rotations.∇differential, values only
+    if constexpr (ROT == ROT_QUAT) {                                    // L(q) H with q normalised (default constructor)
+        const T s = rsqrt_(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+        const T w = p[0] * s, x = p[1] * s, y = p[2] * s, z = p[3] * s;
+        G[0][0] = -x; G[0][1] = -y; G[0][2] = -z;
+        G[1][0] = w;  G[1][1] = -z; G[1][2] = y;
+        G[2][0] = z;  G[2][1] = w;  G[2][2] = -x;
+        G[3][0] = -y; G[3][1] = x;  G[3][2] = w;
+    } else {
+        const T sk[3][3] = {{T(0), -p[2], p[1]}, {p[2], T(0), -p[0]}, {-p[1], p[0], T(0)}};
+        const T a = (ROT == ROT_MRP) ? T(1) - (p[0] * p[0] + p[1] * p[1] + p[2] * p[2]) : T(1);
+        const T c = (ROT == ROT_MRP) ? T(2) : T(1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? a : T(0)) + c * (sk[i][j] + p[i] * p[j]);
+    }
+}
+// value + partials g3,g4,g5 on the error columns 3,4,5 that belong to this role's chunk
+template <class T, mask_t CHUNK>
+__device__ __forceinline__ auto seed_att(T v, T g3, T g4, T g5) {
+    constexpr mask_t M = CHUNK & mask_t(0x38);
+    if constexpr (M == 0) return v;
+    else {
+        SD<T, M> r; r.v = v;
+        if constexpr (chas(M, 3)) r.d[cslot(M, 3)] = g3;
+        if constexpr (chas(M, 4)) r.d[cslot(M, 4)] = g4;
+        if constexpr (chas(M, 5)) r.d[cslot(M, 5)] = g5;
+        return r;
+    }
+}
+template <class Model, class T, mask_t CHUNK, int I>
+__device__ __forceinline__ auto seed_err(const T* z, const T (&G)[4][3]) {
+    constexpr int np = Model::n - 9;
+    if constexpr (I < 3) return seed<T, I, CHUNK>(z[I]);
+    else if constexpr (I < 3 + np) return seed_att<T, CHUNK>(z[I], G[I - 3][0], G[I - 3][1], G[I - 3][2]);
+    else return seed<T, I - (np - 3), CHUNK>(z[I]);
+}
+template <class Model, class T, mask_t CHUNK, size_t... Is>
+__device__ __forceinline__ auto load_seeded_err(const T* z, std::index_sequence<Is...>) {
+    T G[4][3];
+    att_grad<T, Model::rot>(z + 3, G);
+    return vec(seed_err<Model, T, CHUNK, int(Is)>(z, G)...);
+}
+template <class T, class A, size_t... Is> __device__ __forceinline__ void plain_vals(const A& a, T* out, std::index_sequence<Is...>) { ((out[Is] = plain(get<int(Is)>(a))), ...); }
+template <int J, class T, class A, size_t... Is>
+__device__ __forceinline__ auto contract_col(const T (&G)[4][3], const A& att, std::index_sequence<Is...>) { return ((G[Is][J] * get<int(Is)>(att)) + ...); }
+// rows of the result in error coordinates: [r+; G(x+)' att+; v+; w+]
+template <class Model, class T, class XN>
+__device__ __forceinline__ auto project_err(const XN& xn) {
+    constexpr int np = Model::n - 9;
+    auto att = slice<3, np>(xn);
+    T p[4], G[4][3];
+    plain_vals(att, p, std::make_index_sequence<size_t(np)>{});
+    att_grad<T, Model::rot>(p, G);
+    using Seq = std::make_index_sequence<size_t(np)>;
+    return cat(slice<0, 3>(xn), vec(contract_col<0>(G, att, Seq{}), contract_col<1>(G, att, Seq{}), contract_col<2>(G, att, Seq{})),
+               slice<3 + np, 6>(xn));
+}
+
 // all threads of the CTA meet here between "results are in registers" and "results go to the smem images":
 // thread 0 first waits until the previous tile's bulk stores have finished reading those images.
-template <int NTHR>
+template <int NTHR, int ISSUERS>
 __device__ __forceinline__ void images_free_barrier(int tid) {
-    if (tid == 0) bulk_wait_read0();
+    if (tid < ISSUERS) bulk_wait_read0();      // bulk groups are per thread: every thread that issued stores waits for its own
     asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
 }
 
 // One role: evaluate the map for one knot with partials for the columns in CHUNK; write this role's share.
-template <class Model, int Q, class T, bool WITH_J, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL>
+template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC>
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
-    auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, std::make_index_sequence<size_t(NZ)>{});
-    auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
-    images_free_barrier<NTHR>(tid);
-    if constexpr (WITH_J) put_cols<n, CHUNK>(xn, jrow, std::make_index_sequence<size_t(NZ)>{});
-    if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
+    if constexpr (ERR) {
+        auto zz = load_seeded_err<Model, T, CHUNK>(zrow, std::make_index_sequence<size_t(NZ)>{});
+        auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
+        auto e = project_err<Model, T>(xn);
+        images_free_barrier<NTHR, ISSUERS>(tid);
+        put_cols<Model::nerr, CHUNK, VEC>(e, jrow, std::make_index_sequence<size_t(Model::nerr + m)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
+    } else {
+        auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, std::make_index_sequence<size_t(NZ)>{});
+        auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
+        images_free_barrier<NTHR, ISSUERS>(tid);
+        if constexpr (WITH_J) put_cols<n, CHUNK, VEC>(xn, jrow, std::make_index_sequence<size_t(NZ)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
+    }
 }
 
 template <int R, class L> struct list_at;
 template <int R, mask_t M0, mask_t... Ms> struct list_at<R, MaskList<M0, Ms...>> { static constexpr mask_t value = list_at<R - 1, MaskList<Ms...>>::value; };
 template <mask_t M0, mask_t... Ms> struct list_at<0, MaskList<M0, Ms...>> { static constexpr mask_t value = M0; };
 
-template <class Model, int Q, class T, bool WITH_J, class Chunks, int NTHR, int ROLL, int R = 0>
+template <class Model, int Q, class T, bool WITH_J, bool ERR, class Chunks, int NTHR, int ROLL, int ISSUERS, bool VEC, int R = 0>
 __device__ __forceinline__ void dispatch_role(int role, const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     if constexpr (R + 1 == Chunks::count) {
-        role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR, ROLL>(model, zrow, h, jrow, orow, tid);
+        role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC>(model, zrow, h, jrow, orow, tid);
     } else {
-        if (role == R) role_body<Model, Q, T, WITH_J, list_at<R, Chunks>::value, R == 0, NTHR, ROLL>(model, zrow, h, jrow, orow, tid);
-        else dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR, ROLL, R + 1>(role, model, zrow, h, jrow, orow, tid);
+        if (role == R) role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC>(model, zrow, h, jrow, orow, tid);
+        else dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, ISSUERS, VEC, R + 1>(role, model, zrow, h, jrow, orow, tid);
     }
 }
 
-// cooperative copies between a dense knot-major smem image [cnt][W] and global memory
+// cooperative copies between a knot-major smem image [cnt][W] (row pitch P >= W) and global memory
 template <class T>
-__device__ __forceinline__ void coop_load(T* img, const T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
-    const int total = cnt * W;
+__device__ __forceinline__ void coop_load(T* img, int P, const T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
     if (layout == LAYOUT_AOS) {
-        const T* src = g + k0 * W;
-        for (int i = tid; i < total; i += nthr) img[i] = src[i];
+        if (P == W) {
+            const T* src = g + k0 * W;
+            for (int i = tid; i < cnt * W; i += nthr) img[i] = src[i];
+        } else {
+            const int lane = tid & 31, nw = nthr >> 5;
+            for (int r = tid >> 5; r < cnt; r += nw) { const T* src = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) img[r * P + e] = src[e]; }
+        }
     } else {
-        for (int i = tid; i < total; i += nthr) { const int c = i / cnt, kt = i - c * cnt; img[kt * W + c] = g[(long long)c * N + k0 + kt]; }
+        for (int i = tid; i < cnt * W; i += nthr) { const int c = i / cnt, kt = i - c * cnt; img[kt * P + c] = g[(long long)c * N + k0 + kt]; }
     }
 }
 template <class T>
-__device__ __forceinline__ void coop_store(const T* img, T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
-    const int total = cnt * W;
+__device__ __forceinline__ void coop_store(const T* img, int P, T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
     if (layout == LAYOUT_AOS) {
-        T* dst = g + k0 * W;
-        for (int i = tid; i < total; i += nthr) dst[i] = img[i];
+        if (P == W) {
+            T* dst = g + k0 * W;
+            for (int i = tid; i < cnt * W; i += nthr) dst[i] = img[i];
+        } else {   // one warp per knot row: conflict-free smem reads (unit stride), fully coalesced global writes
+            const int lane = tid & 31, nw = nthr >> 5;
+            for (int r = tid >> 5; r < cnt; r += nw) { T* dst = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) dst[e] = img[r * P + e]; }
+        }
     } else {
-        for (int i = tid; i < total; i += nthr) { const int c = i / cnt, kt = i - c * cnt; g[(long long)c * N + k0 + kt] = img[kt * W + c]; }
+        for (int i = tid; i < cnt * W; i += nthr) { const int c = i / cnt, kt = i - c * cnt; g[(long long)c * N + k0 + kt] = img[kt * P + c]; }
     }
 }
 
-template <class Model, int TILE, bool WITH_J, class T>
+__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+template <class Model, int TILE, bool WITH_J, class T, bool ERR = false>
 struct KnotSmem {
-    static constexpr int n = Model::n, NZ = Model::n + Model::m, E = Model::n * NZ;
+    static constexpr int n = Model::n, NZ = Model::n + Model::m;
+    static constexpr int JR = ERR ? Model::nerr : n, JC = ERR ? Model::nerr + Model::m : NZ, E = JR * JC;   // Jacobian image shape
+    // Row pitch of the Jacobian image.  Thread kt writes element e of its knot to word kt*PJ + e, so a pitch that is a multiple
+    // of 32 words puts all lanes of a warp on ONE bank (E = 192 for n=12, m=4).  The quaternion models have odd E (221, 247):
+    // dense image, conflict-free, leaves by ONE TMA bulk store per tile.  The n = 12 models (E even, columns = whole 16-byte
+    // units) get a pitch of an ODD number of 16-byte units, write their columns with 16-byte stores (conflict-free) and leave
+    // by one TMA bulk store PER KNOT ROW, issued by TILE threads in parallel.
+    // (only when the dense image would be badly conflicted: >= 16 lanes per bank; the 8-way case E = 216 fp32 measured faster dense)
+    static constexpr bool ROWSTORE = WITH_J && JR >= 12 && (E % 2 == 0) && ((JR * sizeof(T)) % 16 == 0) &&
+                                     cgcd(int(E * sizeof(T) / 4), 32) >= 16;
+    static constexpr int units16 = int((E * sizeof(T) + 15) / 16);
+    static constexpr int PJ = ROWSTORE ? int(((units16 % 2 == 0) ? units16 + 1 : units16) * 16 / sizeof(T)) : E;
+    static constexpr int ISSUERS = ROWSTORE ? TILE : 1;
     static constexpr size_t in_bytes = size_t(TILE) * NZ * sizeof(T);
-    static constexpr size_t j_bytes = WITH_J ? size_t(TILE) * E * sizeof(T) : 0;
+    static constexpr size_t j_bytes = WITH_J ? size_t(TILE) * PJ * sizeof(T) : 0;
+    static constexpr size_t j_dense_bytes = WITH_J ? size_t(TILE) * E * sizeof(T) : 0;
     static constexpr size_t o_bytes = size_t(TILE) * n * sizeof(T);
     static constexpr size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
     static constexpr size_t off_in0 = 0;
@@ -156,12 +270,12 @@ struct KnotSmem {
     static constexpr size_t total = off_bar + 16;
 };
 
-template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL>
+template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL, bool ERR = false>
 __global__ void __launch_bounds__(TILE * Chunks::count, MINB)
 knot_kernel(const Model model, const KnotArgs<T> a) {
-    constexpr int n = Model::n, NZ = Model::n + Model::m, E = n * NZ;
+    using S = KnotSmem<Model, TILE, WITH_J, T, ERR>;
+    constexpr int n = Model::n, NZ = Model::n + Model::m, E = S::E;
     constexpr int NTHR = TILE * Chunks::count;
-    using S = KnotSmem<Model, TILE, WITH_J, T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* in_img[2] = {reinterpret_cast<T*>(smem_raw + S::off_in0), reinterpret_cast<T*>(smem_raw + S::off_in1)};
     T* j_img = reinterpret_cast<T*>(smem_raw + S::off_j);
@@ -206,7 +320,7 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
         // (2) this tile's inputs
         const bool tma = tile_tma(tile);
         if (tma) { mbar_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1; }
-        else { coop_load(in_img[s], a.Z, k0, cnt, NZ, N, a.layout, tid, NTHR); __syncthreads(); }
+        else { coop_load(in_img[s], NZ, a.Z, k0, cnt, NZ, N, a.layout, tid, NTHR); __syncthreads(); }
         // (3) compute in registers
         const T* zrow = in_img[s] + kt * NZ;
         T h = T(0);
@@ -214,23 +328,29 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
         (void)cnt;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
-        dispatch_role<Model, Q, T, WITH_J, Chunks, NTHR, ROLL>(role, model, zrow, h, j_img + kt * E, want_o ? o_img + kt * n : nullptr, tid);
+        dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, S::ISSUERS, S::ROWSTORE>(role, model, zrow, h, j_img + kt * S::PJ, want_o ? o_img + kt * n : nullptr, tid);
         // (5) publish
         if (tma) {
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) {
-                if (want_j) bulk_store(a.J + k0 * E, smem_u32(j_img), uint32_t(S::j_bytes));
+            if constexpr (S::ROWSTORE) {
+                if (tid < TILE) {
+                    if (want_j) bulk_store(a.J + (k0 + tid) * E, smem_u32(j_img + tid * S::PJ), uint32_t(E * sizeof(T)));
+                    if (tid == 0 && want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                    bulk_commit();
+                }
+            } else if (tid == 0) {
+                if (want_j) bulk_store(a.J + k0 * E, smem_u32(j_img), uint32_t(S::j_dense_bytes));
                 if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
                 bulk_commit();
             }
         } else {
             __syncthreads();
-            if (want_j) coop_store(j_img, a.J, k0, cnt, E, N, a.layout, tid, NTHR);
-            if (want_o) coop_store(o_img, a.out, k0, cnt, n, N, a.layout, tid, NTHR);
+            if (want_j) coop_store(j_img, S::PJ, a.J, k0, cnt, E, N, a.layout, tid, NTHR);
+            if (want_o) coop_store(o_img, n, a.out, k0, cnt, n, N, a.layout, tid, NTHR);
         }
     }
-    if (tid == 0) bulk_wait0();
+    if (tid < S::ISSUERS) bulk_wait0();
 }
 
 }  // namespace rdb

@@ -113,13 +113,16 @@ struct KnotConfig<Model, T, true, Q> {
 
 struct DeviceInfo { int device; int sm_count; int pdl; };   // pdl: launch with programmatic stream serialization
 
-template <class Model, int Q, class T, bool WITH_J>
+// shape seen by the tiling rules in error-state mode: nerr rows, nerr + m columns (like an n = 12 model)
+template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m; };
+
+template <class Model, int Q, class T, bool WITH_J, bool ERR = false>
 struct KnotLaunch {
-    using Cfg = KnotConfig<Model, T, WITH_J, Q>;
-    using S = KnotSmem<Model, Cfg::TILE, WITH_J, T>;
+    using Cfg = KnotConfig<std::conditional_t<ERR, ErrShape<Model>, Model>, T, WITH_J, Q>;
+    using S = KnotSmem<Model, Cfg::TILE, WITH_J, T, ERR>;
     static constexpr int NTHR = Cfg::TILE * Cfg::Chunks::count;
     static int run(const Model& model, const KnotArgs<T>& a, const DeviceInfo& dev, cudaStream_t st) {
-        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL>;
+        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL, ERR>;
         static int occ_cache[64];   // CTAs/SM per device id; 0 = not yet configured on that device
         const int d = dev.device & 63;
         if (occ_cache[d] == 0) {
@@ -151,6 +154,7 @@ struct KnotRequest {
     int Q;               // QuadRule (Q_CONTINUOUS for dynamics / continuous Jacobian)
     int dtype;           // 0 = f32, 1 = f64
     int with_j;
+    int err;             // error-state Jacobian  G(x+)' [A B] blkdiag(G(x), I)  (rigid bodies; needs with_j)
     ModelParams<double> params;
     const void* Z; const double* dt; double dt0; void* J; void* out; long long N; int layout;
     // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)
@@ -191,13 +195,13 @@ inline ModelParams<T> cast_params(const ModelParams<double>& p) {
     return q;
 }
 
-template <template <class> class ModelT, class T, int Q, bool WITH_J>
+template <template <class> class ModelT, class T, int Q, bool WITH_J, bool ERR = false>
 inline int run_one(const KnotRequest& r) {
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.layout = r.layout;
-    return KnotLaunch<ModelT<T>, Q, T, WITH_J>::run(model, a, r.dev, r.stream);
+    return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
 template <template <class> class ModelT, class T, int Q>
 inline int run_rollout(const KnotRequest& r) {
@@ -214,6 +218,10 @@ inline int run_rollout(const KnotRequest& r) {
 template <template <class> class ModelT, class T, int Q>
 inline int run_q(const KnotRequest& r) {
     if (r.op == OP_ROLLOUT) return run_rollout<ModelT, T, Q>(r);
+    if (r.err) {
+        if constexpr (ModelT<T>::rot != ROT_NONE && Q != Q_CONTINUOUS) return run_one<ModelT, T, Q, true, true>(r);
+        else return -2;
+    }
     return r.with_j ? run_one<ModelT, T, Q, true>(r) : run_one<ModelT, T, Q, false>(r);
 }
 template <template <class> class ModelT, class T>

@@ -50,6 +50,26 @@ def bench(name, gm, Q, dtype, N, dt=0.01, iters=20):
     gbs = N * es * ((n + m) + n * (n + m)) / t / 1e9
     print(f"BENCH {name:24s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
 
+def bench_err(name, gm, Q, dtype, N, dt=0.01, iters=20):
+    rng = np.random.default_rng(2)
+    Z = torch.from_numpy(rand_inputs(gm._h, N, rng).astype(dtype)).cuda()
+    ne, m = gm._h.nerr, gm._h.m
+    J = torch.empty((N, ne + m, ne), dtype=Z.dtype, device='cuda')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(3): gm._h.discrete_error_jacobian(Q, Z, dt, J=J)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gm._h.discrete_error_jacobian(Q, Z, dt, J=J); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = np.median(ts) * 1e-3
+    es = Z.element_size()
+    gbs = N * es * ((gm._h.n + m) + ne * (ne + m)) / t / 1e9
+    print(f"BENCH-ERR {name:20s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     cp, cpo = rd.Cartpole(), o.cartpole()
@@ -66,6 +86,9 @@ if __name__ == "__main__":
     check("body quat body", rd.Body(bodyframe=True), o.body(o.ROT_QUAT, o.BODYFRAME), 3, np.float64)
     check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
+    bench_err("quadrotor", qd, 3, np.float32, 262144)
+    bench_err("quadrotor", qd, 3, np.float64, 262144)
+    bench_err("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float64, 1 << 20, dt=0.1)
     bench("cartpole", cp, 3, np.float64, 1 << 20)
     bench("cartpole", cp, 3, np.float64, 1 << 23)
     bench("cartpole", cp, 3, np.float32, 1 << 22)

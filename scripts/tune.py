@@ -19,6 +19,7 @@ sys.path.insert(0, CSRC)
 UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
     "quadrotor": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "cartpole": ("cartpole_f64", dict(RDB_KIND=0, RDB_DTYPE=1)),
+    "quadbody": ("quad_quat_body_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=0)),
     "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite": ("body_mrp_world_f64", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite32": ("body_mrp_world_f32", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=0)),
@@ -37,6 +38,13 @@ VARIANTS = {
         "roll2_2r_t32": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=32, RDB_TUNE_MINB=4, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
         "roll1_3rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x3C00u", RDB_TUNE_C2="0x1C000u"),
         "roll2_1r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=4, RDB_TUNE_C0="0x1FFFFu"),
+    },
+    "quadbody": {
+        "base": {},
+        "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+        "3r_t128": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+        "3rb_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x3C00u", RDB_TUNE_C2="0x1C000u"),
+        "4r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
     },
     "quadrotor64": {
         "base": {},
@@ -117,12 +125,13 @@ import rdb200 as rd
 import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
-wl = {"satellite32": "satellite", "quadrotor64": "quadrotor"}.get(name, name)
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
 if name == "quadrotor64": dtn = "float64"
 if len(sys.argv) > 3: N = int(sys.argv[3])
 mk, Q = bench.gpu_model(wl, rd)
+if name == 'quadbody': mk = lambda: rd.Quadrotor(bodyframe=True)
 model = mk(); h = model._h
 nsets = 4
 Zs = [torch.from_numpy(bench.make_inputs(n, m, N, dtn, i)).cuda() for i in range(nsets)]
@@ -136,6 +145,7 @@ for i in range(steps): h.discrete_jacobian(Q.code, Zs[i % nsets], dt, J=Js[i % n
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / steps * 1e3
 omk, oQ = bench.oracle_model(wl)
+if name == 'quadbody': omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
 idx = np.arange(0, N, 4099)
 ref = o.discrete_jacobian(omk(), oQ, Zs[0].cpu().numpy()[idx].astype(np.float64), dt)
 err = float(np.abs(Js[0].cpu().numpy()[idx] - ref).max())

@@ -350,3 +350,47 @@ def test_reference_api_rigid_body_liestate(rd):
     dG = np.zeros((12, 12))
     rd.grad_errstate_jacobian_(model, dG, zz[0, :13], x0)
     assert np.abs(dG - o.grad_errstate_jacobian(om, zz[:, :13], x0[None])[0].T).max() < 1e-12
+
+
+# ---- fused error-state Jacobian -------------------------------------------------------------------------------------
+def _error_jacobian_ref(om, Q, Z, dt):
+    """Gn' [A B] blkdiag(G, I) assembled from the oracle's jacobian / errstate_jacobian / discrete_dynamics."""
+    n, m, ne = om.n, om.m, om.nerr
+    J = o.as_matrix(o.discrete_jacobian(om, Q, Z, dt))                 # (N, n, n+m)
+    xn = o.discrete_dynamics(om, Q, Z, dt)
+    G = o.as_matrix(o.errstate_jacobian(om, Z[:, :n]))                 # (N, n, nerr)
+    Gn = o.as_matrix(o.errstate_jacobian(om, xn))
+    A = np.einsum("kia,kij,kjb->kab", Gn, J[:, :, :n], G)
+    B = np.einsum("kia,kij->kaj", Gn, J[:, :, n:])
+    return np.concatenate([A, B], axis=2)                              # (N, nerr, nerr+m)
+
+
+@pytest.mark.parametrize("name", ["quad_quat_world", "quad_mrp_world", "body_quat_body", "body_rp_world", "satellite_mrp", "cartpole"])
+def test_discrete_error_jacobian(rd, torch_, name):
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    N = 1500
+    Z = rand_inputs(om.n, om.m, N, np.random.default_rng(61))
+    if om.n == 13:
+        Z[:, 3:7] *= 1.3                                                # off the unit sphere: G normalises, the dynamics does not
+    dt = np.random.default_rng(62).uniform(0.0, 0.1, N)
+    for dtype, tol in ((np.float64, 1e-10), (np.float32, 1e-4)):
+        Zt = Z.astype(dtype)
+        for Q in (o.RK4, o.RK2, o.EULER, o.RK3):
+            ref = _error_jacobian_ref(om, Q, Zt.astype(np.float64), dt)
+            xn = np.empty((N, om.n), dtype=dtype)
+            Jb = gm._h.discrete_error_jacobian(Q, Zt, dt, xn=xn)
+            assert Jb.shape == (N, om.nerr + om.m, om.nerr)
+            assert np.abs(o.as_matrix(Jb) - ref).max() < tol
+            assert np.abs(xn - o.discrete_dynamics(om, Q, Zt.astype(np.float64), dt)).max() < tol
+        Jd = gm._h.discrete_error_jacobian(o.RK4, dev(torch_, Zt), dt)
+        Js = gm._h.discrete_error_jacobian(o.RK4, dev(torch_, np.ascontiguousarray(Zt.T)), dt, layout=rd.SOA)
+        torch_.cuda.synchronize()
+        ref = _error_jacobian_ref(om, o.RK4, Zt.astype(np.float64), dt)
+        assert np.abs(o.as_matrix(Jd.cpu().numpy()) - ref).max() < tol
+        assert np.array_equal(Js.cpu().numpy().T.reshape(N, om.nerr + om.m, om.nerr), Jd.cpu().numpy())
+    # reference-facing spelling, one knot
+    dm = rd.DiscretizedDynamics(gm, rd.RK4)
+    z = rd.KnotPoint(Z[0, :om.n], Z[0, om.n:], 0.0, 0.05)
+    Jbar, y = np.zeros((om.nerr, om.nerr + om.m)), np.zeros(om.n)
+    rd.discrete_error_jacobian_(dm, Jbar, y, z)
+    assert np.abs(Jbar - _error_jacobian_ref(om, o.RK4, Z[:1], 0.05)[0]).max() < 1e-10
