@@ -39,6 +39,8 @@ WORKLOADS = {
     "quadrotor": ("BASELINE configs[2]: Quadrotor RigidBody{QuatRotation} (n=13,m=4) RK4, 262144 knot points, fp32", 13, 4, 262144, "float32", 0.01),
     "satellite": ("BASELINE configs[3]: Satellite RigidBody{MRP} (n=12,m=6) RK2, 2^20 knot points, fp64", 12, 6, 1 << 20, "float64", 0.1),
 }
+SWEEP_DESC = ("BASELINE configs[4]: mixed trajectory sweep, 4096 trajectories x 256 knot points, first half Cartpole (fp64), second half "
+              "Quadrotor (fp32), RK4, per-trajectory dt, contiguous trajectory blocks per rank (strong scaling)")
 
 
 def make_inputs(n, m, N, dtype, seed):
@@ -172,6 +174,67 @@ def physical_gpu_index(local):
     return local
 
 
+def run_sweep(args):
+    """BASELINE configs[4]: the 4096 x 256 mixed sweep, sharded by contiguous trajectory blocks (strong scaling: total work fixed)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import rdb200 as rd
+    from rdb200 import sharding as sh
+    ntraj, K = 4096, 256
+    segs = sh.partition_segments({"cartpole": ntraj // 2, "quadrotor": ntraj // 2}, world, rank)
+    work = []
+    for name, (lo, hi) in segs.items():
+        _, n, m, _, dtn, _ = WORKLOADS[name]
+        mk, Q = gpu_model(name, rd)
+        model = mk()
+        cnt = (hi - lo) * K
+        nsets = 6
+        Zs = [torch.from_numpy(make_inputs(n, m, cnt, dtn, 17 * rank + i)).cuda() for i in range(nsets)]
+        dt = torch.from_numpy(np.repeat(0.01 * (1 + np.arange(lo, hi) % 4), K)).cuda()
+        Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
+        work.append((model._h, Q.code, Zs, dt, Js, cnt, np.dtype(dtn).itemsize * ((n + m) + n * (n + m))))
+
+    def step(i):
+        for h, qc, Zs, dt, Js, _, _ in work:
+            h.discrete_jacobian(qc, Zs[i % len(Zs)], dt, J=Js[i % len(Zs)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = sh.barrier_max_ms(e0.elapsed_time(e1), device=torch.device("cuda", local))
+    if rank == 0:
+        total = ntraj * K
+        byts = sum(c * b for *_, c, b in work) * world        # every rank holds an equal share of both segments
+        line = {"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+                "config": {"workload": SWEEP_DESC, "l2": "6 rotating buffer sets per segment", "parallelism": f"trajectory-block sharded x{world}"},
+                "roofline": {"bound": "hbm", "achieved": byts / (ms * 1e-3 / args.steps) / 1e9 / world, "peak": 6551.4, "unit": "GB/s per GPU",
+                             "frac": byts / (ms * 1e-3 / args.steps) / 1e9 / world / 6551.4, "traffic": None},
+                "gpu_launches": 2 * args.steps}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -291,11 +354,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS) + ["sweep"])
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU time for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "sweep":
+            args.workload = "cartpole"
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.gpus > 1 and world == 1:
@@ -304,6 +369,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.workload == "sweep":
+        return run_sweep(args)
     return run_ours(args)
 
 

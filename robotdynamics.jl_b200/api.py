@@ -195,11 +195,40 @@ class SampledTrajectory:
     def __iter__(self): return (self[k] for k in range(len(self)))
 
 
+class DeviceTrajectory:
+    """Persistent device mirror of a SampledTrajectory: `data` (N, n+m), `dts` (N,) live in HBM as torch
+    tensors, so repeated linearisations never re-gather the host's Vector{KnotPoint} (an array of pointers to mutable structs,
+    src/knotpoint.jl:213-217) and never cross PCIe.  setstates_/setcontrols_ are sliced H2D copies (src/trajectories.jl:215-250);
+    jacobian_ / discrete_error_jacobian_ / discrete_dynamics accept it wherever a SampledTrajectory is accepted and write into
+    device outputs."""
+
+    def __init__(self, Z, device=None, dtype=None):
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.n, self.m = Z.n, Z.m
+        host = Z.data if dtype is None else Z.data.astype(dtype)
+        self.data = torch.from_numpy(np.ascontiguousarray(host)).to(dev)
+        self.dts = torch.from_numpy(np.ascontiguousarray(Z.dts)).to(dev)
+        self.times = Z.times.copy()
+
+    def __len__(self): return self.data.shape[0]
+
+    def to_host(self):
+        Z = SampledTrajectory.__new__(SampledTrajectory)
+        Z.n, Z.m, Z.data, Z.dts, Z.times = self.n, self.m, self.data.cpu().numpy(), self.dts.cpu().numpy(), self.times.copy()
+        return Z
+
+
 def states(Z): return Z.data[:, :Z.n]
 def controls(Z): return Z.data[:, Z.n:]
 def gettimes(Z): return Z.times
-def setstates_(Z, X): Z.data[:, :Z.n] = X
-def setcontrols_(Z, U): Z.data[:len(U), Z.n:] = U
+def _like(Z, A):
+    if isinstance(Z, DeviceTrajectory) and not _abi._is_torch(A):
+        import torch
+        return torch.as_tensor(np.asarray(A), dtype=Z.data.dtype, device=Z.data.device)
+    return A
+def setstates_(Z, X): Z.data[:, :Z.n] = _like(Z, X)
+def setcontrols_(Z, U): Z.data[:len(U), Z.n:] = _like(Z, U)
 
 
 class DynamicsJacobian:
@@ -230,9 +259,9 @@ def _batch(z):
     """-> (Z (N, n+m) array/tensor, t, dt, single?)."""
     if isinstance(z, KnotPoint):
         return np.ascontiguousarray(z.z[None, :]), np.array([z.t]), np.array([z.dt]), True
-    if isinstance(z, SampledTrajectory):
+    if isinstance(z, (SampledTrajectory, DeviceTrajectory)):
         return z.data, z.times, z.dts, False
-    raise TypeError(f"expected a KnotPoint or SampledTrajectory, got {type(z).__name__}")
+    raise TypeError(f"expected a KnotPoint, SampledTrajectory or DeviceTrajectory, got {type(z).__name__}")
 
 
 def _write(dst, src, single):
@@ -299,7 +328,7 @@ def jacobian_(sig, diff, fun, J, y, z):
     h = fun._h
     yb = None
     if y is not None:
-        yb = np.empty((Z.shape[0], h.n), dtype=Z.dtype) if single or not hasattr(y, "shape") else y
+        yb = _abi.empty_like_kind(Z, (Z.shape[0], h.n)) if single or not hasattr(y, "shape") else y
     if isinstance(fun, DiscretizedDynamics):
         Jb = h.discrete_jacobian(_qcode(fun.integrator), Z, dt, J=None if single or isinstance(J, DynamicsJacobian) else J, xn=yb)
     else:
@@ -334,7 +363,7 @@ def _states_of(model, x):
     """x: KnotPoint | SampledTrajectory | (n,) | (N, >=n) -> (X (N, ld), single?)."""
     if isinstance(x, KnotPoint):
         return np.ascontiguousarray(x.z[None, :]), True
-    if isinstance(x, SampledTrajectory):
+    if isinstance(x, (SampledTrajectory, DeviceTrajectory)):
         return x.data, False
     if _abi._is_torch(x):
         return (x[None, :].contiguous(), True) if x.dim() == 1 else (x, False)
@@ -375,6 +404,23 @@ def rollout_(sig, dmodel, Z, x0=None):
                           np.ascontiguousarray(controls(Z)[None, :-1]), np.ascontiguousarray(Z.dts[None, :]))
     setstates_(Z, X[0])
     return None
+
+
+def rollout_and_linearize(dmodel, x0, U, dt, error_state=False):
+    """Forward pass + linearisation of many trajectories without leaving the device: X = rollout(x0, U),
+    then the (error-state) discrete Jacobians at every non-terminal knot (x_k, u_k).  x0 (ntraj, n), U (ntraj, K-1, m), scalar dt.
+    Returns X (ntraj, K, n) and J (ntraj, K-1, n+m, n) [or (ntraj, K-1, nerr+m, nerr)]; two kernel launches, no host round trip
+    when the inputs are CUDA tensors."""
+    h, Q = dmodel._h, _qcode(dmodel.integrator)
+    X = h.rollout(Q, x0, U, dt)
+    ntraj, K = X.shape[0], X.shape[1]
+    if _abi._is_torch(X):
+        import torch
+        Z = torch.cat([X[:, :-1, :], U], dim=2).reshape(ntraj * (K - 1), h.n + h.m).contiguous()
+    else:
+        Z = np.ascontiguousarray(np.concatenate([X[:, :-1, :], U], axis=2).reshape(ntraj * (K - 1), h.n + h.m))
+    J = (h.discrete_error_jacobian if error_state else h.discrete_jacobian)(Q, Z, float(dt))
+    return X, J.reshape(ntraj, K - 1, J.shape[1], J.shape[2])
 
 
 def rollout_batch(dmodel, x0, U, dt):

@@ -394,3 +394,39 @@ def test_discrete_error_jacobian(rd, torch_, name):
     Jbar, y = np.zeros((om.nerr, om.nerr + om.m)), np.zeros(om.n)
     rd.discrete_error_jacobian_(dm, Jbar, y, z)
     assert np.abs(Jbar - _error_jacobian_ref(om, o.RK4, Z[:1], 0.05)[0]).max() < 1e-10
+
+
+def test_device_trajectory_and_rollout_linearize(rd, torch_):
+    """persistent device trajectory (no per-call gather / PCIe) and rollout + linearisation on the device."""
+    model = rd.Quadrotor()
+    dmodel = rd.DiscretizedDynamics(model, rd.RK4)
+    om = o.quadrotor()
+    rng = np.random.default_rng(71)
+    K = 65
+    Zh = rd.SampledTrajectory(rand_inputs(13, 4, K, rng)[:, :13], 0.5 + rng.random((K - 1, 4)), dt=0.02)
+    Zd = rd.DeviceTrajectory(Zh)
+    J = torch_.zeros((K, 17, 13), dtype=torch_.float64, device="cuda")
+    y = torch_.zeros((K, 13), dtype=torch_.float64, device="cuda")
+    rd.jacobian_(rd.StaticReturn(), rd.B200(), dmodel, J, y, Zd)
+    ref = o.discrete_jacobian(om, o.RK4, Zh.data, Zh.dts)
+    assert np.abs(J.cpu().numpy() - ref).max() < 1e-10
+    U2 = 0.5 + rng.random((K - 1, 4))
+    rd.setcontrols_(Zd, U2)                                       # H2D update of the controls only
+    rd.setcontrols_(Zh, U2)
+    rd.jacobian_(rd.StaticReturn(), rd.B200(), dmodel, J, y, Zd)
+    assert np.abs(J.cpu().numpy() - o.discrete_jacobian(om, o.RK4, Zh.data, Zh.dts)).max() < 1e-10
+    assert np.array_equal(Zd.to_host().data, Zh.data)
+    Jb = torch_.zeros((K, 16, 12), dtype=torch_.float64, device="cuda")
+    rd.discrete_error_jacobian_(dmodel, Jb, None, Zd)
+    assert np.abs(o.as_matrix(Jb.cpu().numpy()) - _error_jacobian_ref(om, o.RK4, Zh.data, Zh.dts)).max() < 1e-10
+    # many trajectories: forward pass + linearisation, all on the device
+    ntraj = 96
+    x0 = rand_inputs(13, 4, ntraj, rng)[:, :13].copy()
+    U = 0.5 + rng.random((ntraj, K - 1, 4))
+    X, Jt = rd.rollout_and_linearize(dmodel, dev(torch_, x0), dev(torch_, U), 0.02)
+    Xo = o.rollout(om, o.RK4, x0, U, 0.02)
+    assert np.abs(X.cpu().numpy() - Xo).max() < 1e-10 * max(1.0, np.abs(Xo).max())
+    Zo = np.concatenate([Xo[:, :-1], U], axis=2).reshape(-1, 17)
+    assert np.abs(Jt.cpu().numpy().reshape(-1, 17, 13) - o.discrete_jacobian(om, o.RK4, Zo, 0.02)).max() < 1e-8
+    Xh, Jh = rd.rollout_and_linearize(dmodel, x0, U, 0.02, error_state=True)        # host arrays, error-state form
+    assert Jh.shape == (ntraj, K - 1, 16, 12) and np.abs(Xh - Xo).max() < 1e-10 * max(1.0, np.abs(Xo).max())
