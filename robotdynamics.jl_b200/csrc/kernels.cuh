@@ -133,10 +133,10 @@ __device__ __forceinline__ auto seed_att(T v, T g3, T g4, T g5) {
     constexpr mask_t M = CHUNK & mask_t(0x38);
     if constexpr (M == 0) return v;
     else {
-        SD<T, M> r; r.v = v;
-        if constexpr (chas(M, 3)) r.d[cslot(M, 3)] = g3;
-        if constexpr (chas(M, 4)) r.d[cslot(M, 4)] = g4;
-        if constexpr (chas(M, 5)) r.d[cslot(M, 5)] = g5;
+        SD<T, M> r; r.v = v; r.zero_parts();
+        if constexpr (chas(M, 3)) r.template set_part<3>(g3);
+        if constexpr (chas(M, 4)) r.template set_part<4>(g4);
+        if constexpr (chas(M, 5)) r.template set_part<5>(g5);
         return r;
     }
 }

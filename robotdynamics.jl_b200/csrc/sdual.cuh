@@ -34,17 +34,74 @@ template <class T> using ident_t = typename ident<T>::type;
 struct Zero {};
 
 // ---------------------------------------------------------------------------------------------
+// Partial storage.  double: one partial per slot.  float: TWO partials per slot (columns 2p, 2p+1 share a float2) so that
+// all partial arithmetic issues as packed fp32x2 instructions (Blackwell `fma.rn.f32x2` / `add.f32x2` / `mul.f32x2`, SASS
+// FFMA2/FADD2/FMUL2): same FMA-pipe flops as scalar FFMA (measured 125 vs 126 FMA/clk/SM, scripts/micro/fma_rate.cu) for HALF
+// the issue slots — and the rigid-body Jacobian kernels are issue-bound.  A slot whose other column is structurally zero
+// carries an explicit 0 in that lane (lane-wise linear arithmetic keeps it 0; it is never read).
+// ---------------------------------------------------------------------------------------------
+#ifndef RDB_PACK_F32
+#define RDB_PACK_F32 0   // measured slower on the quadrotor RK4 kernel (59.3 vs 51.1 us): padded lanes + pair alignment, see profiles/tuning_r01.md
+#endif
+template <class T> struct PK {
+    using vec = T;
+    static constexpr int W = 1;
+    RDB_HD static vec splat(T s) { return s; }
+    RDB_HD static vec zero() { return T(0); }
+    RDB_HD static vec add(vec a, vec b) { return a + b; }
+    RDB_HD static vec sub(vec a, vec b) { return a - b; }
+    RDB_HD static vec mul(vec a, vec b) { return a * b; }
+    RDB_HD static vec fma(vec a, vec b, vec c) { return a * b + c; }      // contracted to one FMA by nvcc
+    RDB_HD static vec neg(vec a) { return -a; }
+    RDB_HD static vec sel(bool on, vec a) { return on ? a : T(0); }
+    template <int L> RDB_HD static T lane(vec a) { return a; }
+    template <int L> RDB_HD static void set_lane(vec& a, T v) { a = v; }
+};
+#if RDB_PACK_F32 && defined(__CUDA_ARCH__)
+template <> struct PK<float> {
+    using vec = float2;
+    static constexpr int W = 2;
+    RDB_HD static vec splat(float s) { return make_float2(s, s); }
+    RDB_HD static vec zero() { return make_float2(0.0f, 0.0f); }
+    RDB_HD static vec add(vec a, vec b) { return __fadd2_rn(a, b); }
+    RDB_HD static vec sub(vec a, vec b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+    RDB_HD static vec mul(vec a, vec b) { return __fmul2_rn(a, b); }
+    RDB_HD static vec fma(vec a, vec b, vec c) { return __ffma2_rn(a, b, c); }
+    RDB_HD static vec neg(vec a) { return make_float2(-a.x, -a.y); }
+    RDB_HD static vec sel(bool on, vec a) { return on ? a : make_float2(0.0f, 0.0f); }
+    template <int L> RDB_HD static float lane(vec a) { return L == 0 ? a.x : a.y; }
+    template <int L> RDB_HD static void set_lane(vec& a, float v) { if (L == 0) a.x = v; else a.y = v; }
+};
+#endif
+// slot mask of a column mask: bit p <-> slot p
+template <class T> __host__ __device__ constexpr mask_t smask(mask_t m) {
+    if (PK<T>::W == 1) return m;
+    mask_t r = 0;
+    for (int p = 0; p < 16; ++p) if ((m >> (2 * p)) & 3u) r |= mask_t(1) << p;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sparse dual number.
 // ---------------------------------------------------------------------------------------------
 template <class T, mask_t M>
 struct SD {
     static_assert(M != 0, "SD needs at least one partial; use plain T otherwise");
+    using P = PK<T>;
     static constexpr mask_t mask = M;
+    static constexpr mask_t slots = smask<T>(M);
+    static constexpr int NS = cpopc(smask<T>(M));
     T v;
-    T d[cpopc(M)];
+    typename P::vec d[NS];
     template <int J> RDB_HD T part() const {
-        if constexpr (chas(M, J)) return d[cslot(M, J)]; else return T(0);
+        if constexpr (chas(M, J)) return P::template lane<J % P::W>(d[cslot(slots, J / P::W)]); else return T(0);
     }
+    // overwrite partial J (J must belong to M)
+    template <int J> RDB_HD void set_part(T val) {
+        static_assert(chas(M, J), "set_part: column not in mask");
+        P::template set_lane<J % P::W>(d[cslot(slots, J / P::W)], val);
+    }
+    RDB_HD void zero_parts() { for (int i = 0; i < NS; ++i) d[i] = P::zero(); }
 };
 
 template <class X> struct is_sd : std::false_type {};
@@ -55,52 +112,47 @@ template <class T, mask_t M> struct mask_of<SD<T, M>> { static constexpr mask_t 
 template <class T> RDB_HD T val(const T& a) { return a; }
 template <class T, mask_t M> RDB_HD T val(const SD<T, M>& a) { return a.v; }
 
-// compile-time loop over the set bits of a mask:  f(std::integral_constant<int,j>)
-template <mask_t M, int J = 0, class F>
-RDB_HD void for_bits(F&& f) {
-    if constexpr ((M >> J) != 0) {
-        if constexpr (chas(M, J)) f(std::integral_constant<int, J>{});
-        for_bits<M, J + 1>(f);
-    }
-}
-
-// ---- SD (+,-) SD --------------------------------------------------------------------------------
+// ---- slot-wise kernels of the binary operations (SA, SB: slot masks of the operands; result slots = SA | SB) -----------
 template <class T, mask_t A, mask_t B, int J = 0>
 RDB_HD void add_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
-    if constexpr (((A | B) >> J) != 0) {
-        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] + b.d[cslot(B, J)];
-        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)];
-        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = b.d[cslot(B, J)];
+    constexpr mask_t SA = smask<T>(A), SB = smask<T>(B), SR = SA | SB;
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SA, J) && chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::add(a.d[cslot(SA, J)], b.d[cslot(SB, J)]);
+        else if constexpr (chas(SA, J)) r.d[cslot(SR, J)] = a.d[cslot(SA, J)];
+        else if constexpr (chas(SB, J)) r.d[cslot(SR, J)] = b.d[cslot(SB, J)];
         add_parts<T, A, B, J + 1>(r, a, b);
     }
 }
 template <class T, mask_t A, mask_t B, int J = 0>
 RDB_HD void sub_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
-    if constexpr (((A | B) >> J) != 0) {
-        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] - b.d[cslot(B, J)];
-        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)];
-        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = -b.d[cslot(B, J)];
+    constexpr mask_t SA = smask<T>(A), SB = smask<T>(B), SR = SA | SB;
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SA, J) && chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::sub(a.d[cslot(SA, J)], b.d[cslot(SB, J)]);
+        else if constexpr (chas(SA, J)) r.d[cslot(SR, J)] = a.d[cslot(SA, J)];
+        else if constexpr (chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::neg(b.d[cslot(SB, J)]);
         sub_parts<T, A, B, J + 1>(r, a, b);
     }
 }
-// r.d = a.d * bv + b.d * av
+// r.d = a.d * bv + b.d * av     (av, bv pre-splatted)
 template <class T, mask_t A, mask_t B, int J = 0>
-RDB_HD void mul_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b) {
-    if constexpr (((A | B) >> J) != 0) {
-        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * b.v + b.d[cslot(B, J)] * a.v;
-        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * b.v;
-        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = b.d[cslot(B, J)] * a.v;
-        mul_parts<T, A, B, J + 1>(r, a, b);
+RDB_HD void mul_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b, typename PK<T>::vec av, typename PK<T>::vec bv) {
+    constexpr mask_t SA = smask<T>(A), SB = smask<T>(B), SR = SA | SB;
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SA, J) && chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::fma(b.d[cslot(SB, J)], av, PK<T>::mul(a.d[cslot(SA, J)], bv));
+        else if constexpr (chas(SA, J)) r.d[cslot(SR, J)] = PK<T>::mul(a.d[cslot(SA, J)], bv);
+        else if constexpr (chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::mul(b.d[cslot(SB, J)], av);
+        mul_parts<T, A, B, J + 1>(r, a, b, av, bv);
     }
 }
-// r.d = (a.d - q * b.d) * ib        (q = a/b, ib = 1/b)
+// r.d = (a.d - q * b.d) * ib  =  a.d * ib + b.d * (-q * ib)        (ib = 1/b, q = a/b; ibv, nqib pre-splatted)
 template <class T, mask_t A, mask_t B, int J = 0>
-RDB_HD void div_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b, T q, T ib) {
-    if constexpr (((A | B) >> J) != 0) {
-        if constexpr (chas(A, J) && chas(B, J)) r.d[cslot(A | B, J)] = (a.d[cslot(A, J)] - q * b.d[cslot(B, J)]) * ib;
-        else if constexpr (chas(A, J)) r.d[cslot(A | B, J)] = a.d[cslot(A, J)] * ib;
-        else if constexpr (chas(B, J)) r.d[cslot(A | B, J)] = -(q * b.d[cslot(B, J)]) * ib;
-        div_parts<T, A, B, J + 1>(r, a, b, q, ib);
+RDB_HD void div_parts(SD<T, (A | B)>& r, const SD<T, A>& a, const SD<T, B>& b, typename PK<T>::vec ibv, typename PK<T>::vec nqib) {
+    constexpr mask_t SA = smask<T>(A), SB = smask<T>(B), SR = SA | SB;
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SA, J) && chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::fma(b.d[cslot(SB, J)], nqib, PK<T>::mul(a.d[cslot(SA, J)], ibv));
+        else if constexpr (chas(SA, J)) r.d[cslot(SR, J)] = PK<T>::mul(a.d[cslot(SA, J)], ibv);
+        else if constexpr (chas(SB, J)) r.d[cslot(SR, J)] = PK<T>::mul(b.d[cslot(SB, J)], nqib);
+        div_parts<T, A, B, J + 1>(r, a, b, ibv, nqib);
     }
 }
 
@@ -109,23 +161,29 @@ RDB_HD SD<T, (A | B)> operator+(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A
 template <class T, mask_t A, mask_t B>
 RDB_HD SD<T, (A | B)> operator-(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A | B)> r; r.v = a.v - b.v; sub_parts<T, A, B>(r, a, b); return r; }
 template <class T, mask_t A, mask_t B>
-RDB_HD SD<T, (A | B)> operator*(const SD<T, A>& a, const SD<T, B>& b) { SD<T, (A | B)> r; r.v = a.v * b.v; mul_parts<T, A, B>(r, a, b); return r; }
+RDB_HD SD<T, (A | B)> operator*(const SD<T, A>& a, const SD<T, B>& b) {
+    SD<T, (A | B)> r; r.v = a.v * b.v; mul_parts<T, A, B>(r, a, b, PK<T>::splat(a.v), PK<T>::splat(b.v)); return r;
+}
 template <class T, mask_t A, mask_t B>
 RDB_HD SD<T, (A | B)> operator/(const SD<T, A>& a, const SD<T, B>& b) {
-    SD<T, (A | B)> r; const T ib = T(1) / b.v; r.v = a.v * ib; div_parts<T, A, B>(r, a, b, r.v, ib); return r;
+    SD<T, (A | B)> r; const T ib = T(1) / b.v; r.v = a.v * ib;
+    div_parts<T, A, B>(r, a, b, PK<T>::splat(ib), PK<T>::splat(-(r.v * ib))); return r;
 }
 
 // ---- SD with scalar -----------------------------------------------------------------------------
-template <class T, mask_t A> RDB_HD SD<T, A> operator-(const SD<T, A>& a) { SD<T, A> r; r.v = -a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = -a.d[i]; return r; }
+template <class T, mask_t A> RDB_HD SD<T, A> scale_parts(const SD<T, A>& a, T value, T s) {
+    SD<T, A> r; r.v = value; const auto sv = PK<T>::splat(s); for (int i = 0; i < SD<T, A>::NS; ++i) r.d[i] = PK<T>::mul(a.d[i], sv); return r;
+}
+template <class T, mask_t A> RDB_HD SD<T, A> operator-(const SD<T, A>& a) { SD<T, A> r; r.v = -a.v; for (int i = 0; i < SD<T, A>::NS; ++i) r.d[i] = PK<T>::neg(a.d[i]); return r; }
 template <class T, mask_t A> RDB_HD SD<T, A> operator+(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r = a; r.v = a.v + b; return r; }
 template <class T, mask_t A> RDB_HD SD<T, A> operator+(ident_t<T> b, const SD<T, A>& a) { SD<T, A> r = a; r.v = b + a.v; return r; }
 template <class T, mask_t A> RDB_HD SD<T, A> operator-(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r = a; r.v = a.v - b; return r; }
-template <class T, mask_t A> RDB_HD SD<T, A> operator-(ident_t<T> b, const SD<T, A>& a) { SD<T, A> r; r.v = b - a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = -a.d[i]; return r; }
-template <class T, mask_t A> RDB_HD SD<T, A> operator*(const SD<T, A>& a, ident_t<T> b) { SD<T, A> r; r.v = a.v * b; for (int i = 0; i < cpopc(A); ++i) r.d[i] = a.d[i] * b; return r; }
-template <class T, mask_t A> RDB_HD SD<T, A> operator*(ident_t<T> b, const SD<T, A>& a) { return a * b; }
-template <class T, mask_t A> RDB_HD SD<T, A> operator/(const SD<T, A>& a, ident_t<T> b) { return a * (T(1) / b); }
+template <class T, mask_t A> RDB_HD SD<T, A> operator-(ident_t<T> b, const SD<T, A>& a) { return scale_parts<T, A>(a, b - a.v, T(-1)); }
+template <class T, mask_t A> RDB_HD SD<T, A> operator*(const SD<T, A>& a, ident_t<T> b) { return scale_parts<T, A>(a, a.v * b, b); }
+template <class T, mask_t A> RDB_HD SD<T, A> operator*(ident_t<T> b, const SD<T, A>& a) { return scale_parts<T, A>(a, a.v * b, b); }
+template <class T, mask_t A> RDB_HD SD<T, A> operator/(const SD<T, A>& a, ident_t<T> b) { const T ib = T(1) / b; return scale_parts<T, A>(a, a.v * ib, ib); }
 template <class T, mask_t A> RDB_HD SD<T, A> operator/(ident_t<T> b, const SD<T, A>& a) {
-    SD<T, A> r; const T ib = T(1) / a.v; r.v = b * ib; const T s = -r.v * ib; for (int i = 0; i < cpopc(A); ++i) r.d[i] = a.d[i] * s; return r;
+    const T ib = T(1) / a.v; const T q = b * ib; return scale_parts<T, A>(a, q, -q * ib);
 }
 
 // ---- Zero algebra -------------------------------------------------------------------------------
@@ -145,14 +203,17 @@ RDB_HD void sincos_(float a, float& s, float& c) { sincosf(a, &s, &c); }
 RDB_HD void sincos_(double a, double& s, double& c) { sincos(a, &s, &c); }
 template <class T, mask_t A>
 RDB_HD void sincos_(const SD<T, A>& a, SD<T, A>& s, SD<T, A>& c) {
-    sincos_(a.v, s.v, c.v);
-    for (int i = 0; i < cpopc(A); ++i) { s.d[i] = c.v * a.d[i]; c.d[i] = -(s.v * a.d[i]); }
+    T sv, cv;
+    sincos_(a.v, sv, cv);
+    const auto cs = PK<T>::splat(cv), ns = PK<T>::splat(-sv);
+    for (int i = 0; i < SD<T, A>::NS; ++i) { s.d[i] = PK<T>::mul(a.d[i], cs); c.d[i] = PK<T>::mul(a.d[i], ns); }
+    s.v = sv; c.v = cv;
 }
 RDB_HD float rsqrt_(float a) { return 1.0f / sqrtf(a); }
 RDB_HD double rsqrt_(double a) { return 1.0 / sqrt(a); }
 template <class T, mask_t A>
 RDB_HD SD<T, A> rsqrt_(const SD<T, A>& a) {   // a^(-1/2);  d = -1/2 a^(-3/2) da
-    SD<T, A> r; r.v = rsqrt_(a.v); const T s = T(-0.5) * r.v / a.v; for (int i = 0; i < cpopc(A); ++i) r.d[i] = s * a.d[i]; return r;
+    const T r = rsqrt_(a.v); return scale_parts<T, A>(a, r, T(-0.5) * r / a.v);
 }
 // max(0, a): ForwardDiff compares values; derivative is 0 when the clamp is active or at exactly 0
 // (reference: test/quadrotor.jl:67-70).
@@ -160,7 +221,7 @@ RDB_HD float relu_(float a) { return a > 0.0f ? a : 0.0f; }
 RDB_HD double relu_(double a) { return a > 0.0 ? a : 0.0; }
 template <class T, mask_t A>
 RDB_HD SD<T, A> relu_(const SD<T, A>& a) {
-    SD<T, A> r; const bool on = a.v > T(0); r.v = on ? a.v : T(0); for (int i = 0; i < cpopc(A); ++i) r.d[i] = on ? a.d[i] : T(0); return r;
+    SD<T, A> r; const bool on = a.v > T(0); r.v = on ? a.v : T(0); for (int i = 0; i < SD<T, A>::NS; ++i) r.d[i] = PK<T>::sel(on, a.d[i]); return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,7 +284,7 @@ template <class T, class A> RDB_HD auto mat3_mul(const T* M, const A& x) {
 // element I of [x;u]: a seeded dual if column I belongs to this thread's column chunk, a plain T otherwise
 template <class T, int I, mask_t CHUNK>
 RDB_HD auto seed(T z) {
-    if constexpr (chas(CHUNK, I)) { SD<T, (mask_t(1) << I)> r; r.v = z; r.d[0] = T(1); return r; }
+    if constexpr (chas(CHUNK, I)) { SD<T, (mask_t(1) << I)> r; r.v = z; r.zero_parts(); r.template set_part<I>(T(1)); return r; }
     else return z;
 }
 template <int J, class T> RDB_HD T partial(const T&) { return T(0); }
@@ -238,11 +299,12 @@ template <class T> struct widen_to {   // plain target
     RDB_HD static T from(const T& a) { return a; }
 };
 template <class T, mask_t B> struct widen_to<SD<T, B>> {
-    RDB_HD static SD<T, B> from(const T& a) { SD<T, B> r; r.v = a; for (int i = 0; i < cpopc(B); ++i) r.d[i] = T(0); return r; }
+    RDB_HD static SD<T, B> from(const T& a) { SD<T, B> r; r.v = a; r.zero_parts(); return r; }
     template <mask_t A, int J = 0>
     RDB_HD static void fill(SD<T, B>& r, const SD<T, A>& a) {
-        if constexpr ((B >> J) != 0) {
-            if constexpr (chas(B, J)) { if constexpr (chas(A, J)) r.d[cslot(B, J)] = a.d[cslot(A, J)]; else r.d[cslot(B, J)] = T(0); }
+        constexpr mask_t SA = smask<T>(A), SB = smask<T>(B);
+        if constexpr ((SB >> J) != 0) {
+            if constexpr (chas(SB, J)) { if constexpr (chas(SA, J)) r.d[cslot(SB, J)] = a.d[cslot(SA, J)]; else r.d[cslot(SB, J)] = PK<T>::zero(); }
             fill<A, J + 1>(r, a);
         }
     }

@@ -27,17 +27,10 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
 
 VARIANTS = {
     "quadrotor": {
-        "base": {},
-        "roll1": dict(RDB_TUNE_ROLL=1),
-        "roll2": dict(RDB_TUNE_ROLL=2),
-        "roll1_2r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
-        "roll2_2r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
-        "roll1_2rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0x1F800u"),
-        "roll2_2rb": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0x1F800u"),
-        "roll1_2r_t128": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
-        "roll2_2r_t32": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=32, RDB_TUNE_MINB=4, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
-        "roll1_3rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x3C00u", RDB_TUNE_C2="0x1C000u"),
-        "roll2_1r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=4, RDB_TUNE_C0="0x1FFFFu"),
+        "pack0": dict(RDB_PACK_F32=0),
+        "pack1": dict(RDB_PACK_F32=1),
+        "pack1_3r": dict(RDB_PACK_F32=1, RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFu", RDB_TUNE_C1="0x3F00u", RDB_TUNE_C2="0x1C000u"),
+        "pack1_2rb": dict(RDB_PACK_F32=1, RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1FC00u"),
     },
     "quadbody": {
         "base": {},
