@@ -40,7 +40,7 @@ typedef enum { RDB_AOS = 0, RDB_SOA = 1 } rdb_layout;
 typedef enum { RDB_EULER = 0, RDB_RK2 = 1, RDB_RK3 = 2, RDB_RK4 = 3 } rdb_integrator;
 /* model families: test/cartpole_model.jl, test/quadrotor.jl, test/rigidbody_test.jl:23-56 (= the Satellite of
  * examples/single_satellite.jl:7-35 with other parameters), test/double_integrator.jl:97-127 */
-typedef enum { RDB_CARTPOLE = 0, RDB_QUADROTOR = 1, RDB_BODY = 2, RDB_DOUBLE_INTEGRATOR = 3 } rdb_model_kind;
+typedef enum { RDB_CARTPOLE = 0, RDB_QUADROTOR = 1, RDB_BODY = 2, RDB_DOUBLE_INTEGRATOR = 3, RDB_CUSTOM = 4 } rdb_model_kind;
 /* rotation parameterisation R of RigidBody{R} (src/liestate.jl:42-46) and velocity_frame (src/rigidbody.jl:258) */
 typedef enum { RDB_ROT_NONE = 0, RDB_ROT_QUAT = 1, RDB_ROT_MRP = 2, RDB_ROT_RP = 3 } rdb_rot;
 typedef enum { RDB_FRAME_WORLD = 0, RDB_FRAME_BODY = 1 } rdb_frame;
@@ -50,7 +50,8 @@ typedef enum {
     RDB_ERR_ARG = -1,            /* bad enum / NULL / negative size        -> Julia ArgumentError           */
     RDB_ERR_NOT_IMPLEMENTED = -2, /* combination has no kernel              -> RobotDynamics.NotImplementedError (src/utils.jl:1-8) */
     RDB_ERR_POINTER_MIX = -3,    /* host and device data pointers mixed in one call                         */
-    RDB_ERR_NO_DEVICE = -4       /* no CUDA device / library built without the kernels                      */
+    RDB_ERR_NO_DEVICE = -4,      /* no CUDA device / library built without the kernels                      */
+    RDB_ERR_COMPILE = -5         /* user model source does not compile (rdb_last_log() has the NVRTC log)   */
 } rdb_status;
 
 int rdb_version(void);
@@ -68,6 +69,18 @@ void rdb_host_free(void* p);
  *   BODY              [mass, J(9, row-major)]                                  test/rigidbody_test.jl:53-54
  *   DOUBLE_INTEGRATOR [D]  (1..3)                                              test/double_integrator.jl:97-100 */
 int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const double* params, int nparams, rdb_model** model);
+/* User-defined model: any `dynamics(model, x, u)` (src/dynamics.jl:81-83), differentiated exactly by forward mode like the
+ * reference's `@autodiff`-generated ForwardAD methods (src/jacobian_gen.jl:485-529).  f_body is the BODY of
+ *     template <class X, class U> auto f(const X& x, const U& u) const
+ * in CUDA C++ against csrc/sdual.cuh: read inputs with get<i>(x), get<j>(u), parameters with p[k], write constants as T(0.5),
+ * use sin_/cos_/sincos_/exp_/sqrt_/relu_ and + - * /, and `return vec(xdot_0, ..., xdot_{n-1});`.  EuclideanState only
+ * (errstate maps are identities), n + m <= 32.  Compiled with NVRTC for sm_100a at creation (syntax) and on first use per
+ * (operation, integrator, dtype); works with every batch entry point below except rdb_discrete_error_jacobian's G-seeding
+ * (which degenerates to rdb_discrete_jacobian for Euclidean states anyway). */
+int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, const double* params, int nparams, rdb_model** model);
+/* compile-only check of a user model body (needs no GPU); on failure rdb_last_log() returns the compiler log */
+int rdb_custom_check(int n, int m, const char* f_body, int nparams, int dtype);
+const char* rdb_last_log(void);
 int rdb_model_destroy(rdb_model* model);
 /* state_dim / control_dim / errstate_dim  (src/functionbase.jl:124-135, src/liestate.jl:124) */
 int rdb_model_dims(const rdb_model* model, int* n, int* m, int* nerr);

@@ -21,16 +21,16 @@ LIB_PATH = os.environ.get("RDB200_LIB") or os.path.join(_PKG, "librdb200.so")   
 F32, F64 = 0, 1
 AOS, SOA = 0, 1
 EULER, RK2, RK3, RK4 = 0, 1, 2, 3
-CARTPOLE, QUADROTOR, BODY, DOUBLE_INTEGRATOR = 0, 1, 2, 3
+CARTPOLE, QUADROTOR, BODY, DOUBLE_INTEGRATOR, CUSTOM = 0, 1, 2, 3, 4
 ROT_NONE, ROT_QUAT, ROT_MRP, ROT_RP = 0, 1, 2, 3
 FRAME_WORLD, FRAME_BODY = 0, 1
 
-ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE = -1, -2, -3, -4
+ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE, ERR_COMPILE = -1, -2, -3, -4, -5
 
 # every symbol include/rdb200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free",
-    "rdb_model_create", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
+    "rdb_model_create", "rdb_model_create_custom", "rdb_custom_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
 )
@@ -67,6 +67,9 @@ def lib():
         L.rdb_host_alloc.argtypes = [ctypes.c_size_t]
         L.rdb_host_free.argtypes = [vp]
         L.rdb_model_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
+        L.rdb_model_create_custom.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
+        L.rdb_custom_check.argtypes = [i32, i32, ctypes.c_char_p, i32, i32]
+        L.rdb_last_log.restype = ctypes.c_char_p
         L.rdb_model_destroy.argtypes = [vp]
         L.rdb_model_dims.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.rdb_dynamics.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp]
@@ -87,8 +90,16 @@ def strerror(code):
 
 
 def check(rc, what):
+    if rc == ERR_COMPILE:
+        raise RDBError(rc, what + "\n" + lib().rdb_last_log().decode(errors="replace")[-3000:])
     if rc != 0:
         raise (NotImplementedModelError if rc == ERR_NOT_IMPLEMENTED else RDBError)(rc, what)
+
+
+def custom_check(n, m, body, nparams=0, dtype=F64):
+    """Compile-only check of a user model body (no GPU needed).  Returns (ok, compiler log)."""
+    rc = lib().rdb_custom_check(int(n), int(m), body.encode(), int(nparams), int(dtype))
+    return rc == 0, lib().rdb_last_log().decode(errors="replace")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -206,14 +217,19 @@ class PinnedArray:
 class ModelHandle:
     """rdb_model: (kind, rot, frame, params) bound to a context."""
 
-    def __init__(self, kind, rot, frame, params, device=None):
+    def __init__(self, kind, rot, frame, params, device=None, custom=None):
         self.ctx = context(device)
         self.kind, self.rot, self.frame = int(kind), int(rot), int(frame)
         self.params = np.ascontiguousarray(params, dtype=np.float64)
         self._h = ctypes.c_void_p()
-        check(lib().rdb_model_create(self.ctx._h, self.kind, self.rot, self.frame,
-                                     self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(self.params),
-                                     ctypes.byref(self._h)), "rdb_model_create")
+        pp = self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if custom is not None:                         # (n, m, body of f): NVRTC-compiled user model
+            n, m, body = custom
+            check(lib().rdb_model_create_custom(self.ctx._h, int(n), int(m), body.encode(), pp, len(self.params),
+                                                ctypes.byref(self._h)), "rdb_model_create_custom")
+        else:
+            check(lib().rdb_model_create(self.ctx._h, self.kind, self.rot, self.frame, pp, len(self.params),
+                                         ctypes.byref(self._h)), "rdb_model_create")
         n, m, ne = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         check(lib().rdb_model_dims(self._h, ctypes.byref(n), ctypes.byref(m), ctypes.byref(ne)), "rdb_model_dims")
         self.n, self.m, self.nerr = n.value, m.value, ne.value

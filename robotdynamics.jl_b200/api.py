@@ -118,6 +118,14 @@ class Satellite(Body):
         super().__init__(R, 1.0, (1.0, 1.0, 1.0), bodyframe, device)
 
 
+class CustomModel(ContinuousDynamics):
+    """Any user `dynamics(model, x, u)`: `body` is the CUDA C++ body of `f(x, u)` written against csrc/sdual.cuh
+    (get<i>(x), get<j>(u), p[k], T(c), sin_/cos_/exp_/sqrt_/relu_, `return vec(...)`), compiled with NVRTC and differentiated
+    by the same forward-mode engine — the GPU counterpart of putting `@autodiff` on a model (src/jacobian_gen.jl:64-82)."""
+    def __init__(self, n, m, body, params=(), device=None):
+        self._h = _abi.ModelHandle(_abi.CUSTOM, _abi.ROT_NONE, 0, params, device, custom=(n, m, body))
+
+
 class DiscreteDynamics(AbstractModel): pass
 
 

@@ -10,6 +10,7 @@
 #include "rdb200.h"
 #include "units.h"
 #include "lie.h"
+#include "custom.h"
 
 using namespace rdb;
 
@@ -38,6 +39,7 @@ struct rdb_model {
     int kind, rot, frame, D;
     int n, m, nerr;
     ModelParams<double> p;
+    CustomModel* custom;   // kind == RDB_CUSTOM: NVRTC-compiled user model (custom.cu)
 };
 
 namespace {
@@ -109,14 +111,20 @@ int map_q(int integrator) {
     return -1;
 }
 
+// built-in models go to their compilation unit, user models to the NVRTC path
+int dispatch(const rdb_model* M, int dtype, KnotRequest* r) {
+    if (M->kind == RDB_CUSTOM) return custom_run(M->custom, *r);
+    UnitFn fn = find_unit(M->kind, M->rot, M->frame, M->D, dtype);
+    return fn ? fn(r) : RDB_ERR_NOT_IMPLEMENTED;
+}
+
 // The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
 int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* dt,
             double dt0, void* J, void* out, void* stream, int err = 0) {
     if (!M || N < 0 || (dtype != RDB_F32 && dtype != RDB_F64) || (layout != RDB_AOS && layout != RDB_SOA)) return RDB_ERR_ARG;
     if (N == 0) return 0;
     if (!Z || (with_j && !J) || (!with_j && !out)) return RDB_ERR_ARG;
-    UnitFn fn = find_unit(M->kind, M->rot, M->frame, M->D, dtype);
-    if (!fn) return RDB_ERR_NOT_IMPLEMENTED;
+    if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
     rdb_context* c = M->ctx;
     RDB_CUDA(cudaSetDevice(c->device));
     const int kind = classify({Z, dt, J, out});
@@ -129,7 +137,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     r.dt0 = dt0; r.layout = layout; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.Z = Z; r.dt = dt; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
-        return fn(&r);
+        return dispatch(M, dtype, &r);
     }
     // host pointers: H2D -> kernel -> D2H per chunk, chunks round-robin over NSLOT streams so the three overlap
     std::lock_guard<std::mutex> lock(c->mu);
@@ -149,7 +157,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
         if (dt && (rc = cuda_rc(cudaMemcpyAsync(s.buf[B_DT], dt + k0, size_t(cnt) * 8, cudaMemcpyHostToDevice, s.st)))) break;
         r.Z = s.buf[B_Z]; r.dt = dt ? (const double*)s.buf[B_DT] : nullptr;
         r.J = J ? s.buf[B_J] : nullptr; r.out = out ? s.buf[B_OUT] : nullptr; r.N = cnt; r.stream = s.st;
-        if ((rc = fn(&r))) break;
+        if ((rc = dispatch(M, dtype, &r))) break;
         if (J && (rc = copy_chunk(J, s.buf[B_J], layout, es, E, N, k0, cnt, cudaMemcpyDeviceToHost, s.st))) break;
         if (out && (rc = copy_chunk(out, s.buf[B_OUT], layout, es, n, N, k0, cnt, cudaMemcpyDeviceToHost, s.st))) break;
     }
@@ -185,6 +193,7 @@ const char* rdb_strerror(int code) {
         case RDB_ERR_NOT_IMPLEMENTED: return "not implemented for this model / integrator / dtype";
         case RDB_ERR_POINTER_MIX: return "host and device data pointers mixed in one call";
         case RDB_ERR_NO_DEVICE: return "no CUDA device available";
+        case RDB_ERR_COMPILE: return "user model failed to compile (see rdb_last_log())";
     }
     if (code > 0) return cudaGetErrorString(cudaError_t(code));
     return "unknown rdb200 status";
@@ -267,7 +276,31 @@ int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const doubl
     return 0;
 }
 
-int rdb_model_destroy(rdb_model* m) { delete m; return 0; }
+int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, const double* params, int np, rdb_model** model) {
+    if (!ctx || !model || !f_body || n < 1 || m < 1 || n + m > 32 || np < 0 || (np > 0 && !params)) return RDB_ERR_ARG;
+    *model = nullptr;
+    // fail at creation, with a readable log, rather than at the first evaluation
+    if (custom_check(n, m, f_body, np, RDB_F64) != 0) return RDB_ERR_COMPILE;
+    rdb_model M;
+    std::memset(&M, 0, sizeof(M));
+    M.ctx = ctx; M.kind = RDB_CUSTOM; M.rot = RDB_ROT_NONE; M.n = n; M.m = m; M.nerr = n;
+    M.custom = custom_create(n, m, f_body, params, np);
+    if (!M.custom) return RDB_ERR_ARG;
+    *model = new (std::nothrow) rdb_model(M);
+    return *model ? 0 : RDB_ERR_ARG;
+}
+
+int rdb_custom_check(int n, int m, const char* f_body, int nparams, int dtype) {
+    return custom_check(n, m, f_body, nparams, dtype) == 0 ? 0 : RDB_ERR_COMPILE;
+}
+
+const char* rdb_last_log(void) { return custom_last_log(); }
+
+int rdb_model_destroy(rdb_model* m) {
+    if (m && m->custom) custom_destroy(m->custom);
+    delete m;
+    return 0;
+}
 
 int rdb_model_dims(const rdb_model* M, int* n, int* m, int* nerr) {
     if (!M) return RDB_ERR_ARG;
@@ -372,8 +405,7 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     if (!M || Q < 0 || ntraj < 0 || K < 1 || (dtype != RDB_F32 && dtype != RDB_F64)) return RDB_ERR_ARG;
     if (ntraj == 0) return 0;
     if (!x0 || !X || (K > 1 && !U)) return RDB_ERR_ARG;
-    UnitFn fn = find_unit(M->kind, M->rot, M->frame, M->D, dtype);
-    if (!fn) return RDB_ERR_NOT_IMPLEMENTED;
+    if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
     rdb_context* c = M->ctx;
     RDB_CUDA(cudaSetDevice(c->device));
     const int kind = classify({x0, U, dt, X});
@@ -384,7 +416,7 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.x0 = x0; r.U = U; r.dt = dt; r.X = X; r.stream = (cudaStream_t)stream;
-        return fn(&r);
+        return dispatch(M, dtype, &r);
     }
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t es = esize(dtype);
@@ -394,7 +426,7 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     r.dt = (const double*)st.in(B_DT, dt, size_t(ntraj) * K * 8);
     r.X = st.outbuf(B_J, size_t(ntraj) * K * M->n * es);
     r.stream = st.s.st;
-    if (!st.rc) st.rc = fn(&r);
+    if (!st.rc) st.rc = dispatch(M, dtype, &r);
     st.back(X, B_J, size_t(ntraj) * K * M->n * es);
     return st.finish();
 }

@@ -23,9 +23,9 @@ namespace rdb {
 // stalls on instruction fetch), at the price of explicit zeros in the early stages.
 template <class Model, class T, class X0, class U, class X>
 struct saturate_impl {
-    using F = decltype(std::declval<const Model&>().f(std::declval<const X&>(), std::declval<const U&>()));
-    using Next = decltype(axpy(std::declval<const X0&>(), std::declval<T>(), std::declval<const F&>()));
-    using type = typename std::conditional_t<std::is_same<Next, X>::value, ident<X>, saturate_impl<Model, T, X0, U, Next>>::type;
+    using F = decltype(rstd::declval<const Model&>().f(rstd::declval<const X&>(), rstd::declval<const U&>()));
+    using Next = decltype(axpy(rstd::declval<const X0&>(), rstd::declval<T>(), rstd::declval<const F&>()));
+    using type = typename rstd::conditional_t<rstd::is_same<Next, X>::value, ident<X>, saturate_impl<Model, T, X0, U, Next>>::type;
 };
 template <class Model, class T, class X0, class U> using saturated_t = typename saturate_impl<Model, T, X0, U, X0>::type;
 
@@ -33,7 +33,7 @@ template <class Model, class T, class X0, class U> using saturated_t = typename 
 template <int ROLL, class T, class Model, class X, class U>
 RDB_HD auto rk4_rolled(const Model& model, const X& x, const U& u, T h) {
     using XS = saturated_t<Model, T, X, U>;
-    using FS = decltype(model.f(std::declval<const XS&>(), u));
+    using FS = decltype(model.f(rstd::declval<const XS&>(), u));
     XS Xs;
     FS acc;
     int s0;

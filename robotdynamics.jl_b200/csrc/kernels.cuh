@@ -18,7 +18,9 @@
 //   * component-major ("SoA") callers, unaligned pointers and the ragged last tile use a cooperative
 //     coalesced copy between the same shared-memory images and global memory.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "integrators.cuh"
 
 namespace rdb {
@@ -68,7 +70,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // ---- compile-time helpers ---------------------------------------------------------------------------------
 template <mask_t... Ms> struct MaskList { static constexpr int count = int(sizeof...(Ms)); };
 template <class T, mask_t CHUNK, size_t... Is>
-__device__ __forceinline__ auto load_seeded(const T* zrow, std::index_sequence<Is...>) {
+__device__ __forceinline__ auto load_seeded(const T* zrow, rstd::index_sequence<Is...>) {
     return vec(seed<T, int(Is), CHUNK>(zrow[Is])...);
 }
 template <class T> __device__ __forceinline__ T plain(const T& a) { return a; }
@@ -78,27 +80,27 @@ template <class T, mask_t M> __device__ __forceinline__ T plain(const SD<T, M>& 
 __device__ __forceinline__ void st16(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 __device__ __forceinline__ void st16(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 template <int N_, int J, class XN, size_t... Ks>
-__device__ __forceinline__ void put_col_v(const XN& xn, float* col, std::index_sequence<Ks...>) {
+__device__ __forceinline__ void put_col_v(const XN& xn, float* col, rstd::index_sequence<Ks...>) {
     (st16(col + 4 * int(Ks), partial<J>(get<4 * int(Ks)>(xn)), partial<J>(get<4 * int(Ks) + 1>(xn)), partial<J>(get<4 * int(Ks) + 2>(xn)),
           partial<J>(get<4 * int(Ks) + 3>(xn))), ...);
 }
 template <int N_, int J, class XN, size_t... Ks>
-__device__ __forceinline__ void put_col_v(const XN& xn, double* col, std::index_sequence<Ks...>) {
+__device__ __forceinline__ void put_col_v(const XN& xn, double* col, rstd::index_sequence<Ks...>) {
     (st16(col + 2 * int(Ks), partial<J>(get<2 * int(Ks)>(xn)), partial<J>(get<2 * int(Ks) + 1>(xn))), ...);
 }
 template <int N_, mask_t CHUNK, int J, bool VEC, class T, class XN, size_t... Is>
-__device__ __forceinline__ void put_col(const XN& xn, T* jrow, std::index_sequence<Is...>) {
+__device__ __forceinline__ void put_col(const XN& xn, T* jrow, rstd::index_sequence<Is...>) {
     if constexpr (chas(CHUNK, J)) {
-        if constexpr (VEC) put_col_v<N_, J>(xn, jrow + N_ * J, std::make_index_sequence<size_t(N_ * sizeof(T) / 16)>{});
+        if constexpr (VEC) put_col_v<N_, J>(xn, jrow + N_ * J, rstd::make_index_sequence<size_t(N_ * sizeof(T) / 16)>{});
         else ((jrow[int(Is) + N_ * J] = partial<J>(get<int(Is)>(xn))), ...);
     }
 }
 template <int N_, mask_t CHUNK, bool VEC, class T, class XN, size_t... Js>
-__device__ __forceinline__ void put_cols(const XN& xn, T* jrow, std::index_sequence<Js...>) {
-    (put_col<N_, CHUNK, int(Js), VEC>(xn, jrow, std::make_index_sequence<size_t(N_)>{}), ...);
+__device__ __forceinline__ void put_cols(const XN& xn, T* jrow, rstd::index_sequence<Js...>) {
+    (put_col<N_, CHUNK, int(Js), VEC>(xn, jrow, rstd::make_index_sequence<size_t(N_)>{}), ...);
 }
 template <class T, class XN, size_t... Is>
-__device__ __forceinline__ void put_vals(const XN& xn, T* orow, std::index_sequence<Is...>) {
+__device__ __forceinline__ void put_vals(const XN& xn, T* orow, rstd::index_sequence<Is...>) {
     ((orow[Is] = plain(get<int(Is)>(xn))), ...);
 }
 
@@ -148,23 +150,23 @@ __device__ __forceinline__ auto seed_err(const T* z, const T (&G)[4][3]) {
     else return seed<T, I - (np - 3), CHUNK>(z[I]);
 }
 template <class Model, class T, mask_t CHUNK, size_t... Is>
-__device__ __forceinline__ auto load_seeded_err(const T* z, std::index_sequence<Is...>) {
+__device__ __forceinline__ auto load_seeded_err(const T* z, rstd::index_sequence<Is...>) {
     T G[4][3];
     att_grad<T, Model::rot>(z + 3, G);
     return vec(seed_err<Model, T, CHUNK, int(Is)>(z, G)...);
 }
-template <class T, class A, size_t... Is> __device__ __forceinline__ void plain_vals(const A& a, T* out, std::index_sequence<Is...>) { ((out[Is] = plain(get<int(Is)>(a))), ...); }
+template <class T, class A, size_t... Is> __device__ __forceinline__ void plain_vals(const A& a, T* out, rstd::index_sequence<Is...>) { ((out[Is] = plain(get<int(Is)>(a))), ...); }
 template <int J, class T, class A, size_t... Is>
-__device__ __forceinline__ auto contract_col(const T (&G)[4][3], const A& att, std::index_sequence<Is...>) { return ((G[Is][J] * get<int(Is)>(att)) + ...); }
+__device__ __forceinline__ auto contract_col(const T (&G)[4][3], const A& att, rstd::index_sequence<Is...>) { return ((G[Is][J] * get<int(Is)>(att)) + ...); }
 // rows of the result in error coordinates: [r+; G(x+)' att+; v+; w+]
 template <class Model, class T, class XN>
 __device__ __forceinline__ auto project_err(const XN& xn) {
     constexpr int np = Model::n - 9;
     auto att = slice<3, np>(xn);
     T p[4], G[4][3];
-    plain_vals(att, p, std::make_index_sequence<size_t(np)>{});
+    plain_vals(att, p, rstd::make_index_sequence<size_t(np)>{});
     att_grad<T, Model::rot>(p, G);
-    using Seq = std::make_index_sequence<size_t(np)>;
+    using Seq = rstd::make_index_sequence<size_t(np)>;
     return cat(slice<0, 3>(xn), vec(contract_col<0>(G, att, Seq{}), contract_col<1>(G, att, Seq{}), contract_col<2>(G, att, Seq{})),
                slice<3 + np, 6>(xn));
 }
@@ -182,18 +184,18 @@ template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
     if constexpr (ERR) {
-        auto zz = load_seeded_err<Model, T, CHUNK>(zrow, std::make_index_sequence<size_t(NZ)>{});
+        auto zz = load_seeded_err<Model, T, CHUNK>(zrow, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         auto e = project_err<Model, T>(xn);
         images_free_barrier<NTHR, ISSUERS>(tid);
-        put_cols<Model::nerr, CHUNK, VEC>(e, jrow, std::make_index_sequence<size_t(Model::nerr + m)>{});
-        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
+        put_cols<Model::nerr, CHUNK, VEC>(e, jrow, rstd::make_index_sequence<size_t(Model::nerr + m)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     } else {
-        auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, std::make_index_sequence<size_t(NZ)>{});
+        auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         images_free_barrier<NTHR, ISSUERS>(tid);
-        if constexpr (WITH_J) put_cols<n, CHUNK, VEC>(xn, jrow, std::make_index_sequence<size_t(NZ)>{});
-        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, std::make_index_sequence<size_t(n)>{}); }
+        if constexpr (WITH_J) put_cols<n, CHUNK, VEC>(xn, jrow, rstd::make_index_sequence<size_t(NZ)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     }
 }
 
@@ -242,6 +244,22 @@ __device__ __forceinline__ void coop_store(const T* img, int P, T* g, long long 
 }
 
 __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+// Dynamic shared memory of knot_kernel as a function of plain integers (jr x jc = Jacobian image shape, es = sizeof(T)); used by
+// KnotSmem below (static_assert) and by custom.cu, which only knows the dimensions of a user model at run time.
+__host__ __device__ constexpr bool knot_rowstore(int jr, int jc, bool with_j, int es) {
+    return with_j && jr >= 12 && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && cgcd(jr * jc * es / 4, 32) >= 16;
+}
+__host__ __device__ constexpr int knot_pitch(int jr, int jc, bool with_j, int es) {
+    const int E = jr * jc, u = (E * es + 15) / 16;
+    return knot_rowstore(jr, jc, with_j, es) ? ((u % 2 == 0) ? u + 1 : u) * 16 / es : E;
+}
+__host__ __device__ constexpr size_t knot_smem_total(int n, int m, int jr, int jc, int TILE, bool with_j, int es) {
+    const size_t a16 = 15;
+    const size_t in_b = (size_t(TILE) * size_t(n + m) * es + a16) & ~a16;
+    const size_t j_b = with_j ? ((size_t(TILE) * size_t(knot_pitch(jr, jc, with_j, es)) * es + a16) & ~a16) : 0;
+    const size_t o_b = (size_t(TILE) * size_t(n) * es + a16) & ~a16;
+    return 2 * in_b + j_b + o_b + 16;
+}
 template <class Model, int TILE, bool WITH_J, class T, bool ERR = false>
 struct KnotSmem {
     static constexpr int n = Model::n, NZ = Model::n + Model::m;
@@ -252,23 +270,23 @@ struct KnotSmem {
     // units) get a pitch of an ODD number of 16-byte units, write their columns with 16-byte stores (conflict-free) and leave
     // by one TMA bulk store PER KNOT ROW, issued by TILE threads in parallel.
     // (only when the dense image would be badly conflicted: >= 16 lanes per bank; the 8-way case E = 216 fp32 measured faster dense)
-    static constexpr bool ROWSTORE = WITH_J && JR >= 12 && (E % 2 == 0) && ((JR * sizeof(T)) % 16 == 0) &&
-                                     cgcd(int(E * sizeof(T) / 4), 32) >= 16;
-    static constexpr int units16 = int((E * sizeof(T) + 15) / 16);
-    static constexpr int PJ = ROWSTORE ? int(((units16 % 2 == 0) ? units16 + 1 : units16) * 16 / sizeof(T)) : E;
+    static constexpr bool ROWSTORE = knot_rowstore(JR, JC, WITH_J, int(sizeof(T)));
+    static constexpr int PJ = knot_pitch(JR, JC, WITH_J, int(sizeof(T)));
     static constexpr int ISSUERS = ROWSTORE ? TILE : 1;
     static constexpr size_t in_bytes = size_t(TILE) * NZ * sizeof(T);
     static constexpr size_t j_bytes = WITH_J ? size_t(TILE) * PJ * sizeof(T) : 0;
     static constexpr size_t j_dense_bytes = WITH_J ? size_t(TILE) * E * sizeof(T) : 0;
     static constexpr size_t o_bytes = size_t(TILE) * n * sizeof(T);
-    static constexpr size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
+    __host__ __device__ static constexpr size_t align16(size_t b) { return (b + 15) & ~size_t(15); }
     static constexpr size_t off_in0 = 0;
     static constexpr size_t off_in1 = align16(in_bytes);
     static constexpr size_t off_j = off_in1 + align16(in_bytes);
     static constexpr size_t off_o = off_j + align16(j_bytes);
     static constexpr size_t off_bar = off_o + align16(o_bytes);
     static constexpr size_t total = off_bar + 16;
+    static_assert(total == knot_smem_total(n, Model::m, JR, JC, TILE, WITH_J, int(sizeof(T))), "smem layout and knot_smem_total disagree");
 };
+
 
 template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL, bool ERR = false>
 __global__ void __launch_bounds__(TILE * Chunks::count, MINB)
@@ -352,5 +370,27 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
     }
     if (tid < S::ISSUERS) bulk_wait0();
 }
+
+// rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
+// (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
+template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, rstd::index_sequence<Is...>) { return vec(p[Is]...); }
+template <class Model, int Q, class T>
+__global__ void __launch_bounds__(64) rollout_kernel(const Model model, const T* __restrict__ x0, const T* __restrict__ U,
+                                                     const double* __restrict__ dt, double dt0, T* __restrict__ X,
+                                                     long long ntraj, int K) {
+    constexpr int n = Model::n, m = Model::m;
+    const long long tr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tr >= ntraj) return;
+    auto x = load_plain(x0 + tr * n, rstd::make_index_sequence<size_t(n)>{});
+    T* Xt = X + tr * (long long)K * n;
+    put_vals(x, Xt, rstd::make_index_sequence<size_t(n)>{});
+    for (int k = 0; k + 1 < K; ++k) {
+        auto u = load_plain(U + (tr * (long long)(K - 1) + k) * m, rstd::make_index_sequence<size_t(m)>{});
+        const T h = T(dt ? dt[tr * K + k] : dt0);
+        x = integrate<Q, T>(model, x, u, h);
+        put_vals(x, Xt + (long long)(k + 1) * n, rstd::make_index_sequence<size_t(n)>{});
+    }
+}
+
 
 }  // namespace rdb

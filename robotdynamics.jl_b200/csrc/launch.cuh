@@ -163,27 +163,6 @@ struct KnotRequest {
     cudaStream_t stream;
 };
 
-// rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
-// (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
-template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, std::index_sequence<Is...>) { return vec(p[Is]...); }
-template <class Model, int Q, class T>
-__global__ void __launch_bounds__(64) rollout_kernel(const Model model, const T* __restrict__ x0, const T* __restrict__ U,
-                                                     const double* __restrict__ dt, double dt0, T* __restrict__ X,
-                                                     long long ntraj, int K) {
-    constexpr int n = Model::n, m = Model::m;
-    const long long tr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (tr >= ntraj) return;
-    auto x = load_plain(x0 + tr * n, std::make_index_sequence<size_t(n)>{});
-    T* Xt = X + tr * (long long)K * n;
-    put_vals(x, Xt, std::make_index_sequence<size_t(n)>{});
-    for (int k = 0; k + 1 < K; ++k) {
-        auto u = load_plain(U + (tr * (long long)(K - 1) + k) * m, std::make_index_sequence<size_t(m)>{});
-        const T h = T(dt ? dt[tr * K + k] : dt0);
-        x = integrate<Q, T>(model, x, u, h);
-        put_vals(x, Xt + (long long)(k + 1) * n, std::make_index_sequence<size_t(n)>{});
-    }
-}
-
 template <class T>
 inline ModelParams<T> cast_params(const ModelParams<double>& p) {
     ModelParams<T> q;

@@ -8,9 +8,19 @@
 // and never occupy a register — without anybody hand-deriving a sparsity pattern per model.
 // Because element types differ, vectors are heterogeneous tuples (Vec<...>) indexed at compile time.
 #pragma once
+// Compiles under nvcc (library build) and under NVRTC (user-defined models, custom.cu): `rstd` is std or cuda::std.
+#ifdef __CUDACC_RTC__
+#include <cuda/std/utility>
+#include <cuda/std/type_traits>
+namespace rstd = cuda::std;
+typedef unsigned int uint32_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <cstdint>
 #include <utility>
 #include <type_traits>
+namespace rstd = std;
+#endif
 
 #ifndef RDB_HD
 #define RDB_HD __host__ __device__ __forceinline__
@@ -104,8 +114,8 @@ struct SD {
     RDB_HD void zero_parts() { for (int i = 0; i < NS; ++i) d[i] = P::zero(); }
 };
 
-template <class X> struct is_sd : std::false_type {};
-template <class T, mask_t M> struct is_sd<SD<T, M>> : std::true_type {};
+template <class X> struct is_sd : rstd::false_type {};
+template <class T, mask_t M> struct is_sd<SD<T, M>> : rstd::true_type {};
 template <class X> struct mask_of { static constexpr mask_t value = 0; };
 template <class T, mask_t M> struct mask_of<SD<T, M>> { static constexpr mask_t value = M; };
 
@@ -191,12 +201,12 @@ RDB_HD Zero operator+(Zero, Zero) { return {}; }
 RDB_HD Zero operator-(Zero, Zero) { return {}; }
 RDB_HD Zero operator*(Zero, Zero) { return {}; }
 RDB_HD Zero operator-(Zero) { return {}; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator+(Zero, const X& x) { return x; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator+(const X& x, Zero) { return x; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD X operator-(const X& x, Zero) { return x; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD auto operator-(Zero, const X& x) { return -x; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD Zero operator*(Zero, const X&) { return {}; }
-template <class X, class = std::enable_if_t<!std::is_same<X, Zero>::value>> RDB_HD Zero operator*(const X&, Zero) { return {}; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD X operator+(Zero, const X& x) { return x; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD X operator+(const X& x, Zero) { return x; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD X operator-(const X& x, Zero) { return x; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD auto operator-(Zero, const X& x) { return -x; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD Zero operator*(Zero, const X&) { return {}; }
+template <class X, class = rstd::enable_if_t<!rstd::is_same<X, Zero>::value>> RDB_HD Zero operator*(const X&, Zero) { return {}; }
 
 // ---- elementary functions -----------------------------------------------------------------------
 RDB_HD void sincos_(float a, float& s, float& c) { sincosf(a, &s, &c); }
@@ -209,6 +219,15 @@ RDB_HD void sincos_(const SD<T, A>& a, SD<T, A>& s, SD<T, A>& c) {
     for (int i = 0; i < SD<T, A>::NS; ++i) { s.d[i] = PK<T>::mul(a.d[i], cs); c.d[i] = PK<T>::mul(a.d[i], ns); }
     s.v = sv; c.v = cv;
 }
+// convenience forms for user-written models
+template <class S> RDB_HD S sin_(const S& a) { S s = a, c = a; sincos_(a, s, c); return s; }
+template <class S> RDB_HD S cos_(const S& a) { S s = a, c = a; sincos_(a, s, c); return c; }
+RDB_HD float exp_(float a) { return expf(a); }
+RDB_HD double exp_(double a) { return exp(a); }
+template <class T, mask_t A> RDB_HD SD<T, A> exp_(const SD<T, A>& a) { const T e = exp_(a.v); return scale_parts<T, A>(a, e, e); }
+RDB_HD float sqrt_(float a) { return sqrtf(a); }
+RDB_HD double sqrt_(double a) { return sqrt(a); }
+template <class T, mask_t A> RDB_HD SD<T, A> sqrt_(const SD<T, A>& a) { const T r = sqrt_(a.v); return scale_parts<T, A>(a, r, T(0.5) / r); }
 RDB_HD float rsqrt_(float a) { return 1.0f / sqrtf(a); }
 RDB_HD double rsqrt_(double a) { return 1.0 / sqrt(a); }
 template <class T, mask_t A>
@@ -230,13 +249,13 @@ RDB_HD SD<T, A> relu_(const SD<T, A>& a) {
 template <int I, class E> struct Leaf { E e; };
 template <class Seq, class... Es> struct VecBase;
 template <size_t... Is, class... Es>
-struct VecBase<std::index_sequence<Is...>, Es...> : Leaf<int(Is), Es>... {
+struct VecBase<rstd::index_sequence<Is...>, Es...> : Leaf<int(Is), Es>... {
     RDB_HD VecBase() {}
     RDB_HD VecBase(const Es&... es) : Leaf<int(Is), Es>{es}... {}
 };
 template <class... Es>
-struct Vec : VecBase<std::index_sequence_for<Es...>, Es...> {
-    using Base = VecBase<std::index_sequence_for<Es...>, Es...>;
+struct Vec : VecBase<rstd::index_sequence_for<Es...>, Es...> {
+    using Base = VecBase<rstd::index_sequence_for<Es...>, Es...>;
     static constexpr int size = int(sizeof...(Es));
     RDB_HD Vec() {}
     RDB_HD Vec(const Es&... es) : Base(es...) {}
@@ -244,24 +263,24 @@ struct Vec : VecBase<std::index_sequence_for<Es...>, Es...> {
 template <int I, class E> RDB_HD const E& get(const Leaf<I, E>& l) { return l.e; }
 template <int I, class E> RDB_HD E& get(Leaf<I, E>& l) { return l.e; }
 template <class... Es> RDB_HD Vec<Es...> vec(const Es&... es) { return Vec<Es...>(es...); }
-template <class V> using iseq = std::make_index_sequence<size_t(V::size)>;
+template <class V> using iseq = rstd::make_index_sequence<size_t(V::size)>;
 
-template <int S, class V, size_t... Is> RDB_HD auto slice_impl(const V& v, std::index_sequence<Is...>) { return vec(get<S + int(Is)>(v)...); }
-template <int S, int L, class V> RDB_HD auto slice(const V& v) { return slice_impl<S>(v, std::make_index_sequence<size_t(L)>{}); }
+template <int S, class V, size_t... Is> RDB_HD auto slice_impl(const V& v, rstd::index_sequence<Is...>) { return vec(get<S + int(Is)>(v)...); }
+template <int S, int L, class V> RDB_HD auto slice(const V& v) { return slice_impl<S>(v, rstd::make_index_sequence<size_t(L)>{}); }
 
 template <class... As, class... Bs, size_t... Is, size_t... Js>
-RDB_HD auto cat_impl(const Vec<As...>& a, const Vec<Bs...>& b, std::index_sequence<Is...>, std::index_sequence<Js...>) { return vec(get<int(Is)>(a)..., get<int(Js)>(b)...); }
-template <class... As, class... Bs> RDB_HD auto cat(const Vec<As...>& a, const Vec<Bs...>& b) { return cat_impl(a, b, std::index_sequence_for<As...>{}, std::index_sequence_for<Bs...>{}); }
+RDB_HD auto cat_impl(const Vec<As...>& a, const Vec<Bs...>& b, rstd::index_sequence<Is...>, rstd::index_sequence<Js...>) { return vec(get<int(Is)>(a)..., get<int(Js)>(b)...); }
+template <class... As, class... Bs> RDB_HD auto cat(const Vec<As...>& a, const Vec<Bs...>& b) { return cat_impl(a, b, rstd::index_sequence_for<As...>{}, rstd::index_sequence_for<Bs...>{}); }
 template <class A, class B, class C, class... R> RDB_HD auto cat(const A& a, const B& b, const C& c, const R&... r) { return cat(cat(a, b), c, r...); }
 
 // elementwise a + s*b, a + b, s*a, a - b  (s scalar of any numeric kind)
-template <class A, class S, class B, size_t... Is> RDB_HD auto axpy_impl(const A& a, const S& s, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) + s * get<int(Is)>(b))...); }
+template <class A, class S, class B, size_t... Is> RDB_HD auto axpy_impl(const A& a, const S& s, const B& b, rstd::index_sequence<Is...>) { return vec((get<int(Is)>(a) + s * get<int(Is)>(b))...); }
 template <class A, class S, class B> RDB_HD auto axpy(const A& a, const S& s, const B& b) { return axpy_impl(a, s, b, iseq<A>{}); }
-template <class A, class B, size_t... Is> RDB_HD auto vadd_impl(const A& a, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) + get<int(Is)>(b))...); }
+template <class A, class B, size_t... Is> RDB_HD auto vadd_impl(const A& a, const B& b, rstd::index_sequence<Is...>) { return vec((get<int(Is)>(a) + get<int(Is)>(b))...); }
 template <class A, class B> RDB_HD auto vadd(const A& a, const B& b) { return vadd_impl(a, b, iseq<A>{}); }
-template <class A, class B, size_t... Is> RDB_HD auto vsub_impl(const A& a, const B& b, std::index_sequence<Is...>) { return vec((get<int(Is)>(a) - get<int(Is)>(b))...); }
+template <class A, class B, size_t... Is> RDB_HD auto vsub_impl(const A& a, const B& b, rstd::index_sequence<Is...>) { return vec((get<int(Is)>(a) - get<int(Is)>(b))...); }
 template <class A, class B> RDB_HD auto vsub(const A& a, const B& b) { return vsub_impl(a, b, iseq<A>{}); }
-template <class S, class A, size_t... Is> RDB_HD auto vscale_impl(const S& s, const A& a, std::index_sequence<Is...>) { return vec((s * get<int(Is)>(a))...); }
+template <class S, class A, size_t... Is> RDB_HD auto vscale_impl(const S& s, const A& a, rstd::index_sequence<Is...>) { return vec((s * get<int(Is)>(a))...); }
 template <class S, class A> RDB_HD auto vscale(const S& s, const A& a) { return vscale_impl(s, a, iseq<A>{}); }
 
 // 3-vector algebra on heterogeneous triples
@@ -314,13 +333,13 @@ template <class T, mask_t B> struct widen_to<SD<T, B>> {
     }
 };
 template <class To, class From, size_t... Is>
-RDB_HD To widen_vec_impl(const From& a, std::index_sequence<Is...>) {
-    return To(widen_to<std::remove_cv_t<std::remove_reference_t<decltype(get<int(Is)>(std::declval<const To&>()))>>>::from(get<int(Is)>(a))...);
+RDB_HD To widen_vec_impl(const From& a, rstd::index_sequence<Is...>) {
+    return To(widen_to<rstd::remove_cv_t<rstd::remove_reference_t<decltype(get<int(Is)>(rstd::declval<const To&>()))>>>::from(get<int(Is)>(a))...);
 }
 template <class To, class From> RDB_HD To widen_vec(const From& a) { return widen_vec_impl<To>(a, iseq<To>{}); }
 template <class To, class T, size_t... Is>
-RDB_HD To zero_vec_impl(std::index_sequence<Is...>) {
-    return To(widen_to<std::remove_cv_t<std::remove_reference_t<decltype(get<int(Is)>(std::declval<const To&>()))>>>::from(T(0))...);
+RDB_HD To zero_vec_impl(rstd::index_sequence<Is...>) {
+    return To(widen_to<rstd::remove_cv_t<rstd::remove_reference_t<decltype(get<int(Is)>(rstd::declval<const To&>()))>>>::from(T(0))...);
 }
 template <class To, class T> RDB_HD To zero_vec() { return zero_vec_impl<To, T>(iseq<To>{}); }
 

@@ -145,3 +145,21 @@ def test_two_rank_gloo_sharding(tmp_path):
                         "--master-port", "29541", str(script), ROOT], capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("OK") == 2
+
+
+PENDULUM = """
+        auto th = get<0>(x); auto om = get<1>(x);
+        return vec(om, -p[0] * sin_(th) - p[1] * om + get<0>(u));
+"""
+
+
+def test_user_model_compiles_without_a_gpu_and_reports_errors():
+    """user-written dynamics are NVRTC-compiled against the embedded headers; syntax errors come back as a log."""
+    import rdb200 as rd
+    ok, log = rd._abi.custom_check(2, 1, PENDULUM, 2)
+    assert ok, log
+    ok, log = rd._abi.custom_check(2, 1, PENDULUM, 2, rd.F32)
+    assert ok, log
+    ok, log = rd._abi.custom_check(2, 1, "return vec(get<1>(x), no_such_symbol);", 0)
+    assert not ok and "no_such_symbol" in log
+    assert not rd._abi.custom_check(30, 5, PENDULUM, 2)[0]            # n + m > 32

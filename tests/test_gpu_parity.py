@@ -430,3 +430,81 @@ def test_device_trajectory_and_rollout_linearize(rd, torch_):
     assert np.abs(Jt.cpu().numpy().reshape(-1, 17, 13) - o.discrete_jacobian(om, o.RK4, Zo, 0.02)).max() < 1e-8
     Xh, Jh = rd.rollout_and_linearize(dmodel, x0, U, 0.02, error_state=True)        # host arrays, error-state form
     assert Jh.shape == (ntraj, K - 1, 16, 12) and np.abs(Xh - Xo).max() < 1e-10 * max(1.0, np.abs(Xo).max())
+
+
+# ---- user-defined models -----------------------------------------------------------------------------------------
+CARTPOLE_BODY = """
+        const T mc = p[0], mp = p[1], l = p[2], g = p[3];
+        auto s = sin_(get<1>(x)); auto c = cos_(get<1>(x));
+        auto qd0 = get<2>(x); auto qd1 = get<3>(x);
+        auto H01 = (mp * l) * c;
+        auto r0 = -((mp * l) * (qd1 * s) * qd1) - get<0>(u);
+        auto r1 = (mp * g * l) * s;
+        auto idet = T(1) / ((mc + mp) * (mp * l * l) - H01 * H01);
+        return vec(qd0, qd1, (H01 * r1 - (mp * l * l) * r0) * idet, (H01 * r0 - (mc + mp) * r1) * idet);
+"""
+# a 7-state, 3-control toy with every elementary function: exercises multi-role tiling of custom models
+TOY_BODY = """
+        auto a = get<0>(x) * get<1>(x) + exp_(T(-0.5) * get<2>(x));
+        auto b = sqrt_(T(1) + get<3>(x) * get<3>(x)) * get<0>(u);
+        auto c = relu_(get<4>(x) - p[0]) + sin_(get<5>(x)) * cos_(get<6>(x));
+        return vec(get<1>(x), a - b, get<3>(x) / (T(2) + get<2>(u) * get<2>(u)), b * c, get<1>(u) - p[1] * get<4>(x), c, a * get<2>(u));
+"""
+
+
+def _toy_f(z, p):
+    x, u = z[:7], z[7:]
+    a = x[0] * x[1] + np.exp(-0.5 * x[2])
+    b = np.sqrt(1 + x[3] * x[3]) * u[0]
+    c = (x[4] - p[0] if np.real(x[4] - p[0]) > 0 else 0 * x[4]) + np.sin(x[5]) * np.cos(x[6])
+    return np.array([x[1], a - b, x[3] / (2 + u[2] * u[2]), b * c, u[1] - p[1] * x[4], c, a * u[2]])
+
+
+def _rk4_cs(f, z, n, h):
+    """complex-step Jacobian of one RK4 step of f (independent reference for a model the oracle does not know)."""
+    def step(zz):
+        x, u = zz[:n], zz[n:]
+        k1 = f(np.r_[x, u]); k2 = f(np.r_[x + h / 2 * k1, u]); k3 = f(np.r_[x + h / 2 * k2, u]); k4 = f(np.r_[x + h * k3, u])
+        return x + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    zc = z.astype(complex)
+    J = np.stack([np.imag(step(zc + 1e-30j * np.eye(len(z))[j])) / 1e-30 for j in range(len(z))], axis=1)
+    return J, np.real(step(zc))
+
+
+def test_user_defined_models(rd, torch_):
+    # (1) the Cartpole re-written as a user model equals the built-in one and the oracle, for every rule and dtype
+    um = rd.CustomModel(4, 1, CARTPOLE_BODY, params=[1.0, 0.2, 0.5, 9.81])
+    assert rd.dims(um) == (4, 1, 4)
+    om = o.cartpole()
+    N = 3000 + 17
+    Z = np.random.default_rng(81).random((N, 5))
+    for dtype, tol in ((np.float64, 1e-10), (np.float32, 1e-4)):
+        Zt = Z.astype(dtype)
+        for Q in QS:
+            xn = np.empty((N, 4), dtype=dtype)
+            J = um._h.discrete_jacobian(Q, Zt, 0.02, xn=xn)
+            assert np.abs(J - o.discrete_jacobian(om, Q, Zt.astype(np.float64), 0.02)).max() < tol
+            assert np.abs(xn - o.discrete_dynamics(om, Q, Zt.astype(np.float64), 0.02)).max() < tol
+        assert np.abs(um._h.jacobian(dev(torch_, Zt)).cpu().numpy() - o.jacobian(om, Zt.astype(np.float64))).max() < tol * 10
+        assert np.abs(um._h.dynamics(Zt) - o.dynamics(om, Zt.astype(np.float64))).max() < tol * 10
+    x0, U = Z[:64, :4].copy(), np.random.default_rng(82).random((64, 19, 1))
+    assert np.abs(um._h.rollout(o.RK4, x0, U, 0.02) - o.rollout(om, o.RK4, x0, U, 0.02)).max() < 1e-10
+    assert np.array_equal(um._h.errstate_jacobian(Z[:5, :4].copy()), np.broadcast_to(np.eye(4), (5, 4, 4)))
+    # the reference-facing spelling works unchanged
+    Jm, y = np.zeros((4, 5)), np.zeros(4)
+    rd.jacobian_(rd.StaticReturn(), rd.ForwardAD(), rd.DiscretizedDynamics(um, rd.RK4), Jm, y, rd.KnotPoint(Z[0, :4], Z[0, 4:], 0.0, 0.02))
+    assert np.abs(Jm - o.as_matrix(o.discrete_jacobian(om, o.RK4, Z[:1], 0.02))[0]).max() < 1e-10
+    # (2) a model nobody built in: 7 states, 3 controls, exp / sqrt / relu / division; checked by complex step
+    p = [0.3, 0.7]
+    toy = rd.CustomModel(7, 3, TOY_BODY, params=p)
+    Zt = np.random.default_rng(83).random((400, 10))
+    xn = np.empty((400, 7))
+    J = toy._h.discrete_jacobian(o.RK4, Zt, 0.05, xn=xn)
+    J32 = toy._h.discrete_jacobian(o.RK4, Zt.astype(np.float32), 0.05)
+    for k in range(0, 400, 37):
+        Jr, xr = _rk4_cs(lambda zz: _toy_f(zz, p), Zt[k], 7, 0.05)
+        assert np.abs(J[k].T - Jr).max() < 1e-10 and np.abs(xn[k] - xr).max() < 1e-12
+        assert np.abs(J32[k].T - Jr).max() < 1e-4
+    with pytest.raises(rd.RDBError) as e:
+        rd.CustomModel(2, 1, "return vec(get<1>(x), nope);")
+    assert e.value.code == rd._abi.ERR_COMPILE and "nope" in str(e.value)
