@@ -183,6 +183,7 @@ __device__ __forceinline__ void images_free_barrier(int tid) {
 template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC>
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    model.reset();                 // per-knot evaluation caches (e.g. Cartpole's stage-1 sincos) start empty
     if constexpr (ERR) {
         auto zz = load_seeded_err<Model, T, CHUNK>(zrow, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(64) rollout_kernel(const Model model, const T*
     for (int k = 0; k + 1 < K; ++k) {
         auto u = load_plain(U + (tr * (long long)(K - 1) + k) * m, rstd::make_index_sequence<size_t(m)>{});
         const T h = T(dt ? dt[tr * K + k] : dt0);
+        model.reset();
         x = integrate<Q, T>(model, x, u, h);
         put_vals(x, Xt + (long long)(k + 1) * n, rstd::make_index_sequence<size_t(n)>{});
     }

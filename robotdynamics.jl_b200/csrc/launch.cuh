@@ -20,8 +20,10 @@ template <int NZ, int CPR> using uniform_chunks = typename gen_chunks<NZ, CPR, s
 // Tuning overrides for experiments (scripts/tune.py): -DRDB_TUNE_TILE / _MINB / _ROLL / _C0.._C8 (chunk masks) apply to the
 // Jacobian kernels of the unit being compiled.
 template <class Model, class T, bool WITH_J, int Q, class Enable = void>
-struct KnotConfigDefault {   // small models (Cartpole, double integrators) and every value-only kernel: one role
-    static constexpr int TILE = 128, MINB = 4, ROLL = 0;
+struct KnotConfigDefault {   // small models (Cartpole, double integrators) and every value-only kernel: one role.
+    // Jacobians of small models: single-warp CTAs (TILE 32), 12 per SM — warps drift apart instead of hitting the FP64-heavy and
+    // FP64-free phases of a tile in lockstep (Cartpole RK4 fp64: 47.5 -> 45.1 us, profiles/tuning_r01.md).
+    static constexpr int TILE = WITH_J ? 32 : 128, MINB = WITH_J ? 12 : 4, ROLL = 0;
     using Chunks = MaskList<WITH_J ? range_mask(0, Model::n + Model::m) : mask_t(0)>;
 };
 // Rigid bodies with Jacobians.  Measured on B200 (profiles/tuning_r01.md): few wide roles beat many narrow ones (every role

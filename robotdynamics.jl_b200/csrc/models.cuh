@@ -39,14 +39,22 @@ template <class T>
 struct Cartpole {
     static constexpr int n = 4, m = 1, nerr = 4, rot = ROT_NONE;
     ModelParams<T> p;
+    // sin/cos of the angle of the first evaluation since reset(): the later RK stages evaluate at angles O(h) away and get
+    // their sin/cos from the angle-addition formula (sincos_near) instead of a second full-range sincos.
+    mutable T th0, s0, c0;
+    mutable bool cached;
+    RDB_HD void reset() const { cached = false; }
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const {
         const T mpl = p.mp * p.l;
         const auto& qd0 = get<2>(x);
         const auto& qd1 = get<3>(x);
         auto th = get<1>(x);
+        T sv, cv;
+        if (!cached) { sincos_(val(th), sv, cv); th0 = val(th); s0 = sv; c0 = cv; cached = true; }
+        else sincos_near(val(th), th0, s0, c0, sv, cv);
         auto s = th, c = th;
-        sincos_(th, s, c);
+        sincos_with(th, sv, cv, s, c);
         // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s]
         const T H00 = p.mc + p.mp, H11 = mpl * p.l;
         auto H01 = mpl * c;
@@ -67,6 +75,7 @@ template <class T, int D>
 struct DoubleIntegrator {
     static constexpr int n = 2 * D, m = D, nerr = 2 * D, rot = ROT_NONE;
     ModelParams<T> p;
+    RDB_HD void reset() const {}
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const { return cat(slice<D, D>(x), u); }
 };
@@ -145,6 +154,7 @@ struct RigidBody {
     // Body/Satellite carry a full SMatrix{3,3} (test/rigidbody_test.jl:24, examples/single_satellite.jl:9).
     static constexpr bool diag_inertia = (KIND == KIND_QUADROTOR);
     ModelParams<T> p;
+    RDB_HD void reset() const {}
 
     template <class W> RDB_HD auto inertia_mul(const W& w) const {
         if constexpr (diag_inertia) return diag3_mul(p.J[0], p.J[4], p.J[8], w); else return mat3_mul(p.J, w);

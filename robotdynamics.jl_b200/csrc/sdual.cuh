@@ -219,6 +219,40 @@ RDB_HD void sincos_(const SD<T, A>& a, SD<T, A>& s, SD<T, A>& c) {
     for (int i = 0; i < SD<T, A>::NS; ++i) { s.d[i] = PK<T>::mul(a.d[i], cs); c.d[i] = PK<T>::mul(a.d[i], ns); }
     s.v = sv; c.v = cv;
 }
+// value-level sincos of an angle NEAR one whose sine and cosine are known:  sin(a0 + d) = s0 cos d + c0 sin d  with
+// degree-11/12 Taylor polynomials in d (|d| <= 1/4: truncation < 3e-18) — about half the FP64 work of a full-range sincos.
+// Used for RK stages 2..4, whose angles differ from the stage-1 angle by O(h).  Falls back to the full sincos otherwise.
+template <class T> __host__ __device__ __noinline__ void sincos_far(T a, T& s, T& c) { sincos_(a, s, c); }   // rare path, kept out of line
+template <class T>
+RDB_HD void sincos_near(T a, T a0, T s0, T c0, T& s, T& c) {
+    const T d = a - a0;
+    if (d > T(0.25) || d < T(-0.25)) { sincos_far(a, s, c); return; }
+    const T d2 = d * d;
+    T ps = T(-2.5052108385441720e-08);                       // -1/11!
+    ps = ps * d2 + T(2.7557319223985893e-06);                //  1/9!
+    ps = ps * d2 + T(-1.9841269841269841e-04);               // -1/7!
+    ps = ps * d2 + T(8.3333333333333332e-03);                //  1/5!
+    ps = ps * d2 + T(-1.6666666666666666e-01);               // -1/3!
+    const T sd = d + d * (d2 * ps);
+    T pc = T(2.0876756987868100e-09);                        //  1/12!
+    pc = pc * d2 + T(-2.7557319223985888e-07);               // -1/10!
+    pc = pc * d2 + T(2.4801587301587302e-05);                //  1/8!
+    pc = pc * d2 + T(-1.3888888888888889e-03);               // -1/6!
+    pc = pc * d2 + T(4.1666666666666664e-02);                //  1/4!
+    pc = pc * d2 + T(-0.5);
+    const T cdm1 = d2 * pc;                                   // cos d - 1
+    s = s0 + (s0 * cdm1 + c0 * sd);
+    c = c0 + (c0 * cdm1 - s0 * sd);
+}
+// duals of sin/cos from their values
+template <class T> RDB_HD void sincos_with(const T&, T sv, T cv, T& s, T& c) { s = sv; c = cv; }
+template <class T, mask_t A>
+RDB_HD void sincos_with(const SD<T, A>& a, T sv, T cv, SD<T, A>& s, SD<T, A>& c) {
+    const auto cs = PK<T>::splat(cv), ns = PK<T>::splat(-sv);
+    for (int i = 0; i < SD<T, A>::NS; ++i) { s.d[i] = PK<T>::mul(a.d[i], cs); c.d[i] = PK<T>::mul(a.d[i], ns); }
+    s.v = sv; c.v = cv;
+}
+
 // convenience forms for user-written models
 template <class S> RDB_HD S sin_(const S& a) { S s = a, c = a; sincos_(a, s, c); return s; }
 template <class S> RDB_HD S cos_(const S& a) { S s = a, c = a; sincos_(a, s, c); return c; }

@@ -49,13 +49,10 @@ VARIANTS = {
     },
     "cartpole": {
         "base": {},
-        "minb4": dict(RDB_TUNE_MINB=4),
-        "minb5": dict(RDB_TUNE_MINB=5),
-        "minb6": dict(RDB_TUNE_MINB=6),
+        "t32_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16),
+        "t32_minb12": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=12),
         "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
-        "t64_minb10": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=10),
-        "t256_minb2": dict(RDB_TUNE_TILE=256, RDB_TUNE_MINB=2),
-        "2r_minb3": dict(RDB_TUNE_C0="0x7u", RDB_TUNE_C1="0x18u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=4),
+        "t64_minb6": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=6),
     },
     "satellite": {
         "base": {},
@@ -101,7 +98,7 @@ def build_variants(workload):
             if "Compiling entry function" in l and "knot_kernel" in l and want in l and "ELb1E" in l:
                 info = " ".join(x.strip() for x in lines[i + 1:i + 4] if "registers" in x or "spill" in x)
         subprocess.check_call([B.NVCC] + B.ARCH + ["-shared", "-o", lib, obj, stub_obj, os.path.join(B.OBJ, "abi.o"), os.path.join(B.OBJ, "lie.o"),
-                               "-cudart", "static"])
+                               os.path.join(B.OBJ, "custom.o"), "-cudart", "static", "-lnvrtc"])
         os.remove(obj)
         return tag, info
 
