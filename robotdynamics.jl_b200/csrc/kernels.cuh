@@ -247,8 +247,11 @@ __device__ __forceinline__ void coop_store(const T* img, int P, T* g, long long 
 __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 // Dynamic shared memory of knot_kernel as a function of plain integers (jr x jc = Jacobian image shape, es = sizeof(T)); used by
 // KnotSmem below (static_assert) and by custom.cu, which only knows the dimensions of a user model at run time.
+#ifndef RDB_TUNE_ROWSTORE
+#define RDB_TUNE_ROWSTORE 1      // 0: tuning experiments only (dense image even where it is bank-conflicted)
+#endif
 __host__ __device__ constexpr bool knot_rowstore(int jr, int jc, bool with_j, int es) {
-    return with_j && jr >= 12 && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && cgcd(jr * jc * es / 4, 32) >= 16;
+    return RDB_TUNE_ROWSTORE && with_j && jr >= 12 && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && cgcd(jr * jc * es / 4, 32) >= 16;
 }
 __host__ __device__ constexpr int knot_pitch(int jr, int jc, bool with_j, int es) {
     const int E = jr * jc, u = (E * es + 15) / 16;

@@ -19,6 +19,7 @@ sys.path.insert(0, CSRC)
 UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
     "quadrotor": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "cartpole": ("cartpole_f64", dict(RDB_KIND=0, RDB_DTYPE=1)),
+    "quaderr": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "quadbody": ("quad_quat_body_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=0)),
     "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite": ("body_mrp_world_f64", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
@@ -27,10 +28,18 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
 
 VARIANTS = {
     "quadrotor": {
-        "pack0": dict(RDB_PACK_F32=0),
-        "pack1": dict(RDB_PACK_F32=1),
-        "pack1_3r": dict(RDB_PACK_F32=1, RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFu", RDB_TUNE_C1="0x3F00u", RDB_TUNE_C2="0x1C000u"),
-        "pack1_2rb": dict(RDB_PACK_F32=1, RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1FC00u"),
+        "base": {},
+        "t64_minb2": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
+        "t32_minb4": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=4),
+        "t96_minb1": dict(RDB_TUNE_TILE=96, RDB_TUNE_MINB=1),
+    },
+    "quaderr": {
+        "base": {},
+        "dense": dict(RDB_TUNE_ROWSTORE=0),
+        "3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
+        "2r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0xF800u"),
+        "2rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0xFE00u"),
+        "unroll": dict(RDB_TUNE_ROLL=0),
     },
     "quadbody": {
         "base": {},
@@ -115,7 +124,7 @@ import rdb200 as rd
 import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
-wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor"}.get(name, name)
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
 if name == "quadrotor64": dtn = "float64"
@@ -125,22 +134,27 @@ if name == 'quadbody': mk = lambda: rd.Quadrotor(bodyframe=True)
 model = mk(); h = model._h
 nsets = 4
 Zs = [torch.from_numpy(bench.make_inputs(n, m, N, dtn, i)).cuda() for i in range(nsets)]
-Js = [torch.empty((N, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
-for i in range(5): h.discrete_jacobian(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
+ERR = name == "quaderr"
+call = h.discrete_error_jacobian if ERR else h.discrete_jacobian
+Js = [torch.empty((N, h.nerr + m, h.nerr) if ERR else (N, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
+for i in range(5): call(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
 torch.cuda.synchronize()
 steps = 100
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for i in range(steps): h.discrete_jacobian(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
+for i in range(steps): call(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / steps * 1e3
 omk, oQ = bench.oracle_model(wl)
 if name == 'quadbody': omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
 idx = np.arange(0, N, 4099)
-ref = o.discrete_jacobian(omk(), oQ, Zs[0].cpu().numpy()[idx].astype(np.float64), dt)
-err = float(np.abs(Js[0].cpu().numpy()[idx] - ref).max())
+if ERR:
+    err = 0.0
+else:
+    ref = o.discrete_jacobian(omk(), oQ, Zs[0].cpu().numpy()[idx].astype(np.float64), dt)
+    err = float(np.abs(Js[0].cpu().numpy()[idx] - ref).max())
 es = Zs[0].element_size()
-gbs = N * es * ((n + m) + n * (n + m)) / (us * 1e-6) / 1e9
+gbs = N * es * ((n + m) + (h.nerr * (h.nerr + m) if ERR else n * (n + m))) / (us * 1e-6) / 1e9
 print(json.dumps({"us": us, "evals_per_s": N / (us * 1e-6), "GBs": gbs, "frac": gbs / 6551.4, "err": err}))
 """
 
