@@ -1,7 +1,7 @@
 // kernels.cuh — the batched knot-point kernel (K1/K2/K3 of SURVEY.md §2) for sm_100a.
 //
 // One template serves dynamics(), discrete_dynamics() and their Jacobians:
-//   knot_kernel<Model, Q, T, TILE, WITH_J, CHUNKS...>
+//   knot_kernel<Model, Q, T, TILE, WITH_J, Chunks, MINB, ROLL, ERR>
 //     Q in {EULER,RK2,RK3,RK4,CONTINUOUS};  WITH_J: also produce d out / d [x;u]  (n x (n+m), column-major [A B],
 //     reference layout: src/jacobian.jl:26-37).
 //
