@@ -199,9 +199,14 @@ def run_sweep(args):
         Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
         work.append((model._h, Q.code, Zs, dt, Js, cnt, np.dtype(dtn).itemsize * ((n + m) + n * (n + m))))
 
+    # the two model segments are independent: one stream each, so their (small, at 8 GPUs launch-bound) kernels overlap
+    streams = [torch.cuda.Stream() for _ in work]
+    main = torch.cuda.current_stream()
+
     def step(i):
-        for h, qc, Zs, dt, Js, _, _ in work:
-            h.discrete_jacobian(qc, Zs[i % len(Zs)], dt, J=Js[i % len(Zs)])
+        for (h, qc, Zs, dt, Js, _, _), st in zip(work, streams):
+            with torch.cuda.stream(st):
+                h.discrete_jacobian(qc, Zs[i % len(Zs)], dt, J=Js[i % len(Zs)])
 
     def barrier():
         if world > 1:
@@ -212,10 +217,14 @@ def run_sweep(args):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(main)
+    for st in streams:
+        st.wait_stream(main)
     for i in range(args.steps):
         step(i)
-    e1.record()
+    for st in streams:
+        main.wait_stream(st)
+    e1.record(main)
     barrier()
     ms = sh.barrier_max_ms(e0.elapsed_time(e1), device=torch.device("cuda", local))
     if rank == 0:

@@ -163,3 +163,18 @@ def test_user_model_compiles_without_a_gpu_and_reports_errors():
     ok, log = rd._abi.custom_check(2, 1, "return vec(get<1>(x), no_such_symbol);", 0)
     assert not ok and "no_such_symbol" in log
     assert not rd._abi.custom_check(30, 5, PENDULUM, 2)[0]            # n + m > 32
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/rdb200.h is plain C99 and the library links from C; without a GPU the example fails loudly (exit status 3)."""
+    import torch
+    exe = str(tmp_path / "rdb_example")
+    libdir = os.path.join(ROOT, "robotdynamics.jl_b200")
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_example.c"),
+                        "-o", exe, "-L", libdir, "-lrdb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "[A B] of knot 0" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr, r.stdout + r.stderr
