@@ -78,8 +78,18 @@ int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const doubl
  * (operation, integrator, dtype); works with every batch entry point below except rdb_discrete_error_jacobian's G-seeding
  * (which degenerates to rdb_discrete_jacobian for Euclidean states anyway). */
 int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, const double* params, int nparams, rdb_model** model);
+/* User-defined RigidBody{R}: the reference's rigid-body extension interface is forces(model,x,u) / moments(model,x,u) / mass /
+ * inertia (src/rigidbody.jl:244-257, e.g. examples/single_satellite.jl:17-35).  wrench_body is the body of a function that sees
+ *     q (attitude as the quaternion Rotations.jl builds for it, Vec4 [w,x,y,z]; use quat_rotate<T>(q, vec3) for q*r),
+ *     r, v, w (Vec3), u (m controls), p[k] (user parameters), mass
+ * and returns vec(Fx, Fy, Fz, tx, ty, tz): force in the WORLD frame, torque in the BODY frame.  The library supplies the
+ * kinematics, Newton / Euler equations, velocity frame, LieState (R, (3,6)) error maps and the error-state Jacobian.
+ * J: 3x3 inertia, row-major.  n = 13 (quaternion) or 12 (MRP, Rodrigues). */
+int rdb_model_create_custom_rigid(rdb_context* ctx, int rot, int frame, int m, const char* wrench_body, double mass, const double* J,
+                                  const double* params, int nparams, rdb_model** model);
 /* compile-only check of a user model body (needs no GPU); on failure rdb_last_log() returns the compiler log */
 int rdb_custom_check(int n, int m, const char* f_body, int nparams, int dtype);
+int rdb_custom_rigid_check(int rot, int frame, int m, const char* wrench_body, int nparams, int dtype);
 const char* rdb_last_log(void);
 int rdb_model_destroy(rdb_model* model);
 /* state_dim / control_dim / errstate_dim  (src/functionbase.jl:124-135, src/liestate.jl:124) */

@@ -30,7 +30,7 @@ ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE, ERR_COMPILE = -1, 
 # every symbol include/rdb200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free",
-    "rdb_model_create", "rdb_model_create_custom", "rdb_custom_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
+    "rdb_model_create", "rdb_model_create_custom", "rdb_model_create_custom_rigid", "rdb_custom_check", "rdb_custom_rigid_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
 )
@@ -68,7 +68,9 @@ def lib():
         L.rdb_host_free.argtypes = [vp]
         L.rdb_model_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_model_create_custom.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
+        L.rdb_model_create_custom_rigid.argtypes = [vp, i32, i32, i32, ctypes.c_char_p, dbl, ctypes.POINTER(dbl), ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_custom_check.argtypes = [i32, i32, ctypes.c_char_p, i32, i32]
+        L.rdb_custom_rigid_check.argtypes = [i32, i32, i32, ctypes.c_char_p, i32, i32]
         L.rdb_last_log.restype = ctypes.c_char_p
         L.rdb_model_destroy.argtypes = [vp]
         L.rdb_model_dims.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
@@ -94,6 +96,12 @@ def check(rc, what):
         raise RDBError(rc, what + "\n" + lib().rdb_last_log().decode(errors="replace")[-3000:])
     if rc != 0:
         raise (NotImplementedModelError if rc == ERR_NOT_IMPLEMENTED else RDBError)(rc, what)
+
+
+def custom_rigid_check(rot, frame, m, body, nparams=0, dtype=F64):
+    """Compile-only check of a user rigid-body wrench (no GPU needed).  Returns (ok, compiler log)."""
+    rc = lib().rdb_custom_rigid_check(int(rot), int(frame), int(m), body.encode(), int(nparams), int(dtype))
+    return rc == 0, lib().rdb_last_log().decode(errors="replace")
 
 
 def custom_check(n, m, body, nparams=0, dtype=F64):
@@ -223,10 +231,16 @@ class ModelHandle:
         self.params = np.ascontiguousarray(params, dtype=np.float64)
         self._h = ctypes.c_void_p()
         pp = self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-        if custom is not None:                         # (n, m, body of f): NVRTC-compiled user model
+        if custom is not None and len(custom) == 3:    # (n, m, body of f): NVRTC-compiled user model
             n, m, body = custom
             check(lib().rdb_model_create_custom(self.ctx._h, int(n), int(m), body.encode(), pp, len(self.params),
                                                 ctypes.byref(self._h)), "rdb_model_create_custom")
+        elif custom is not None:                       # (m, wrench body, mass, J): RigidBody{R} with a user wrench
+            m, body, mass, J = custom
+            J = np.ascontiguousarray(J, dtype=np.float64).reshape(9)
+            check(lib().rdb_model_create_custom_rigid(self.ctx._h, self.rot, self.frame, int(m), body.encode(), float(mass),
+                                                      J.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), pp, len(self.params),
+                                                      ctypes.byref(self._h)), "rdb_model_create_custom_rigid")
         else:
             check(lib().rdb_model_create(self.ctx._h, self.kind, self.rot, self.frame, pp, len(self.params),
                                          ctypes.byref(self._h)), "rdb_model_create")

@@ -126,6 +126,14 @@ class CustomModel(ContinuousDynamics):
         self._h = _abi.ModelHandle(_abi.CUSTOM, _abi.ROT_NONE, 0, params, device, custom=(n, m, body))
 
 
+class CustomRigidBody(RigidBody):
+    """RigidBody{R} with user forces / moments (the reference's rigid-body extension interface, src/rigidbody.jl:244-257):
+    `wrench_body` sees q, r, v, w, u, p[k], mass and returns vec(F_world (3), tau_body (3)); the library supplies the rest,
+    including the LieState error maps and the error-state Jacobian."""
+    def __init__(self, R, m, wrench_body, mass, J, params=(), bodyframe=False, device=None):
+        self._h = _abi.ModelHandle(_abi.CUSTOM, R.code, int(bool(bodyframe)), params, device, custom=(m, wrench_body, mass, _inertia(J)))
+
+
 class DiscreteDynamics(AbstractModel): pass
 
 

@@ -290,8 +290,33 @@ int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, 
     return *model ? 0 : RDB_ERR_ARG;
 }
 
+int rdb_model_create_custom_rigid(rdb_context* ctx, int rot, int frame, int m, const char* wrench_body, double mass, const double* J,
+                                  const double* params, int np, rdb_model** model) {
+    if (!ctx || !model || !wrench_body || !J || m < 1 || m > 12 || np < 0 || (np > 0 && !params) || rot < RDB_ROT_QUAT || rot > RDB_ROT_RP ||
+        (frame != 0 && frame != 1) || !(mass > 0.0))
+        return RDB_ERR_ARG;
+    *model = nullptr;
+    const int n = 9 + (rot == RDB_ROT_QUAT ? 4 : 3);
+    if (custom_check(n, m, wrench_body, np, RDB_F64, rot, frame) != 0) return RDB_ERR_COMPILE;
+    rdb_model M;
+    std::memset(&M, 0, sizeof(M));
+    M.ctx = ctx; M.kind = RDB_CUSTOM; M.rot = rot; M.frame = frame; M.n = n; M.m = m; M.nerr = 12;
+    M.p.mass = mass; M.p.inv_mass = 1.0 / mass;
+    for (int i = 0; i < 9; ++i) M.p.J[i] = J[i];
+    inv3(M.p.J, M.p.Jinv);
+    M.custom = custom_create(n, m, wrench_body, params, np, rot, frame, &M.p);
+    if (!M.custom) return RDB_ERR_ARG;
+    *model = new (std::nothrow) rdb_model(M);
+    return *model ? 0 : RDB_ERR_ARG;
+}
+
 int rdb_custom_check(int n, int m, const char* f_body, int nparams, int dtype) {
     return custom_check(n, m, f_body, nparams, dtype) == 0 ? 0 : RDB_ERR_COMPILE;
+}
+
+int rdb_custom_rigid_check(int rot, int frame, int m, const char* wrench_body, int nparams, int dtype) {
+    if (rot < RDB_ROT_QUAT || rot > RDB_ROT_RP || (frame != 0 && frame != 1) || m < 1) return RDB_ERR_ARG;
+    return custom_check(9 + (rot == RDB_ROT_QUAT ? 4 : 3), m, wrench_body, nparams, dtype, rot, frame) == 0 ? 0 : RDB_ERR_COMPILE;
 }
 
 const char* rdb_last_log(void) { return custom_last_log(); }

@@ -146,6 +146,34 @@ template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) 
 // ------------------------------------------------------------------------------------------------
 // RigidBody{R} with the Quadrotor or Body/Satellite wrench
 // ------------------------------------------------------------------------------------------------
+// The part every RigidBody{R} shares (reference: src/rigidbody.jl:213-236): kinematics, Newton and Euler equations around a
+// wrench supplied by the concrete model — `wrench(q, r, v, w, u)` returns vec(F/m in the world frame (3), tau in the body frame (3))
+// (reference: forces / moments / wrenches, src/rigidbody.jl:244-257).
+template <class T, int ROT, int FRAME, bool DIAG_INERTIA, class X, class U, class Wrench>
+RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const Wrench& wrench) {
+    constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
+    auto r = slice<0, 3>(x);
+    auto att = slice<3, np>(x);
+    auto v = slice<3 + np, 3>(x);
+    auto w = slice<6 + np, 3>(x);
+    auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised)
+    auto xi = wrench(q, r, v, w, u);
+    auto Fm = slice<0, 3>(xi);
+    auto tau = slice<3, 3>(xi);
+    auto qdot = rot_kinematics<T, ROT>(att, w);
+    // omega_dot = Jinv (tau - w x (J w))
+    auto Jw = [&]() { if constexpr (DIAG_INERTIA) return diag3_mul(p.J[0], p.J[4], p.J[8], w); else return mat3_mul(p.J, w); }();
+    auto rhs = vsub(tau, cross3(w, Jw));
+    auto wdot = [&]() { if constexpr (DIAG_INERTIA) return diag3_mul(p.Jinv[0], p.Jinv[4], p.Jinv[8], rhs); else return mat3_mul(p.Jinv, rhs); }();
+    if constexpr (FRAME == FRAME_WORLD) {
+        return cat(v, qdot, Fm, wdot);
+    } else {
+        auto rdot = quat_rotate<T>(q, v);
+        auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3(w, v));
+        return cat(rdot, qdot, vdot, wdot);
+    }
+}
+
 template <class T, int KIND, int ROT, int FRAME>
 struct RigidBody {
     static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
@@ -156,52 +184,26 @@ struct RigidBody {
     ModelParams<T> p;
     RDB_HD void reset() const {}
 
-    template <class W> RDB_HD auto inertia_mul(const W& w) const {
-        if constexpr (diag_inertia) return diag3_mul(p.J[0], p.J[4], p.J[8], w); else return mat3_mul(p.J, w);
-    }
-    template <class W> RDB_HD auto inertia_inv_mul(const W& w) const {
-        if constexpr (diag_inertia) return diag3_mul(p.Jinv[0], p.Jinv[4], p.Jinv[8], w); else return mat3_mul(p.Jinv, w);
-    }
-
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const {
-        auto att = slice<3, np>(x);
-        auto v = slice<3 + np, 3>(x);
-        auto w = slice<6 + np, 3>(x);
-        auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised)
-
         // wrench: F/m in the world frame (the 1/m of vdot = F/m is folded into the few scalars that build F, instead of
         // scaling every partial of the rotated vector), tau in the body frame
-        auto wrench = [&]() {
+        return rigid_body_f<T, ROT, FRAME, diag_inertia>(p, x, u, [&](const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
             if constexpr (KIND == KIND_QUADROTOR) {
-                auto F1 = relu_(p.kf * get<0>(u));
-                auto F2 = relu_(p.kf * get<1>(u));
-                auto F3 = relu_(p.kf * get<2>(u));
-                auto F4 = relu_(p.kf * get<3>(u));
+                auto F1 = relu_(p.kf * get<0>(uu));
+                auto F2 = relu_(p.kf * get<1>(uu));
+                auto F3 = relu_(p.kf * get<2>(uu));
+                auto F4 = relu_(p.kf * get<3>(uu));
                 auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, p.inv_mass * (F1 + F2 + F3 + F4)));
                 const T g0 = p.mg[0] * p.inv_mass, g1 = p.mg[1] * p.inv_mass, g2 = p.mg[2] * p.inv_mass;
                 auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
-                               p.km * (get<0>(u) - get<1>(u) + get<2>(u) - get<3>(u)));
+                               p.km * (get<0>(uu) - get<1>(uu) + get<2>(uu) - get<3>(uu)));
                 return cat(Fm, tau);
             } else {
-                return cat(quat_rotate<T>(q, vscale(p.inv_mass, slice<0, 3>(u))), slice<3, 3>(u));
+                return cat(quat_rotate<T>(q, vscale(p.inv_mass, slice<0, 3>(uu))), slice<3, 3>(uu));
             }
-        };
-        auto xi = wrench();
-        auto Fm = slice<0, 3>(xi);
-        auto tau = slice<3, 3>(xi);
-
-        auto qdot = rot_kinematics<T, ROT>(att, w);
-        // omega_dot = Jinv (tau - w x (J w))
-        auto wdot = inertia_inv_mul(vsub(tau, cross3(w, inertia_mul(w))));
-        if constexpr (FRAME == FRAME_WORLD) {
-            return cat(v, qdot, Fm, wdot);
-        } else {
-            auto rdot = quat_rotate<T>(q, v);
-            auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3(w, v));
-            return cat(rdot, qdot, vdot, wdot);
-        }
+        });
     }
 };
 

@@ -178,3 +178,22 @@ def test_c_abi_from_plain_c(tmp_path):
         assert r.returncode == 0 and "[A B] of knot 0" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr, r.stdout + r.stderr
+
+
+QUAD_WRENCH = """
+                // test/quadrotor.jl:56-96 as a user wrench: p = [kf, km, L, gx, gy, gz]
+                auto F1 = relu_(p[0] * get<0>(u)); auto F2 = relu_(p[0] * get<1>(u));
+                auto F3 = relu_(p[0] * get<2>(u)); auto F4 = relu_(p[0] * get<3>(u));
+                auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, F1 + F2 + F3 + F4));
+                return vec(mass * p[3] + get<0>(qF), mass * p[4] + get<1>(qF), mass * p[5] + get<2>(qF),
+                           p[2] * (F2 - F4), p[2] * (F3 - F1), p[1] * (get<0>(u) - get<1>(u) + get<2>(u) - get<3>(u)));
+"""
+
+
+def test_user_rigid_body_wrench_compiles_without_a_gpu():
+    """The reference's rigid-body extension interface (forces / moments, src/rigidbody.jl:244-257) as a user wrench body."""
+    import rdb200 as rd
+    ok, log = rd._abi.custom_rigid_check(rd._abi.ROT_QUAT, 0, 4, QUAD_WRENCH, 6, rd.F32)
+    assert ok, log
+    ok, log = rd._abi.custom_rigid_check(rd._abi.ROT_MRP, 1, 4, "return vec(get<0>(u), oops);", 0)
+    assert not ok and "oops" in log

@@ -508,3 +508,34 @@ def test_user_defined_models(rd, torch_):
     with pytest.raises(rd.RDBError) as e:
         rd.CustomModel(2, 1, "return vec(get<1>(x), nope);")
     assert e.value.code == rd._abi.ERR_COMPILE and "nope" in str(e.value)
+
+
+def test_user_rigid_body_wrench(rd, torch_):
+    """A Quadrotor defined by the USER through forces/moments (reference: test/quadrotor.jl:56-96 on the RigidBody interface,
+    src/rigidbody.jl:244-257) equals the oracle's quadrotor for every rotation / frame, including the LieState maps and the
+    error-state Jacobian."""
+    from test_abi_host import QUAD_WRENCH
+    rng = np.random.default_rng(91)
+    for Rname, rc, frame in (("QuatRotation", o.ROT_QUAT, o.WORLD), ("MRP", o.ROT_MRP, o.BODYFRAME), ("RodriguesParam", o.ROT_RP, o.WORLD)):
+        om = o.quadrotor(rc, frame)
+        um = rd.CustomRigidBody(getattr(rd, Rname), 4, QUAD_WRENCH, mass=0.5, J=(0.0023, 0.0023, 0.004),
+                                params=[1.0, 0.0245, 0.175, 0.0, 0.0, -9.81], bodyframe=bool(frame))
+        assert (um.n, um.m, rd.errstate_dim(um)) == (om.n, om.m, 12) and um.statevectortype is rd.RotationState
+        N = 700
+        Z = rand_inputs(om.n, om.m, N, rng)
+        for dtype, tol in ((np.float64, 1e-10), (np.float32, 1e-4)):
+            Zt = Z.astype(dtype)
+            Z64 = Zt.astype(np.float64)
+            for Q in (o.RK4, o.RK2):
+                xn = np.empty((N, om.n), dtype=dtype)
+                J = um._h.discrete_jacobian(Q, Zt, 0.03, xn=xn)
+                assert np.abs(J - o.discrete_jacobian(om, Q, Z64, 0.03)).max() < tol
+                assert np.abs(xn - o.discrete_dynamics(om, Q, Z64, 0.03)).max() < tol
+            Jb = um._h.discrete_error_jacobian(o.RK4, dev(torch_, Zt), 0.03)
+            assert np.abs(o.as_matrix(Jb.cpu().numpy()) - _error_jacobian_ref(om, o.RK4, Z64, 0.03)).max() < tol
+            assert np.abs(um._h.dynamics(Zt) - o.dynamics(om, Z64)).max() < tol * max(1.0, np.abs(o.dynamics(om, Z64)).max())
+        X = np.ascontiguousarray(Z[:, :om.n])
+        assert np.abs(um._h.errstate_jacobian(X) - o.errstate_jacobian(om, X)).max() < 1e-12
+        x0, U = X[:50].copy(), rng.random((50, 15, 4))
+        ref = o.rollout(om, o.RK4, x0, U, 0.02)
+        assert np.abs(um._h.rollout(o.RK4, x0, U, 0.02) - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
