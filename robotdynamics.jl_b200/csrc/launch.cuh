@@ -35,7 +35,11 @@ struct KnotConfigDefault<Model, float, true, Q, std::enable_if_t<(Model::n >= 12
     static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
     static constexpr int TILE = (heavy && m == 4) ? 128 : 64;
     static constexpr int MINB = (heavy && m == 4) ? 1 : 2;
-    using Heavy = std::conditional_t<m == 4, MaskList<range_mask(0, n - 1), range_mask(n - 1, NZ)>,                    // {r,att,v,w0,w1} {w2,u}
+    // m = 4: two wide roles.  World-frame quaternion models split after w1 ({r,q,v,w0,w1} {w2,u}: 51 us on C3); body-frame and
+    // 3-parameter attitudes couple more rows to v and w and balance better split after v ({r,att,v} {w,u}: quadrotor body frame
+    // 162 -> 137 us, quadrotor{MRP} 78 -> 74 us; profiles/tuning_r01.md).
+    static constexpr int split = (Model::rot == ROT_QUAT && Model::frame == FRAME_WORLD) ? n - 1 : n - 3;
+    using Heavy = std::conditional_t<m == 4, MaskList<range_mask(0, split), range_mask(split, NZ)>,
                                               MaskList<range_mask(0, n - 3), range_mask(n - 3, n + 2), range_mask(n + 2, NZ)>>;  // {r,att,v} {w,u0,u1} {u2..u5}
     using Light = std::conditional_t<m == 4, MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, NZ)>,            // {r,att} {v,w} {u}
                                               MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + 3), range_mask(n + 3, NZ)>>;
@@ -116,7 +120,7 @@ struct KnotConfig<Model, T, true, Q> {
 struct DeviceInfo { int device; int sm_count; int pdl; };   // pdl: launch with programmatic stream serialization
 
 // shape seen by the tiling rules in error-state mode: nerr rows, nerr + m columns (like an n = 12 model)
-template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m; };
+template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m, rot = ROT_QUAT, frame = FRAME_WORLD; };
 
 template <class Model, int Q, class T, bool WITH_J, bool ERR = false>
 struct KnotLaunch {

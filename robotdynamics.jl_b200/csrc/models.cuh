@@ -177,7 +177,7 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
 template <class T, int KIND, int ROT, int FRAME>
 struct RigidBody {
     static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
-    static constexpr int n = 9 + np, m = (KIND == KIND_QUADROTOR) ? 4 : 6, nerr = 12, rot = ROT;
+    static constexpr int n = 9 + np, m = (KIND == KIND_QUADROTOR) ? 4 : 6, nerr = 12, rot = ROT, frame = FRAME;
     // The reference Quadrotor stores its inertia as Diagonal{Float64} (test/quadrotor.jl:25-26): only the diagonal exists.
     // Body/Satellite carry a full SMatrix{3,3} (test/rigidbody_test.jl:24, examples/single_satellite.jl:9).
     static constexpr bool diag_inertia = (KIND == KIND_QUADROTOR);

@@ -20,6 +20,7 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
     "quadrotor": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "cartpole": ("cartpole_f64", dict(RDB_KIND=0, RDB_DTYPE=1)),
     "quaderr": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
+    "quadmrp": ("quad_mrp_world_f32", dict(RDB_KIND=1, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=0)),
     "quadbody": ("quad_quat_body_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=0)),
     "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite": ("body_mrp_world_f64", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
@@ -43,10 +44,16 @@ VARIANTS = {
     },
     "quadbody": {
         "base": {},
-        "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
-        "3r_t128": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
-        "3rb_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x3C00u", RDB_TUNE_C2="0x1C000u"),
-        "4r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
+        "roll2_2r": dict(RDB_TUNE_ROLL=2),
+        "roll2_3r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+        "roll1_3rc": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1C00u", RDB_TUNE_C2="0x1E000u"),
+        "roll1_2rc": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1FC00u"),
+    },
+    "quadmrp": {
+        "base": {},
+        "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
+        "2rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0xFE00u"),
+        "roll2": dict(RDB_TUNE_ROLL=2),
     },
     "quadrotor64": {
         "base": {},
@@ -55,6 +62,10 @@ VARIANTS = {
         "roll1_3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
         "roll2_3r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
         "roll1_4r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
+        "roll1_5r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x380u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x6000u", RDB_TUNE_C4="0x18000u"),
+        "roll1_5r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x380u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x6000u", RDB_TUNE_C4="0x18000u"),
+        "roll1_6r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x60u", RDB_TUNE_C2="0x380u", RDB_TUNE_C3="0x1C00u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
+        "roll1_4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
     },
     "cartpole": {
         "base": {},
@@ -124,14 +135,16 @@ import rdb200 as rd
 import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
-wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor"}.get(name, name)
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
 if name == "quadrotor64": dtn = "float64"
 if len(sys.argv) > 3: N = int(sys.argv[3])
 mk, Q = bench.gpu_model(wl, rd)
 if name == 'quadbody': mk = lambda: rd.Quadrotor(bodyframe=True)
+if name == 'quadmrp': mk = lambda: rd.Quadrotor(rd.MRP)
 model = mk(); h = model._h
+n, m = h.n, h.m
 nsets = 4
 Zs = [torch.from_numpy(bench.make_inputs(n, m, N, dtn, i)).cuda() for i in range(nsets)]
 ERR = name == "quaderr"
@@ -147,6 +160,7 @@ e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / steps * 1e3
 omk, oQ = bench.oracle_model(wl)
 if name == 'quadbody': omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
+if name == 'quadmrp': omk = lambda: o.quadrotor(o.ROT_MRP)
 idx = np.arange(0, N, 4099)
 if ERR:
     err = 0.0

@@ -539,3 +539,14 @@ def test_user_rigid_body_wrench(rd, torch_):
         x0, U = X[:50].copy(), rng.random((50, 15, 4))
         ref = o.rollout(om, o.RK4, x0, U, 0.02)
         assert np.abs(um._h.rollout(o.RK4, x0, U, 0.02) - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
+
+
+def test_sixteen_million_knots_64bit_indexing(rd, torch_):
+    """N = 2^24 + 5 Cartpole knots in fp32 (1.3 GB of Jacobians): element offsets exceed 2^31; strided sample + ragged tail vs oracle."""
+    N = (1 << 24) + 5
+    gen = torch_.Generator(device="cuda").manual_seed(7)
+    Z = torch_.rand((N, 5), dtype=torch_.float32, device="cuda", generator=gen)
+    J = rd.Cartpole()._h.discrete_jacobian(o.RK4, Z, 0.01)
+    idx = torch_.cat([torch_.arange(0, N, 65521, device="cuda"), torch_.arange(N - 40, N, device="cuda")])
+    ref = o.discrete_jacobian(o.cartpole(), o.RK4, Z[idx].cpu().numpy().astype(np.float64), 0.01)
+    assert np.abs(J[idx].cpu().numpy() - ref).max() < 1e-4
