@@ -8,6 +8,7 @@
 //
 // Here the attitude IS normalised (default R(w,x,y,z) constructor), unlike inside dynamics.
 #include "lie.h"
+#include "kernels.cuh"   // mbarrier / bulk-copy PTX helpers
 
 namespace rdb {
 
@@ -64,6 +65,46 @@ __global__ void __launch_bounds__(256) errstate_jacobian_kernel(int rot, int n, 
         else v = (j == i - np + 3) ? T(1) : T(0);
         G[idx] = v;
     }
+}
+
+// Rigid bodies (the hot one: G is n x 12 per knot, 624 B in fp32, and only its 4x3 / 3x3 attitude block depends on the state).
+// The output of a tile of TILE knots is one contiguous byte range, so the kernel keeps two shared-memory IMAGES of it: the
+// structural 0/1 pattern is written once per CTA, each tile only overwrites its knots' attitude-block entries (12 or 9 stores per
+// knot) and one TMA bulk store ships the image; the two images alternate so a store drains while the next tile is prepared.
+// Pure store stream: HBM-write bound.
+template <class T, int NP, int TILE>
+__global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, long long N, const T* __restrict__ X, int ldx, T* __restrict__ G) {
+    constexpr int n = 9 + NP, ne = 12, PER = n * ne;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* img[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw) + TILE * PER};
+    for (int e = threadIdx.x; e < 2 * TILE * PER; e += TILE) {
+        const int r = e % PER, j = r / n, i = r - j * n;
+        img[0][e] = (i < 3) ? T(j == i) : (i < 3 + NP) ? T(0) : T(j == i - NP + 3);
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long ntiles = (N + TILE - 1) / TILE;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const long long k0 = tile * TILE;
+        const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
+        T* im = img[it & 1];
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this image is done reading
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const T* p = X + (k0 + threadIdx.x) * ldx + 3;
+            T pp[4] = {p[0], p[1], p[2], NP == 4 ? p[NP - 1] : T(0)};
+            T* row = im + threadIdx.x * PER;
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) row[(3 + i) + n * (3 + j)] = grad_differential(rot, pp, i, j);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) { bulk_store(G + k0 * PER, smem_u32(im), uint32_t(cnt * PER * sizeof(T))); bulk_commit(); }
+    }
+    if (threadIdx.x == 0) bulk_wait0();
 }
 
 // ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p)
@@ -129,6 +170,41 @@ __global__ void __launch_bounds__(256) state_diff_kernel(int rot, int n, int ne,
     }
 }
 
+// Tiled state_diff for rigid bodies: one thread per knot computes all 12 error components (one quaternion product instead of
+// three), the tile leaves through shared memory with unit-stride stores.
+template <class T, int NP, int TILE>
+__global__ void __launch_bounds__(TILE) state_diff_tile_kernel(int rot, long long N, const T* __restrict__ X, int ldx, const T* __restrict__ X0, int ldx0,
+                                                                T* __restrict__ dX) {
+    constexpr int ne = 12;
+    __shared__ T img[TILE][ne + 1];
+    const long long ntiles = (N + TILE - 1) / TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long k0 = tile * TILE;
+        const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const T* x = X + (k0 + threadIdx.x) * ldx;
+            const T* x0 = X0 + (k0 + threadIdx.x) * ldx0;
+            T* o = img[threadIdx.x];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) o[i] = x[i] - x0[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o[6 + i] = x[3 + NP + i] - x0[3 + NP + i];
+            T q[4], q0[4];
+            unit_quat(rot, x + 3, q);
+            unit_quat(rot, x0 + 3, q0);
+            const T c0 = q0[0], c1 = -q0[1], c2 = -q0[2], c3 = -q0[3];     // conj(q0) (x) q, then the Cayley map vec / scalar
+            const T ie0 = T(1) / (c0 * q[0] - c1 * q[1] - c2 * q[2] - c3 * q[3]);
+            o[3] = (c0 * q[1] + c1 * q[0] + c2 * q[3] - c3 * q[2]) * ie0;
+            o[4] = (c0 * q[2] - c1 * q[3] + c2 * q[0] + c3 * q[1]) * ie0;
+            o[5] = (c0 * q[3] + c1 * q[2] - c2 * q[1] + c3 * q[0]) * ie0;
+        }
+        __syncthreads();
+        T* out = dX + k0 * ne;
+        for (int e = threadIdx.x; e < cnt * ne; e += TILE) { const int kt = e / ne; out[e] = img[kt][e - kt * ne]; }
+    }
+}
+
 static unsigned grid_for(long long total, int sm_count) {
     long long g = (total + 255) / 256;
     const long long cap = (long long)sm_count * 8;
@@ -138,6 +214,23 @@ static unsigned grid_for(long long total, int sm_count) {
 
 int lie_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, void* G, int sm_count, cudaStream_t st) {
     if (N <= 0) return 0;
+    if (rot != ROT_NONE && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {      // rigid bodies, 16-byte aligned output: TMA image kernel
+        const int np = rot == ROT_QUAT ? 4 : 3;
+        const int TILE = dtype == 0 ? 64 : 32;
+        const size_t smem = size_t(2) * TILE * (9 + np) * 12 * (dtype == 0 ? 4 : 8);
+        const long long ntiles = (N + TILE - 1) / TILE, cap = (long long)sm_count * 2;
+        const unsigned g = unsigned(ntiles < cap ? ntiles : cap);
+        auto go = [&](auto kern, auto* x, auto* out) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return int(e);
+            kern<<<g, TILE, smem, st>>>(rot, N, x, ldx, out);
+            return int(cudaGetLastError());
+        };
+        if (dtype == 0) return np == 4 ? go(errstate_jacobian_tma_kernel<float, 4, 64>, (const float*)X, (float*)G)
+                                       : go(errstate_jacobian_tma_kernel<float, 3, 64>, (const float*)X, (float*)G);
+        return np == 4 ? go(errstate_jacobian_tma_kernel<double, 4, 32>, (const double*)X, (double*)G)
+                       : go(errstate_jacobian_tma_kernel<double, 3, 32>, (const double*)X, (double*)G);
+    }
     const unsigned g = grid_for(N * (long long)n * ne, sm_count);
     if (dtype == 0) errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (float*)G);
     else errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (double*)G);
@@ -154,6 +247,19 @@ int lie_grad_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, c
 int lie_state_diff(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, const void* X0, int ldx0, void* dX,
                    int sm_count, cudaStream_t st) {
     if (N <= 0) return 0;
+    if (rot != ROT_NONE) {
+        constexpr int TILE = 128;
+        const long long ntiles = (N + TILE - 1) / TILE, cap = (long long)sm_count * 12;
+        const unsigned g = unsigned(ntiles < cap ? ntiles : cap);
+        if (dtype == 0) {
+            if (rot == ROT_QUAT) state_diff_tile_kernel<float, 4, TILE><<<g, TILE, 0, st>>>(rot, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
+            else state_diff_tile_kernel<float, 3, TILE><<<g, TILE, 0, st>>>(rot, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
+        } else {
+            if (rot == ROT_QUAT) state_diff_tile_kernel<double, 4, TILE><<<g, TILE, 0, st>>>(rot, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);
+            else state_diff_tile_kernel<double, 3, TILE><<<g, TILE, 0, st>>>(rot, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);
+        }
+        return int(cudaGetLastError());
+    }
     const unsigned g = grid_for(N * (long long)ne, sm_count);
     if (dtype == 0) state_diff_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
     else state_diff_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);

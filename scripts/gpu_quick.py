@@ -70,6 +70,38 @@ def bench_err(name, gm, Q, dtype, N, dt=0.01, iters=20):
     print(f"BENCH-ERR {name:20s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
 
 
+def bench_misc():
+    """LieState kernels and rollout: device-resident timings."""
+    qd = rd.Quadrotor()
+    rng = np.random.default_rng(3)
+    N = 1 << 20
+    X = torch.from_numpy(rand_inputs(qd._h, N, rng).astype(np.float32)).cuda()
+    G = torch.empty((N, 12, 13), dtype=torch.float32, device='cuda')
+    d = torch.empty((N, 12), dtype=torch.float32, device='cuda')
+    def timeit(f, iters=20):
+        for _ in range(3): f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters): f()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+    t = timeit(lambda: qd._h.errstate_jacobian(X, G=G))
+    print(f"BENCH-MISC errstate_jacobian fp32 N={N}: {t*1e6:.1f} us  {N*4*(4+156)/t/1e9:.0f} GB/s (read q 16 B + write G 624 B per knot)", flush=True)
+    X0 = X.flip(0).contiguous()
+    t = timeit(lambda: qd._h.state_diff(X, X0, dX=d))
+    print(f"BENCH-MISC state_diff fp32 N={N}: {t*1e6:.1f} us  {N*4*(34+12)/t/1e9:.0f} GB/s", flush=True)
+    ntraj, K = 4096, 256
+    x0 = X[:ntraj, :13].contiguous(); U = torch.rand((ntraj, K - 1, 4), dtype=torch.float32, device='cuda')
+    Xo = torch.empty((ntraj, K, 13), dtype=torch.float32, device='cuda')
+    t = timeit(lambda: qd._h.rollout(3, x0, U, 0.01, X=Xo), iters=5)
+    print(f"BENCH-MISC rollout quadrotor RK4 fp32 {ntraj} x {K}: {t*1e3:.2f} ms  {ntraj*(K-1)/t:.3e} steps/s", flush=True)
+    cp = rd.Cartpole()
+    x0c = torch.rand((ntraj, 4), dtype=torch.float64, device='cuda'); Uc = torch.rand((ntraj, K - 1, 1), dtype=torch.float64, device='cuda')
+    t = timeit(lambda: cp._h.rollout(3, x0c, Uc, 0.01), iters=5)
+    print(f"BENCH-MISC rollout cartpole RK4 fp64 {ntraj} x {K}: {t*1e3:.2f} ms  {ntraj*(K-1)/t:.3e} steps/s", flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     cp, cpo = rd.Cartpole(), o.cartpole()
@@ -86,6 +118,7 @@ if __name__ == "__main__":
     check("body quat body", rd.Body(bodyframe=True), o.body(o.ROT_QUAT, o.BODYFRAME), 3, np.float64)
     check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
+    bench_misc()
     bench_err("quadrotor", qd, 3, np.float32, 262144)
     bench_err("quadrotor", qd, 3, np.float64, 262144)
     bench_err("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float64, 1 << 20, dt=0.1)

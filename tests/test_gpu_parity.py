@@ -550,3 +550,33 @@ def test_sixteen_million_knots_64bit_indexing(rd, torch_):
     idx = torch_.cat([torch_.arange(0, N, 65521, device="cuda"), torch_.arange(N - 40, N, device="cuda")])
     ref = o.discrete_jacobian(o.cartpole(), o.RK4, Z[idx].cpu().numpy().astype(np.float64), 0.01)
     assert np.abs(J[idx].cpu().numpy() - ref).max() < 1e-4
+
+
+def test_calls_are_cuda_graph_capturable(rd, torch_):
+    """Device-pointer calls only enqueue work on the caller's stream (no syncs, no allocations), so a solver can capture its
+    whole linearisation step in a CUDA graph and replay it (launch-bound regimes: many small batches)."""
+    cp, qd = rd.Cartpole(), rd.Quadrotor()
+    rng = np.random.default_rng(101)
+    Zc = dev(torch_, rng.random((5000, 5)))
+    Zq = dev(torch_, rand_inputs(13, 4, 3000, rng).astype(np.float32))
+    Jc = torch_.zeros((5000, 5, 4), dtype=torch_.float64, device="cuda")
+    Jq = torch_.zeros((3000, 17, 13), dtype=torch_.float32, device="cuda")
+    Gq = torch_.zeros((3000, 12, 13), dtype=torch_.float32, device="cuda")
+    def step():
+        cp._h.discrete_jacobian(o.RK4, Zc, 0.01, J=Jc)
+        qd._h.discrete_jacobian(o.RK4, Zq, 0.01, J=Jq)
+        qd._h.errstate_jacobian(Zq, G=Gq)
+    step()                                                        # warm-up outside capture (kernel attributes, occupancy query)
+    torch_.cuda.synchronize()
+    ref_c, ref_q = Jc.clone(), Jq.clone()
+    g = torch_.cuda.CUDAGraph()
+    s = torch_.cuda.Stream()
+    with torch_.cuda.stream(s):
+        with torch_.cuda.graph(g, stream=s):
+            step()
+    Jc.zero_(); Jq.zero_(); Gq.zero_()
+    Zc.mul_(0.5)                                                  # new inputs, same buffers
+    g.replay()
+    torch_.cuda.synchronize()
+    assert np.abs(Jc.cpu().numpy() - o.discrete_jacobian(o.cartpole(), o.RK4, Zc.cpu().numpy(), 0.01)).max() < 1e-10
+    assert torch_.equal(Jq, ref_q) and not torch_.equal(Jc, ref_c) and float(Gq.abs().sum()) > 0
