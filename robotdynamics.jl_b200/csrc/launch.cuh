@@ -1,6 +1,5 @@
 // launch.cuh — per-(model, dtype) tiling configuration and the host-side launcher of knot_kernel.
 #pragma once
-#include <cstdio>
 #include "kernels.cuh"
 
 namespace rdb {

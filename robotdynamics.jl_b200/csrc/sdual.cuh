@@ -33,7 +33,6 @@ using mask_t = uint32_t;
 __host__ __device__ constexpr int cpopc(mask_t m) { int c = 0; while (m) { c += int(m & 1u); m >>= 1; } return c; }
 __host__ __device__ constexpr bool chas(mask_t m, int j) { return (m >> j) & 1u; }
 __host__ __device__ constexpr int cslot(mask_t m, int j) { return cpopc(m & ((mask_t(1) << j) - 1u)); }
-__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 template <class T> struct ident { using type = T; };
 template <class T> using ident_t = typename ident<T>::type;
