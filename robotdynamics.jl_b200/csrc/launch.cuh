@@ -32,14 +32,13 @@ struct KnotConfigDefault<Model, float, true, Q, std::enable_if_t<(Model::n >= 12
     static constexpr int n = Model::n, m = Model::m, NZ = n + m;
     static constexpr bool heavy = (Q == Q_RK3 || Q == Q_RK4);
     static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
-    static constexpr int TILE = (heavy && m == 4) ? 128 : 64;
-    static constexpr int MINB = (heavy && m == 4) ? 1 : 2;
-    // m = 4: two wide roles.  World-frame quaternion models split after w1 ({r,q,v,w0,w1} {w2,u}: 51 us on C3); body-frame and
-    // 3-parameter attitudes couple more rows to v and w and balance better split after v ({r,att,v} {w,u}: quadrotor body frame
-    // 162 -> 137 us, quadrotor{MRP} 78 -> 74 us; profiles/tuning_r01.md).
+    static constexpr int TILE = heavy ? 128 : 64;
+    static constexpr int MINB = heavy ? 1 : 2;
+    // RK3 / RK4: two wide roles.  World-frame quaternion models split after w1 ({r,q,v,w0,w1} {w2,u}: C3 51 us, Body 67 -> 58 us);
+    // body-frame and 3-parameter attitudes couple more rows to v and w and balance better split after v ({r,att,v} {w,u}:
+    // quadrotor body frame 162 -> 137 us, quadrotor{MRP} 78 -> 74 us; profiles/tuning_r01.md).
     static constexpr int split = (Model::rot == ROT_QUAT && Model::frame == FRAME_WORLD) ? n - 1 : n - 3;
-    using Heavy = std::conditional_t<m == 4, MaskList<range_mask(0, split), range_mask(split, NZ)>,
-                                              MaskList<range_mask(0, n - 3), range_mask(n - 3, n + 2), range_mask(n + 2, NZ)>>;  // {r,att,v} {w,u0,u1} {u2..u5}
+    using Heavy = MaskList<range_mask(0, split), range_mask(split, NZ)>;
     using Light = std::conditional_t<m == 4, MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, NZ)>,            // {r,att} {v,w} {u}
                                               MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + 3), range_mask(n + 3, NZ)>>;
     using Chunks = std::conditional_t<heavy, Heavy, Light>;

@@ -20,6 +20,7 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
     "quadrotor": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "cartpole": ("cartpole_f64", dict(RDB_KIND=0, RDB_DTYPE=1)),
     "quaderr": ("quad_quat_world_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
+    "bodyquat": ("body_quat_world_f32", dict(RDB_KIND=2, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=0)),
     "quadmrp": ("quad_mrp_world_f32", dict(RDB_KIND=1, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=0)),
     "quadbody": ("quad_quat_body_f32", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=0)),
     "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
@@ -48,6 +49,13 @@ VARIANTS = {
         "roll2_3r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
         "roll1_3rc": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1C00u", RDB_TUNE_C2="0x1E000u"),
         "roll1_2rc": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x1FC00u"),
+    },
+    "bodyquat": {
+        "base": {},
+        "2r_a": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x7F000u"),
+        "2r_b": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x7FC00u"),
+        "3r_t128": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3FFu", RDB_TUNE_C1="0x7C00u", RDB_TUNE_C2="0x78000u"),
+        "3r_b": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0xF000u", RDB_TUNE_C2="0x70000u"),
     },
     "quadmrp": {
         "base": {},
@@ -135,7 +143,7 @@ import rdb200 as rd
 import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
-wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor"}.get(name, name)
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor", "bodyquat": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
 if name == "quadrotor64": dtn = "float64"
@@ -143,6 +151,7 @@ if len(sys.argv) > 3: N = int(sys.argv[3])
 mk, Q = bench.gpu_model(wl, rd)
 if name == 'quadbody': mk = lambda: rd.Quadrotor(bodyframe=True)
 if name == 'quadmrp': mk = lambda: rd.Quadrotor(rd.MRP)
+if name == 'bodyquat': mk = lambda: rd.Body()
 model = mk(); h = model._h
 n, m = h.n, h.m
 nsets = 4
@@ -161,6 +170,7 @@ us = e0.elapsed_time(e1) / steps * 1e3
 omk, oQ = bench.oracle_model(wl)
 if name == 'quadbody': omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
 if name == 'quadmrp': omk = lambda: o.quadrotor(o.ROT_MRP)
+if name == 'bodyquat': omk = lambda: o.body()
 idx = np.arange(0, N, 4099)
 if ERR:
     err = 0.0
