@@ -58,10 +58,31 @@ RDB_HD auto rk4_rolled(const Model& model, const X& x, const U& u, T h) {
     return axpy(x, h / T(6), acc);
 }
 
+// RK3 (k3 at x - k1 + 2 k2, weights (1,4,1)/6) with stages 2 and 3 rolled over the saturated types.  P = x - h f1 stays in
+// its sparse stage-1 type; only the stage point, the accumulator and the current stage derivative are saturated.
+template <class T, class Model, class X, class U>
+RDB_HD auto rk3_rolled(const Model& model, const X& x, const U& u, T h) {
+    using XS = saturated_t<Model, T, X, U>;
+    using FS = decltype(model.f(rstd::declval<const XS&>(), u));
+    const auto f1 = model.f(x, u);
+    const auto P = axpy(x, -h, f1);
+    XS Xs = widen_vec<XS>(axpy(x, T(0.5) * h, f1));
+    FS acc = widen_vec<FS>(f1);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const FS f = model.f(Xs, u);
+        acc = axpy(acc, s == 0 ? T(4) : T(1), f);
+        if (s == 0) Xs = widen_vec<XS>(axpy(P, T(2) * h, f));
+    }
+    return axpy(x, h / T(6), acc);
+}
+
 template <int Q, class T, int ROLL = 0, class Model, class X, class U>
 RDB_HD auto integrate(const Model& model, const X& x, const U& u, T h) {
     if constexpr (Q == Q_RK4 && ROLL != 0) {
         return rk4_rolled<ROLL, T>(model, x, u, h);
+    } else if constexpr (Q == Q_RK3 && ROLL != 0) {
+        return rk3_rolled<T>(model, x, u, h);
     } else if constexpr (Q == Q_CONTINUOUS) {
         return model.f(x, u);
     } else if constexpr (Q == Q_EULER) {

@@ -31,7 +31,7 @@ template <class Model, int Q>
 struct KnotConfigDefault<Model, float, true, Q, std::enable_if_t<(Model::n >= 12)>> {
     static constexpr int n = Model::n, m = Model::m, NZ = n + m;
     static constexpr bool heavy = (Q == Q_RK3 || Q == Q_RK4);
-    static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
+    static constexpr int ROLL = heavy ? 1 : 0;
     static constexpr int TILE = heavy ? 128 : 64;
     static constexpr int MINB = heavy ? 1 : 2;
     // RK3 / RK4: two wide roles.  World-frame quaternion models split after w1 ({r,q,v,w0,w1} {w2,u}: C3 51 us, Body 67 -> 58 us);
@@ -48,7 +48,7 @@ template <class Model, int Q>
 struct KnotConfigDefault<Model, double, true, Q, std::enable_if_t<(Model::n >= 12)>> {
     static constexpr int n = Model::n, m = Model::m, NZ = n + m;
     static constexpr bool heavy = (Q == Q_RK3 || Q == Q_RK4);
-    static constexpr int ROLL = (Q == Q_RK4) ? 1 : 0;
+    static constexpr int ROLL = heavy ? 1 : 0;
     static constexpr int TILE = 64;
     static constexpr int MINB = heavy ? 1 : 2;
     using Heavy = MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + m / 2), range_mask(n + m / 2, NZ)>;   // {r,att} {v,w} {u lo} {u hi}
