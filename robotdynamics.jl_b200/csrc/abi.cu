@@ -11,6 +11,8 @@
 #include "units.h"
 #include "lie.h"
 #include "custom.h"
+#include "layout.h"
+#include <map>
 
 using namespace rdb;
 
@@ -26,9 +28,14 @@ struct Slot {
 };
 }  // namespace
 
+// knot-major scratch for component-major callers, one set per stream that has used it
+struct SoaScratch { void* buf[3] = {nullptr, nullptr, nullptr}; size_t cap[3] = {0, 0, 0}; };
+
 struct rdb_context {
     int device = 0;
     int sm_count = 0;
+    std::map<cudaStream_t, SoaScratch> soa;   // guarded by soa_mu
+    std::mutex soa_mu;
     int pdl = 1;     // programmatic dependent launch of the knot kernels (RDB200_PDL=0 disables)
     Slot slot[NSLOT];
     std::mutex mu;   // the staging slots are shared by all host-pointer calls on this context
@@ -118,6 +125,40 @@ int dispatch(const rdb_model* M, int dtype, KnotRequest* r) {
     return fn ? fn(r) : RDB_ERR_NOT_IMPLEMENTED;
 }
 
+// Component-major ("SoA") callers: transpose a chunk of knots to the knot-major layout the kernels stream, evaluate, transpose the
+// results back.  All on the caller's stream; scratch is per (context, stream), so calls on one stream simply queue up.
+constexpr size_t SOA_SCRATCH_BYTES = size_t(256) << 20;     // knot-major Jacobian scratch per stream: bounds the chunk length
+int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long ld) {
+    rdb_context* c = M->ctx;
+    const size_t es = esize(dtype);
+    const int n = M->n, NZ = M->n + M->m, E = r.err ? M->nerr * (M->nerr + M->m) : n * NZ;
+    SoaScratch* sc;
+    { std::lock_guard<std::mutex> lock(c->soa_mu); sc = &c->soa[r.stream]; }
+    long long SOA_CHUNK = (long long)(SOA_SCRATCH_BYTES / (size_t(E) * es));
+    SOA_CHUNK = SOA_CHUNK < 1024 ? 1024 : (SOA_CHUNK / 1024) * 1024;
+    const long long cap = r.N < SOA_CHUNK ? r.N : SOA_CHUNK;
+    const size_t need[3] = {size_t(cap) * NZ * es, r.J ? size_t(cap) * E * es : 0, r.out ? size_t(cap) * n * es : 0};
+    for (int i = 0; i < 3; ++i)
+        if (need[i] > sc->cap[i]) {
+            if (sc->buf[i]) RDB_CUDA(cudaFree(sc->buf[i]));
+            sc->buf[i] = nullptr; sc->cap[i] = 0;
+            RDB_CUDA(cudaMalloc(&sc->buf[i], need[i]));
+            sc->cap[i] = need[i];
+        }
+    for (long long k0 = 0; k0 < r.N; k0 += SOA_CHUNK) {
+        const long long cnt = (r.N - k0 < SOA_CHUNK) ? (r.N - k0) : SOA_CHUNK;
+        int rc = soa_to_aos(dtype, (const char*)r.Z + size_t(k0) * es, ld, sc->buf[0], NZ, cnt, r.stream);
+        if (rc) return rc;
+        KnotRequest q = r;
+        q.Z = sc->buf[0]; q.J = r.J ? sc->buf[1] : nullptr; q.out = r.out ? sc->buf[2] : nullptr; q.N = cnt;
+        q.dt = r.dt ? r.dt + k0 : nullptr;
+        if ((rc = dispatch(M, dtype, &q))) return rc;
+        if (r.J && (rc = aos_to_soa(dtype, sc->buf[1], (char*)r.J + size_t(k0) * es, ld, E, cnt, r.stream))) return rc;
+        if (r.out && (rc = aos_to_soa(dtype, sc->buf[2], (char*)r.out + size_t(k0) * es, ld, n, cnt, r.stream))) return rc;
+    }
+    return 0;
+}
+
 // The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
 int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* dt,
             double dt0, void* J, void* out, void* stream, int err = 0) {
@@ -134,10 +175,10 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     std::memset(&r, 0, sizeof(r));
     if (M->rot == RDB_ROT_NONE) err = 0;     // EuclideanState: G = I (src/statevectortype.jl:149-155)
     r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.err = err; r.params = M->p;
-    r.dt0 = dt0; r.layout = layout; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
+    r.dt0 = dt0; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
         r.Z = Z; r.dt = dt; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
-        return dispatch(M, dtype, &r);
+        return layout == RDB_SOA ? dispatch_soa(M, dtype, r, N) : dispatch(M, dtype, &r);
     }
     // host pointers: H2D -> kernel -> D2H per chunk, chunks round-robin over NSLOT streams so the three overlap
     std::lock_guard<std::mutex> lock(c->mu);
@@ -157,7 +198,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
         if (dt && (rc = cuda_rc(cudaMemcpyAsync(s.buf[B_DT], dt + k0, size_t(cnt) * 8, cudaMemcpyHostToDevice, s.st)))) break;
         r.Z = s.buf[B_Z]; r.dt = dt ? (const double*)s.buf[B_DT] : nullptr;
         r.J = J ? s.buf[B_J] : nullptr; r.out = out ? s.buf[B_OUT] : nullptr; r.N = cnt; r.stream = s.st;
-        if ((rc = dispatch(M, dtype, &r))) break;
+        if ((rc = (layout == RDB_SOA ? dispatch_soa(M, dtype, r, cnt) : dispatch(M, dtype, &r)))) break;
         if (J && (rc = copy_chunk(J, s.buf[B_J], layout, es, E, N, k0, cnt, cudaMemcpyDeviceToHost, s.st))) break;
         if (out && (rc = copy_chunk(out, s.buf[B_OUT], layout, es, n, N, k0, cnt, cudaMemcpyDeviceToHost, s.st))) break;
     }
@@ -223,6 +264,8 @@ int rdb_destroy(rdb_context* c) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         for (auto& b : s.buf) if (b) cudaFree(b);
     }
+    cudaDeviceSynchronize();
+    for (auto& kv : c->soa) for (auto& b : kv.second.buf) if (b) cudaFree(b);
     delete c;
     return 0;
 }

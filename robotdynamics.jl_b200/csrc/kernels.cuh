@@ -15,8 +15,9 @@
 //     TMA bulk copy (cp.async.bulk + mbarrier complete_tx, double-buffered, prefetched one tile ahead), results
 //     are assembled as the exact output image in shared memory and leave by one TMA bulk store per tile that
 //     drains while the next tile computes.  No per-element global address arithmetic exists on that path.
-//   * component-major ("SoA") callers, unaligned pointers and the ragged last tile use a cooperative
-//     coalesced copy between the same shared-memory images and global memory.
+//   * unaligned pointers and the ragged last tile use a cooperative coalesced copy between the same shared-memory images
+//     and global memory; component-major ("SoA") callers are served by coalesced transposes around this kernel (layout.cu):
+//     one contiguous stream per tile is what HBM and the TMA engine like, 221 streams a megabyte apart are not.
 #pragma once
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
@@ -29,14 +30,13 @@ enum Layout { LAYOUT_AOS = 0, LAYOUT_SOA = 1 };
 
 template <class T>
 struct KnotArgs {
-    const T* Z;          // [x;u] per knot: AOS (N, n+m) knot-major  |  SOA (n+m, N) component-major
+    const T* Z;          // [x;u] per knot, knot-major (N, n+m)
     const double* dt;    // per-knot step (N) or nullptr -> dt0      (KnotPoint.dt is Float64: src/knotpoint.jl:148-153)
     double dt0;
-    T* J;                // AOS (N, n+m, n) == per knot n x (n+m) column-major | SOA (n*(n+m), N);  may be nullptr
+    T* J;                // (N, n+m, n): per knot an n x (n+m) column-major matrix;  may be nullptr
                          // (error-state mode: nerr x (nerr+m) per knot instead)
-    T* out;              // xdot or x+ : AOS (N, n) | SOA (n, N);  may be nullptr
+    T* out;              // xdot or x+, (N, n);  may be nullptr
     long long N;
-    int layout;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copies (TMA engine; SASS: UBLKCP / SYNCS) ------------------------
@@ -214,33 +214,26 @@ __device__ __forceinline__ void dispatch_role(int role, const Model& model, cons
     }
 }
 
-// cooperative copies between a knot-major smem image [cnt][W] (row pitch P >= W) and global memory
+// cooperative copies between a knot-major smem image [cnt][W] (row pitch P >= W) and knot-major global memory: the fallback for
+// unaligned pointers and the ragged last tile (component-major callers are transposed outside the kernel, layout.cu)
 template <class T>
-__device__ __forceinline__ void coop_load(T* img, int P, const T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
-    if (layout == LAYOUT_AOS) {
-        if (P == W) {
-            const T* src = g + k0 * W;
-            for (int i = tid; i < cnt * W; i += nthr) img[i] = src[i];
-        } else {
-            const int lane = tid & 31, nw = nthr >> 5;
-            for (int r = tid >> 5; r < cnt; r += nw) { const T* src = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) img[r * P + e] = src[e]; }
-        }
+__device__ __forceinline__ void coop_load(T* img, int P, const T* g, long long k0, int cnt, int W, int tid, int nthr) {
+    if (P == W) {
+        const T* src = g + k0 * W;
+        for (int i = tid; i < cnt * W; i += nthr) img[i] = src[i];
     } else {
-        for (int i = tid; i < cnt * W; i += nthr) { const int c = i / cnt, kt = i - c * cnt; img[kt * P + c] = g[(long long)c * N + k0 + kt]; }
+        const int lane = tid & 31, nw = nthr >> 5;
+        for (int r = tid >> 5; r < cnt; r += nw) { const T* src = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) img[r * P + e] = src[e]; }
     }
 }
 template <class T>
-__device__ __forceinline__ void coop_store(const T* img, int P, T* g, long long k0, int cnt, int W, long long N, int layout, int tid, int nthr) {
-    if (layout == LAYOUT_AOS) {
-        if (P == W) {
-            T* dst = g + k0 * W;
-            for (int i = tid; i < cnt * W; i += nthr) dst[i] = img[i];
-        } else {   // one warp per knot row: conflict-free smem reads (unit stride), fully coalesced global writes
-            const int lane = tid & 31, nw = nthr >> 5;
-            for (int r = tid >> 5; r < cnt; r += nw) { T* dst = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) dst[e] = img[r * P + e]; }
-        }
-    } else {
-        for (int i = tid; i < cnt * W; i += nthr) { const int c = i / cnt, kt = i - c * cnt; g[(long long)c * N + k0 + kt] = img[kt * P + c]; }
+__device__ __forceinline__ void coop_store(const T* img, int P, T* g, long long k0, int cnt, int W, int tid, int nthr) {
+    if (P == W) {
+        T* dst = g + k0 * W;
+        for (int i = tid; i < cnt * W; i += nthr) dst[i] = img[i];
+    } else {   // one warp per knot row: conflict-free smem reads (unit stride), fully coalesced global writes
+        const int lane = tid & 31, nw = nthr >> 5;
+        for (int r = tid >> 5; r < cnt; r += nw) { T* dst = g + (k0 + r) * W; for (int e = lane; e < W; e += 32) dst[e] = img[r * P + e]; }
     }
 }
 
@@ -312,7 +305,7 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
     const bool want_j = WITH_J && a.J != nullptr;
     const bool want_o = a.out != nullptr;
     // TMA path needs the reference's knot-major layout and 16-byte aligned streams
-    const bool tma_ok = a.layout == LAYOUT_AOS && ((reinterpret_cast<uintptr_t>(a.Z) | reinterpret_cast<uintptr_t>(a.J) |
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(a.Z) | reinterpret_cast<uintptr_t>(a.J) |
                                                     reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
     auto tile_tma = [&](long long tile) { return tma_ok && (tile + 1) * TILE <= N; };
 
@@ -342,7 +335,7 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
         // (2) this tile's inputs
         const bool tma = tile_tma(tile);
         if (tma) { mbar_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1; }
-        else { coop_load(in_img[s], NZ, a.Z, k0, cnt, NZ, N, a.layout, tid, NTHR); __syncthreads(); }
+        else { coop_load(in_img[s], NZ, a.Z, k0, cnt, NZ, tid, NTHR); __syncthreads(); }
         // (3) compute in registers
         const T* zrow = in_img[s] + kt * NZ;
         T h = T(0);
@@ -368,8 +361,8 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
             }
         } else {
             __syncthreads();
-            if (want_j) coop_store(j_img, S::PJ, a.J, k0, cnt, E, N, a.layout, tid, NTHR);
-            if (want_o) coop_store(o_img, n, a.out, k0, cnt, n, N, a.layout, tid, NTHR);
+            if (want_j) coop_store(j_img, S::PJ, a.J, k0, cnt, E, tid, NTHR);
+            if (want_o) coop_store(o_img, n, a.out, k0, cnt, n, tid, NTHR);
         }
     }
     if (tid < S::ISSUERS) bulk_wait0();

@@ -160,7 +160,7 @@ struct KnotRequest {
     int with_j;
     int err;             // error-state Jacobian  G(x+)' [A B] blkdiag(G(x), I)  (rigid bodies; needs with_j)
     ModelParams<double> params;
-    const void* Z; const double* dt; double dt0; void* J; void* out; long long N; int layout;
+    const void* Z; const double* dt; double dt0; void* J; void* out; long long N;   // knot-major (component-major is handled in abi.cu)
     // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)
     const void* x0; const void* U; void* X; long long ntraj; int K;
     DeviceInfo dev;
@@ -183,7 +183,7 @@ inline int run_one(const KnotRequest& r) {
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
-    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.layout = r.layout;
+    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N;
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
 template <template <class> class ModelT, class T, int Q>

@@ -70,6 +70,22 @@ def bench_err(name, gm, Q, dtype, N, dt=0.01, iters=20):
     print(f"BENCH-ERR {name:20s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
 
 
+def bench_soa(name, gm, Q, dtype, N, dt=0.01, iters=10):
+    rng = np.random.default_rng(2)
+    n, m = gm._h.n, gm._h.m
+    Z = torch.from_numpy(np.ascontiguousarray(rand_inputs(gm._h, N, rng).astype(dtype).T)).cuda()
+    J = torch.empty((n * (n + m), N), dtype=Z.dtype, device='cuda')
+    for _ in range(3): gm._h.discrete_jacobian(Q, Z, dt, J=J, layout=rd.SOA)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): gm._h.discrete_jacobian(Q, Z, dt, J=J, layout=rd.SOA)
+    e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / iters * 1e-3
+    gbs = N * Z.element_size() * ((n + m) + n * (n + m)) / t / 1e9
+    print(f"BENCH-SOA {name:20s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
+
+
 def bench_misc():
     """LieState kernels and rollout: device-resident timings."""
     qd = rd.Quadrotor()
@@ -119,6 +135,8 @@ if __name__ == "__main__":
     check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
     bench_misc()
+    bench_soa("cartpole", cp, 3, np.float64, 1 << 20)
+    bench_soa("quadrotor", qd, 3, np.float32, 262144)
     bench_err("quadrotor", qd, 3, np.float32, 262144)
     bench_err("quadrotor", qd, 3, np.float64, 262144)
     bench_err("satellite mrp rk2", rd.Satellite(rd.MRP), 1, np.float64, 1 << 20, dt=0.1)

@@ -126,7 +126,7 @@ def build_variants(workload):
             if "Compiling entry function" in l and "knot_kernel" in l and want in l and "ELb1E" in l:
                 info = " ".join(x.strip() for x in lines[i + 1:i + 4] if "registers" in x or "spill" in x)
         subprocess.check_call([B.NVCC] + B.ARCH + ["-shared", "-o", lib, obj, stub_obj, os.path.join(B.OBJ, "abi.o"), os.path.join(B.OBJ, "lie.o"),
-                               os.path.join(B.OBJ, "custom.o"), "-cudart", "static", "-lnvrtc"])
+                               os.path.join(B.OBJ, "custom.o"), os.path.join(B.OBJ, "layout.o"), "-cudart", "static", "-lnvrtc"])
         os.remove(obj)
         return tag, info
 
