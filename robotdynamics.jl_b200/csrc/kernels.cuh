@@ -176,6 +176,7 @@ __device__ __forceinline__ auto project_err(const XN& xn) {
 template <int NTHR, int ISSUERS>
 __device__ __forceinline__ void images_free_barrier(int tid) {
     if (tid < ISSUERS) bulk_wait_read0();      // bulk groups are per thread: every thread that issued stores waits for its own
+    __syncwarp();                              // bar.sync is an aligned barrier: the warp must be converged when it executes it
     asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
 }
 
