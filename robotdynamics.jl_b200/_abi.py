@@ -117,13 +117,18 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
+_DTYPE_CODES = {}          # dtype object -> F32 / F64 (filled lazily: a per-call string conversion costs more than the launch)
+
+
 def dtype_code(a):
-    name = str(a.dtype).replace("torch.", "")
-    if name == "float32":
-        return F32
-    if name == "float64":
-        return F64
-    raise TypeError(f"rdb200 computes in float32 or float64, got {a.dtype}")
+    dt = a.dtype
+    code = _DTYPE_CODES.get(dt)
+    if code is None:
+        name = str(dt).replace("torch.", "")
+        if name not in ("float32", "float64"):
+            raise TypeError(f"rdb200 computes in float32 or float64, got {a.dtype}")
+        code = _DTYPE_CODES[dt] = F32 if name == "float32" else F64
+    return code
 
 
 def ptr(a):
@@ -160,6 +165,8 @@ def as_f64(a, like):
         return None
     if _is_torch(like):
         import torch
+        if _is_torch(a) and a.dtype == torch.float64 and a.device == like.device and a.is_contiguous():
+            return a
         return torch.as_tensor(a, dtype=torch.float64, device=like.device).contiguous()
     return np.ascontiguousarray(a, dtype=np.float64)
 
