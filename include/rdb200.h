@@ -36,8 +36,10 @@ typedef struct rdb_model rdb_model;     /* immutable model description; replaces
 typedef enum { RDB_F32 = 0, RDB_F64 = 1 } rdb_dtype;
 typedef enum { RDB_AOS = 0, RDB_SOA = 1 } rdb_layout;
 /* QuadratureRule subtypes: src/integration.jl:69 (Euler), :109 (RK3), :258 (RK4); RK2 = explicit midpoint
- * (v0.3 name kept by BASELINE; semantics pinned by test/old_tests/linear_tests.jl:135-141). */
-typedef enum { RDB_EULER = 0, RDB_RK2 = 1, RDB_RK3 = 2, RDB_RK4 = 3 } rdb_integrator;
+ * (v0.3 name kept by BASELINE; semantics pinned by test/old_tests/linear_tests.jl:135-141).  ImplicitMidpoint: src/integration.jl:620
+ * (Newton solve :422-463, implicit-function-theorem Jacobian :524-543); accepted by rdb_discrete_dynamics / rdb_discrete_jacobian
+ * for the built-in models. */
+typedef enum { RDB_EULER = 0, RDB_RK2 = 1, RDB_RK3 = 2, RDB_RK4 = 3, RDB_IMPLICIT_MIDPOINT = 4 } rdb_integrator;
 /* model families: test/cartpole_model.jl, test/quadrotor.jl, test/rigidbody_test.jl:23-56 (= the Satellite of
  * examples/single_satellite.jl:7-35 with other parameters), test/double_integrator.jl:97-127 */
 typedef enum { RDB_CARTPOLE = 0, RDB_QUADROTOR = 1, RDB_BODY = 2, RDB_DOUBLE_INTEGRATOR = 3, RDB_CUSTOM = 4 } rdb_model_kind;

@@ -127,6 +127,23 @@ def step(model, Q, x, u, h):
     return x + (k1 + 2 * k2 + 2 * k3 + k4) / 6
 
 
+def implicit_midpoint_step(model, x, u, h, iters=30):
+    """x2 solving x + h f((x + x2)/2, u) - x2 = 0 by Newton with a complex-step Jacobian of the residual; works on complex
+    inputs, so differentiating THROUGH the converged solve by complex step gives the implicit-function-theorem Jacobian
+    (reference: src/integration.jl:422-463, 524-543, 620-694) without forming it."""
+    x = np.asarray(x, dtype=complex); u = np.asarray(u, dtype=complex)
+    x2 = x.copy()
+    n = len(x)
+    for _ in range(iters):
+        r = x + h * model.f((x + x2) / 2, u) - x2
+        # d r / d x2 at the REAL part (the imaginary parts are O(1e-30) perturbations carried along linearly)
+        xr, ur, x2r = np.real(x), np.real(u), np.real(x2)
+        A = np.stack([np.imag(xr + h * model.f((xr + x2r + 1e-30j * np.eye(n)[j]) / 2, ur.astype(complex)) - (x2r + 1e-30j * np.eye(n)[j])) / 1e-30
+                      for j in range(n)], axis=1)
+        x2 = x2 - np.linalg.solve(A.astype(complex), r)
+    return x2
+
+
 def complex_step_jacobian(fun, z, h=1e-30):
     z = np.asarray(z, dtype=complex)
     cols = []
@@ -139,6 +156,8 @@ def complex_step_jacobian(fun, z, h=1e-30):
 
 def discrete_jacobian(model, Q, z, h):
     n = model.n
+    if Q == "implicit_midpoint":
+        return complex_step_jacobian(lambda zz: implicit_midpoint_step(model, zz[:n], zz[n:], h), z)
     return complex_step_jacobian(lambda zz: step(model, Q, zz[:n], zz[n:], h), z)
 
 

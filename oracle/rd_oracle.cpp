@@ -74,7 +74,7 @@ template <int NP> inline double val(const Dual<NP>& a) { return a.v; }
 enum Kind { CARTPOLE = 0, QUADROTOR = 1, BODY = 2, DOUBLE_INTEGRATOR = 3 };
 enum Rot { ROT_NONE = 0, ROT_QUAT = 1, ROT_MRP = 2, ROT_RP = 3 };
 enum Frame { FRAME_WORLD = 0, FRAME_BODY = 1 };
-enum Quad { EULER = 0, RK2 = 1, RK3 = 2, RK4 = 3 };
+enum Quad { EULER = 0, RK2 = 1, RK3 = 2, RK4 = 3, IMPLICIT_MIDPOINT = 4 };
 
 struct Model {
     int kind, rot, frame;
@@ -446,6 +446,64 @@ static void jac_chain(const Model& M, int Q, const double* z, double t, double h
 }
 
 // ---------------------------------------------------------------------------------------------
+// ImplicitMidpoint — src/integration.jl:422-463 (Newton solve), :524-543 (implicit-function-theorem Jacobian),
+// :620-694 (residual x1 + h f((x1+x2)/2, u1, t+h/2) - x2 and its Jacobians J1 = [I + h/2 A, h B], J2 = h/2 A - I).
+// Newton: x2 <- x1; up to 10 iterations; Jacobians are evaluated BEFORE the convergence test ||r||_2 < 1e-12, so on exit they
+// belong to the returned iterate; J = -(J2 \ J1).  LU with partial pivoting like LAPACK getrf (src/utils.jl:32-54).
+// ---------------------------------------------------------------------------------------------
+static void lu_solve_inplace(int n, double* A /* n x n col-major, destroyed */, int nrhs, double* B /* n x nrhs col-major */) {
+    for (int k = 0; k < n; ++k) {
+        int p = k; double best = std::fabs(A[k + n * k]);
+        for (int i = k + 1; i < n; ++i) if (std::fabs(A[i + n * k]) > best) { best = std::fabs(A[i + n * k]); p = i; }
+        if (p != k) {
+            for (int j = 0; j < n; ++j) std::swap(A[k + n * j], A[p + n * j]);
+            for (int j = 0; j < nrhs; ++j) std::swap(B[k + n * j], B[p + n * j]);
+        }
+        const double inv = 1.0 / A[k + n * k];
+        for (int i = k + 1; i < n; ++i) {
+            const double l = A[i + n * k] * inv;
+            A[i + n * k] = l;
+            for (int j = k + 1; j < n; ++j) A[i + n * j] -= l * A[k + n * j];
+            for (int j = 0; j < nrhs; ++j) B[i + n * j] -= l * B[k + n * j];
+        }
+    }
+    for (int j = 0; j < nrhs; ++j)
+        for (int i = n - 1; i >= 0; --i) {
+            double s = B[i + n * j];
+            for (int c = i + 1; c < n; ++c) s -= A[i + n * c] * B[c + n * j];
+            B[i + n * j] = s / A[i + n * i];
+        }
+}
+
+static void implicit_midpoint(const Model& M, const double* z, double t, double h, double* xn, double* J /* may be null */) {
+    const int n = M.n, m = M.m, nz = n + m;
+    const double* x = z; const double* u = z + n;
+    double x2[NMAX], xm[NMAX], f[NMAX], r[NMAX];
+    double J1[NMAX * (NMAX + 6)], A2[NMAX * NMAX], W[NMAX * NMAX];
+    for (int i = 0; i < n; ++i) x2[i] = x[i];
+    for (int iter = 0; iter < 10; ++iter) {
+        for (int i = 0; i < n; ++i) xm[i] = (x[i] + x2[i]) / 2;
+        dynamics<double>(M, xm, u, t + h / 2, f);
+        double nrm = 0;
+        for (int i = 0; i < n; ++i) { r[i] = x[i] + h * f[i] - x2[i]; nrm += r[i] * r[i]; }
+        cont_jacobian(M, xm, u, t + h / 2, J1);
+        for (int i = 0; i < n * nz; ++i) J1[i] *= h;
+        for (int i = 0; i < n * n; ++i) { J1[i] /= 2; A2[i] = J1[i]; }
+        for (int i = 0; i < n; ++i) { J1[i + n * i] += 1.0; A2[i + n * i] -= 1.0; }
+        if (std::sqrt(nrm) < 1e-12) break;
+        for (int i = 0; i < n * n; ++i) W[i] = A2[i];
+        lu_solve_inplace(n, W, 1, r);
+        for (int i = 0; i < n; ++i) x2[i] -= r[i];
+    }
+    for (int i = 0; i < n; ++i) xn[i] = x2[i];
+    if (J) {
+        for (int i = 0; i < n * n; ++i) W[i] = A2[i];
+        for (int i = 0; i < n * nz; ++i) J[i] = -J1[i];
+        lu_solve_inplace(n, W, nz, J);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LieState error-state maps — src/liestate.jl:210-320 for LieState(R, (3,6)) (src/rigidbody.jl:48),
 // Euclidean fall-backs src/statevectortype.jl:144-155.
 // ---------------------------------------------------------------------------------------------
@@ -577,7 +635,8 @@ int rdo_discrete_dynamics(int kind, int rot, int frame, const double* params, in
     const int nz = M.n + M.m;
     RDO_LOOP(N, nthreads) {
         const double* z = Z + k * nz;
-        integrate<double>(M, Q, z, z + M.n, t ? t[k] : 0.0, dt ? dt[k] : dt0, xn + k * M.n);
+        if (Q == IMPLICIT_MIDPOINT) implicit_midpoint(M, z, t ? t[k] : 0.0, dt ? dt[k] : dt0, xn + k * M.n, nullptr);
+        else integrate<double>(M, Q, z, z + M.n, t ? t[k] : 0.0, dt ? dt[k] : dt0, xn + k * M.n);
     }
     return 0;
 }
@@ -603,7 +662,8 @@ int rdo_discrete_jacobian(int kind, int rot, int frame, const double* params, in
     RDO_LOOP(N, nthreads) {
         const double* z = Z + k * nz;
         double tk = t ? t[k] : 0.0, hk = dt ? dt[k] : dt0;
-        if (method == 0) jac_ad_dispatch(M, Q, z, tk, hk, J + k * nj);
+        if (Q == IMPLICIT_MIDPOINT) { double xn[NMAX]; implicit_midpoint(M, z, tk, hk, xn, J + k * nj); }
+        else if (method == 0) jac_ad_dispatch(M, Q, z, tk, hk, J + k * nj);
         else jac_chain(M, Q, z, tk, hk, J + k * nj);
     }
     return 0;

@@ -20,7 +20,7 @@ _LIB = None
 CARTPOLE, QUADROTOR, BODY, DOUBLE_INTEGRATOR = 0, 1, 2, 3
 ROT_NONE, ROT_QUAT, ROT_MRP, ROT_RP = 0, 1, 2, 3
 WORLD, BODYFRAME = 0, 1
-EULER, RK2, RK3, RK4 = 0, 1, 2, 3
+EULER, RK2, RK3, RK4, IMPLICIT_MIDPOINT = 0, 1, 2, 3, 4
 AD, CHAIN = 0, 1
 
 

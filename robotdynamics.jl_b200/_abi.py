@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("RDB200_LIB") or os.path.join(_PKG, "librdb200.so")   
 
 F32, F64 = 0, 1
 AOS, SOA = 0, 1
-EULER, RK2, RK3, RK4 = 0, 1, 2, 3
+EULER, RK2, RK3, RK4, IMPLICIT_MIDPOINT = 0, 1, 2, 3, 4
 CARTPOLE, QUADROTOR, BODY, DOUBLE_INTEGRATOR, CUSTOM = 0, 1, 2, 3, 4
 ROT_NONE, ROT_QUAT, ROT_MRP, ROT_RP = 0, 1, 2, 3
 FRAME_WORLD, FRAME_BODY = 0, 1

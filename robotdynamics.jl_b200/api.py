@@ -41,6 +41,7 @@ class Euler(QuadratureRule): code = _abi.EULER
 class RK2(QuadratureRule): code = _abi.RK2
 class RK3(QuadratureRule): code = _abi.RK3
 class RK4(QuadratureRule): code = _abi.RK4
+class ImplicitMidpoint(QuadratureRule): code = _abi.IMPLICIT_MIDPOINT
 
 class QuatRotation: code = _abi.ROT_QUAT
 class UnitQuaternion(QuatRotation): pass

@@ -114,6 +114,7 @@ int sync_slots(rdb_context* c) {
 int map_q(int integrator) {
     switch (integrator) {
         case RDB_EULER: return Q_EULER; case RDB_RK2: return Q_RK2; case RDB_RK3: return Q_RK3; case RDB_RK4: return Q_RK4;
+        case RDB_IMPLICIT_MIDPOINT: return Q_IMPLICIT_MIDPOINT;
     }
     return -1;
 }

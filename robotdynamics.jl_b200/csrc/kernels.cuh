@@ -369,6 +369,81 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
     if (tid < S::ISSUERS) bulk_wait0();
 }
 
+// ---- ImplicitMidpoint ----------------------------------------------------------------------------------------------------
+// x2 solves  x1 + h f((x1 + x2)/2, u1) - x2 = 0  (reference: src/integration.jl:620-694): Newton from x2 = x1, at most 10 iterations,
+// residual and Jacobians evaluated before the convergence test ||r||_2 < tol, step dx = (h/2 A - I) \ r by LU with partial
+// pivoting (src/integration.jl:422-463, src/utils.jl:32-54); Jacobian by the implicit function theorem, J = -(h/2 A - I) \ [I + h/2 A, h B]
+// (src/integration.jl:524-543).  One thread per knot: the continuous Jacobian comes from ONE forward-mode evaluation with all n+m
+// columns seeded (it is sparse, so it fits registers); the small dense solves run on per-thread local arrays.
+template <class T, int N_>
+__device__ __forceinline__ void lu_solve_inplace(T* A /* N_ x N_ col-major, destroyed */, int nrhs, T* B /* N_ x nrhs col-major */) {
+    for (int k = 0; k < N_; ++k) {
+        int p = k; T best = fabs(A[k + N_ * k]);
+        for (int i = k + 1; i < N_; ++i) { const T v = fabs(A[i + N_ * k]); if (v > best) { best = v; p = i; } }
+        if (p != k) {
+            for (int j = 0; j < N_; ++j) { const T t = A[k + N_ * j]; A[k + N_ * j] = A[p + N_ * j]; A[p + N_ * j] = t; }
+            for (int j = 0; j < nrhs; ++j) { const T t = B[k + N_ * j]; B[k + N_ * j] = B[p + N_ * j]; B[p + N_ * j] = t; }
+        }
+        const T inv = T(1) / A[k + N_ * k];
+        for (int i = k + 1; i < N_; ++i) {
+            const T l = A[i + N_ * k] * inv;
+            for (int j = k + 1; j < N_; ++j) A[i + N_ * j] -= l * A[k + N_ * j];
+            for (int j = 0; j < nrhs; ++j) B[i + N_ * j] -= l * B[k + N_ * j];
+        }
+    }
+    for (int j = 0; j < nrhs; ++j)
+        for (int i = N_ - 1; i >= 0; --i) {
+            T s = B[i + N_ * j];
+            for (int c = i + 1; c < N_; ++c) s -= A[i + N_ * c] * B[c + N_ * j];
+            B[i + N_ * j] = s / A[i + N_ * i];
+        }
+}
+
+template <class Model, class T, bool WITH_J>
+__global__ void __launch_bounds__(128) implicit_midpoint_kernel(const Model model, const KnotArgs<T> a) {
+    constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    constexpr mask_t ALL = (NZ >= 32) ? ~mask_t(0) : ((mask_t(1) << NZ) - 1u);
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const T* z = a.Z + k * NZ;
+    const T h = T(a.dt ? a.dt[k] : a.dt0);
+    const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
+    T zm[NZ], x2[n], r[n], J1[n * NZ], A2[n * n], W[n * n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x2[i] = z[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) zm[n + i] = z[n + i];
+    for (int iter = 0; iter < 10; ++iter) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) zm[i] = (z[i] + x2[i]) * T(0.5);
+        model.reset();
+        auto zz = load_seeded<T, ALL>(zm, rstd::make_index_sequence<size_t(NZ)>{});
+        auto f = model.f(slice<0, n>(zz), slice<n, m>(zz));
+        put_vals(f, r, rstd::make_index_sequence<size_t(n)>{});
+        put_cols<n, ALL, false>(f, J1, rstd::make_index_sequence<size_t(NZ)>{});
+        T nrm = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { r[i] = z[i] + h * r[i] - x2[i]; nrm += r[i] * r[i]; }
+        for (int i = 0; i < n * NZ; ++i) J1[i] *= h;
+        for (int i = 0; i < n * n; ++i) { J1[i] *= T(0.5); A2[i] = J1[i]; }
+        for (int i = 0; i < n; ++i) { J1[i + n * i] += T(1); A2[i + n * i] -= T(1); }
+        if (sqrt(nrm) < tol) break;
+        for (int i = 0; i < n * n; ++i) W[i] = A2[i];
+        lu_solve_inplace<T, n>(W, 1, r);
+        for (int i = 0; i < n; ++i) x2[i] -= r[i];
+    }
+    if (a.out) { T* o = a.out + k * n; for (int i = 0; i < n; ++i) o[i] = x2[i]; }
+    if constexpr (WITH_J) {
+        if (a.J) {
+            for (int i = 0; i < n * n; ++i) W[i] = A2[i];
+            for (int i = 0; i < n * NZ; ++i) J1[i] = -J1[i];
+            lu_solve_inplace<T, n>(W, NZ, J1);
+            T* Jo = a.J + k * (long long)(n * NZ);
+            for (int i = 0; i < n * NZ; ++i) Jo[i] = J1[i];
+        }
+    }
+}
+
 // rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
 // (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
 template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, rstd::index_sequence<Is...>) { return vec(p[Is]...); }

@@ -186,6 +186,19 @@ inline int run_one(const KnotRequest& r) {
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N;
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
+template <template <class> class ModelT, class T>
+inline int run_implicit(const KnotRequest& r) {
+    if (r.op != OP_KNOT || r.err) return -2;
+    ModelT<T> model; model.p = cast_params<T>(r.params);
+    KnotArgs<T> a;
+    a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
+    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N;
+    if (r.N <= 0) return 0;
+    const unsigned grid = unsigned((r.N + 127) / 128);
+    if (r.with_j) implicit_midpoint_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, a);
+    else implicit_midpoint_kernel<ModelT<T>, T, false><<<grid, 128, 0, r.stream>>>(model, a);
+    return int(cudaGetLastError());
+}
 template <template <class> class ModelT, class T, int Q>
 inline int run_rollout(const KnotRequest& r) {
     if constexpr (Q == Q_CONTINUOUS) return -2;
@@ -215,6 +228,7 @@ inline int run_t(const KnotRequest& r) {
         case Q_RK3: return run_q<ModelT, T, Q_RK3>(r);
         case Q_RK4: return run_q<ModelT, T, Q_RK4>(r);
         case Q_CONTINUOUS: return run_q<ModelT, T, Q_CONTINUOUS>(r);
+        case Q_IMPLICIT_MIDPOINT: return run_implicit<ModelT, T>(r);
     }
     return -2;
 }

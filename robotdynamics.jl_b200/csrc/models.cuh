@@ -18,7 +18,7 @@ namespace rdb {
 enum ModelKind { KIND_CARTPOLE = 0, KIND_QUADROTOR = 1, KIND_BODY = 2, KIND_DOUBLE_INTEGRATOR = 3 };
 enum RotKind { ROT_NONE = 0, ROT_QUAT = 1, ROT_MRP = 2, ROT_RP = 3 };
 enum FrameKind { FRAME_WORLD = 0, FRAME_BODY = 1 };
-enum QuadRule { Q_EULER = 0, Q_RK2 = 1, Q_RK3 = 2, Q_RK4 = 3, Q_CONTINUOUS = 4 };
+enum QuadRule { Q_EULER = 0, Q_RK2 = 1, Q_RK3 = 2, Q_RK4 = 3, Q_CONTINUOUS = 4, Q_IMPLICIT_MIDPOINT = 5 };
 
 // Parameter block shared by host and device (passed to kernels by value).
 template <class T>

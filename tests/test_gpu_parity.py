@@ -580,3 +580,28 @@ def test_calls_are_cuda_graph_capturable(rd, torch_):
     torch_.cuda.synchronize()
     assert np.abs(Jc.cpu().numpy() - o.discrete_jacobian(o.cartpole(), o.RK4, Zc.cpu().numpy(), 0.01)).max() < 1e-10
     assert torch_.equal(Jq, ref_q) and not torch_.equal(Jc, ref_c) and float(Gq.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("name", ["cartpole", "quad_quat_world", "body_mrp_body", "satellite_mrp", "di3"])
+def test_implicit_midpoint(rd, torch_, name):
+    """ImplicitMidpoint on the GPU (per-thread Newton + pivoted LU + implicit-function-theorem Jacobian) against the oracle."""
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    N = 900
+    Z = rand_inputs(om.n, om.m, N, np.random.default_rng(111))
+    dt = np.random.default_rng(112).uniform(0.005, 0.1, N)
+    ref_J = o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z, dt)
+    ref_x = o.discrete_dynamics(om, o.IMPLICIT_MIDPOINT, Z, dt)
+    xn = np.empty((N, om.n))
+    J = gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, Z, dt, xn=xn)
+    assert np.abs(J - ref_J).max() < 1e-10 and np.abs(xn - ref_x).max() < 1e-10
+    Jd = gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, dev(torch_, Z), dt)
+    xd = gm._h.discrete_dynamics(rd._abi.IMPLICIT_MIDPOINT, dev(torch_, Z), dt)
+    assert np.array_equal(Jd.cpu().numpy(), J) and np.abs(xd.cpu().numpy() - ref_x).max() < 1e-10
+    Z32 = Z.astype(np.float32)
+    J32 = gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, Z32, dt)
+    assert np.abs(J32 - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z32.astype(np.float64), dt)).max() < 2e-4
+    # reference-facing spelling
+    dm = rd.DiscretizedDynamics(gm, rd.ImplicitMidpoint)
+    Jm, y = np.zeros((om.n, om.n + om.m)), np.zeros(om.n)
+    rd.jacobian_(rd.InPlace(), rd.ForwardAD(), dm, Jm, y, rd.KnotPoint(Z[0, :om.n], Z[0, om.n:], 0.0, float(dt[0])))
+    assert np.abs(Jm - o.as_matrix(ref_J)[0]).max() < 1e-10 and np.abs(y - ref_x[0]).max() < 1e-10
