@@ -62,10 +62,36 @@ handle(m) = throw(RD.NotImplementedError("no B200 kernel for $(typeof(m))"))
 #       [m.mass; vec(Matrix(m.J)'); m.gravity; m.motor_dist; m.kf; m.km])
 # handle(m::Satellite{R}) where R = Handle(KIND_BODY, rotcode(R), framecode(m), [m.mass; vec(Matrix(m.J)')])
 
+"""
+    custom_handle(n, m, f_body; params=Float64[])
+
+Any user `dynamics(model, x, u)`: `f_body` is the CUDA C++ body of `f(x, u)` (see include/rdb200.h, rdb_model_create_custom); the
+library compiles it with NVRTC and differentiates it by forward mode, like `@autodiff` does on the CPU (src/jacobian_gen.jl:64-82).
+"""
+function custom_handle(n::Integer, m::Integer, f_body::AbstractString; params::Vector{Float64}=Float64[])
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:rdb_model_create_custom, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cstring, Ptr{Cdouble}, Cint, Ref{Ptr{Cvoid}}),
+               context().ptr, n, m, f_body, params, length(params), r)
+    rc == -5 && error("user model does not compile:\n" * unsafe_string(ccall((:rdb_last_log, LIB), Cstring, ())))
+    check(rc, "rdb_model_create_custom")
+    finalizer(h -> ccall((:rdb_model_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr), Handle(r[]))
+end
+
+"RigidBody{R} with user forces / moments (src/rigidbody.jl:244-257): `wrench_body` returns vec(F_world..., tau_body...)."
+function custom_rigid_handle(::Type{R}, m::Integer, wrench_body::AbstractString, mass::Real, J::AbstractMatrix;
+                             params::Vector{Float64}=Float64[], bodyframe::Bool=false) where {R}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    Jrow = collect(Float64, vec(Matrix(J)'))
+    check(ccall((:rdb_model_create_custom_rigid, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Cstring, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ref{Ptr{Cvoid}}),
+                context().ptr, rotcode(R), Cint(bodyframe), m, wrench_body, mass, Jrow, params, length(params), r), "rdb_model_create_custom_rigid")
+    finalizer(h -> ccall((:rdb_model_destroy, LIB), Cint, (Ptr{Cvoid},), h.ptr), Handle(r[]))
+end
+
 const HANDLES = IdDict{Any,Handle}()
 gethandle(m) = get!(() -> handle(m), HANDLES, m)
 
-const INTEGRATOR = Dict{Any,Cint}(RD.Euler => 0, RD.RK3 => 2, RD.RK4 => 3)    # RK2 = 1: the v0.3 name, add when it returns to src/
+const INTEGRATOR = Dict{Any,Cint}(RD.Euler => 0, RD.RK3 => 2, RD.RK4 => 3, RD.ImplicitMidpoint => 4)   # RK2 = 1: the v0.3 name, add when it returns to src/
 dtypecode(::Type{Float32}) = Cint(0); dtypecode(::Type{Float64}) = Cint(1)
 
 # ---- gather / scatter between the reference containers and the batched images ---------------------------------------
