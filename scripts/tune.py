@@ -65,15 +65,10 @@ VARIANTS = {
     },
     "quadrotor64": {
         "base": {},
-        "roll1_c3": dict(RDB_TUNE_ROLL=1),
-        "roll1_2r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
-        "roll1_3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
-        "roll2_3r": dict(RDB_TUNE_ROLL=2, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
-        "roll1_4r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
-        "roll1_5r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x380u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x6000u", RDB_TUNE_C4="0x18000u"),
-        "roll1_5r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x380u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x6000u", RDB_TUNE_C4="0x18000u"),
-        "roll1_6r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x60u", RDB_TUNE_C2="0x380u", RDB_TUNE_C3="0x1C00u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
-        "roll1_4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x6000u", RDB_TUNE_C3="0x18000u"),
+        "4rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0x7C0u", RDB_TUNE_C2="0x3800u", RDB_TUNE_C3="0x1C000u"),
+        "4rc": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0xF80u", RDB_TUNE_C2="0x7000u", RDB_TUNE_C3="0x18000u"),
+        "5rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x3E0u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x6000u", RDB_TUNE_C4="0x18000u"),
+        "3rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFu", RDB_TUNE_C1="0x1F00u", RDB_TUNE_C2="0x1E000u"),
     },
     "cartpole": {
         "base": {},
