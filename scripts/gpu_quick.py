@@ -135,6 +135,9 @@ if __name__ == "__main__":
     check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
     bench_misc()
+    bench("cartpole implicit-midpoint", cp, 4, np.float64, 1 << 20)
+    bench("quadrotor implicit-midpoint", qd, 4, np.float32, 262144)
+    bench("quadrotor implicit-midpoint", qd, 4, np.float64, 262144)
     bench_soa("cartpole", cp, 3, np.float64, 1 << 20)
     bench_soa("quadrotor", qd, 3, np.float32, 262144)
     bench_err("quadrotor", qd, 3, np.float32, 262144)
