@@ -18,7 +18,7 @@ using namespace rdb;
 
 namespace {
 constexpr int NSLOT = 3;                 // pipeline depth of the host-pointer path
-constexpr long long HOST_CHUNK = 1 << 16;  // knot points per pipelined chunk
+constexpr long long HOST_CHUNK_DEFAULT = 1 << 16;  // knot points per pipelined chunk (RDB200_HOST_CHUNK overrides, for experiments)
 enum { B_Z = 0, B_DT = 1, B_J = 2, B_OUT = 3, B_AUX = 4, NBUF = 5 };
 
 struct Slot {
@@ -37,6 +37,7 @@ struct rdb_context {
     std::map<cudaStream_t, SoaScratch> soa;   // guarded by soa_mu
     std::mutex soa_mu;
     int pdl = 1;     // programmatic dependent launch of the knot kernels (RDB200_PDL=0 disables)
+    long long host_chunk = HOST_CHUNK_DEFAULT;
     Slot slot[NSLOT];
     std::mutex mu;   // the staging slots are shared by all host-pointer calls on this context
 };
@@ -187,6 +188,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     const int n = M->n, NZ = M->n + M->m, E = err ? M->nerr * (M->nerr + M->m) : n * NZ;
     int rc = 0;
     long long ci = 0;
+    const long long HOST_CHUNK = c->host_chunk;
     const long long cap_knots = N < HOST_CHUNK ? N : HOST_CHUNK;
     for (long long k0 = 0; k0 < N && !rc; k0 += HOST_CHUNK, ++ci) {
         const long long cnt = (N - k0 < HOST_CHUNK) ? (N - k0) : HOST_CHUNK;
@@ -253,6 +255,7 @@ int rdb_create(int device, rdb_context** ctx) {
     c->device = device;
     RDB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char* e = std::getenv("RDB200_PDL")) c->pdl = (e[0] != '0');
+    if (const char* e = std::getenv("RDB200_HOST_CHUNK")) { const long long v = std::atoll(e); if (v >= 1024) c->host_chunk = v; }
     for (auto& s : c->slot) RDB_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     *ctx = c;
     return 0;
