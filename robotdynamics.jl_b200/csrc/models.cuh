@@ -58,10 +58,10 @@ struct Cartpole {
         // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s]
         const T H00 = p.mc + p.mp, H11 = mpl * p.l;
         auto H01 = mpl * c;
-        auto r0 = -(mpl * (qd1 * s) * qd1) - get<0>(u);
+        auto r0 = -(mpl * (s * sq_(qd1))) - get<0>(u);
         auto r1 = (mpl * p.g) * s;
         // qdd = -H \ r   (closed-form 2x2 solve, like StaticArrays)
-        auto idet = T(1) / (H00 * H11 - H01 * H01);
+        auto idet = T(1) / (H00 * H11 - sq_(H01));
         auto qdd0 = (H01 * r1 - H11 * r0) * idet;
         auto qdd1 = (H01 * r0 - H00 * r1) * idet;
         return vec(qd0, qd1, qdd0, qdd1);
@@ -88,13 +88,24 @@ template <class T, class Q, class R>
 RDB_HD auto quat_rotate(const Q& q, const R& r) {
     const auto& w = get<0>(q);
     auto v = slice<1, 3>(q);
-    auto a = w * w - dot3(v, v);
+    auto a = sq_(w) - norm2_3(v);
     auto vr2 = T(2) * dot3(v, r);
     auto w2 = T(2) * w;
     auto c = cross3(v, r);
     return vec(a * get<0>(r) + get<0>(v) * vr2 + w2 * get<0>(c),
                a * get<1>(r) + get<1>(v) * vr2 + w2 * get<1>(c),
                a * get<2>(r) + get<2>(v) * vr2 + w2 * get<2>(c));
+}
+// q * [0, 0, s]: s times the third column of the (un-normalised) rotation matrix — 4 squares + 4 + 3 products instead of the
+// 9 products the general formula spends on a vector with two structural zeros
+template <class T, class Q, class S>
+RDB_HD auto quat_rotate_z(const Q& q, const S& s) {
+    const auto& w = get<0>(q); const auto& x = get<1>(q); const auto& y = get<2>(q); const auto& z = get<3>(q);
+    auto c0 = x * z + w * y;                         // half of R[0][2], R[1][2]: the 2 goes onto the scalar s (few partials)
+    auto c1 = y * z - w * x;
+    auto c2 = (sq_(w) + sq_(z)) - (sq_(x) + sq_(y));
+    auto s2 = T(2) * s;
+    return vec(c0 * s2, c1 * s2, c2 * s);
 }
 template <class Q> RDB_HD auto quat_conj(const Q& q) { return vec(get<0>(q), -get<1>(q), -get<2>(q), -get<3>(q)); }
 
@@ -103,12 +114,12 @@ template <class T, int ROT, class P>
 RDB_HD auto to_quat(const P& p) {
     if constexpr (ROT == ROT_QUAT) return p;
     else if constexpr (ROT == ROT_MRP) {
-        auto n2 = dot3(p, p);
+        auto n2 = norm2_3(p);
         auto i1 = T(1) / (T(1) + n2);
         auto M = T(2) * i1;
         return vec((T(1) - n2) * i1, M * get<0>(p), M * get<1>(p), M * get<2>(p));
     } else {
-        auto M = rsqrt_(T(1) + dot3(p, p));
+        auto M = rsqrt_(T(1) + norm2_3(p));
         return vec(M, M * get<0>(p), M * get<1>(p), M * get<2>(p));
     }
 }
@@ -128,7 +139,7 @@ RDB_HD auto rot_kinematics(const P& p, const W& w) {
         auto pw = dot3(p, w);
         auto c = cross3(p, w);
         if constexpr (ROT == ROT_MRP) {  // 1/4 [(1-|p|^2) I + 2 skew(p) + 2 p p'] w
-            auto a = T(1) - dot3(p, p);
+            auto a = T(1) - norm2_3(p);
             return vec(T(0.25) * (a * get<0>(w) + T(2) * (get<0>(c) + get<0>(p) * pw)),
                        T(0.25) * (a * get<1>(w) + T(2) * (get<1>(c) + get<1>(p) * pw)),
                        T(0.25) * (a * get<2>(w) + T(2) * (get<2>(c) + get<2>(p) * pw)));
@@ -162,9 +173,17 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
     auto tau = slice<3, 3>(xi);
     auto qdot = rot_kinematics<T, ROT>(att, w);
     // omega_dot = Jinv (tau - w x (J w))
-    auto Jw = [&]() { if constexpr (DIAG_INERTIA) return diag3_mul(p.J[0], p.J[4], p.J[8], w); else return mat3_mul(p.J, w); }();
-    auto rhs = vsub(tau, cross3(w, Jw));
-    auto wdot = [&]() { if constexpr (DIAG_INERTIA) return diag3_mul(p.Jinv[0], p.Jinv[4], p.Jinv[8], rhs); else return mat3_mul(p.Jinv, rhs); }();
+    auto wdot = [&]() {
+        if constexpr (DIAG_INERTIA) {      // w x (J w) = ((J3-J2) wy wz, (J1-J3) wz wx, (J2-J1) wx wy): three products instead of six
+            const auto& wx = get<0>(w); const auto& wy = get<1>(w); const auto& wz = get<2>(w);
+            const T J1 = p.J[0], J2 = p.J[4], J3 = p.J[8];
+            return vec(p.Jinv[0] * (get<0>(tau) - (J3 - J2) * (wy * wz)),
+                       p.Jinv[4] * (get<1>(tau) - (J1 - J3) * (wz * wx)),
+                       p.Jinv[8] * (get<2>(tau) - (J2 - J1) * (wx * wy)));
+        } else {
+            return mat3_mul(p.Jinv, vsub(tau, cross3(w, mat3_mul(p.J, w))));
+        }
+    }();
     if constexpr (FRAME == FRAME_WORLD) {
         return cat(v, qdot, Fm, wdot);
     } else {
@@ -194,7 +213,7 @@ struct RigidBody {
                 auto F2 = relu_(p.kf * get<1>(uu));
                 auto F3 = relu_(p.kf * get<2>(uu));
                 auto F4 = relu_(p.kf * get<3>(uu));
-                auto qF = quat_rotate<T>(q, vec(Zero{}, Zero{}, p.inv_mass * (F1 + F2 + F3 + F4)));
+                auto qF = quat_rotate_z<T>(q, p.inv_mass * (F1 + F2 + F3 + F4));
                 const T g0 = p.mg[0] * p.inv_mass, g1 = p.mg[1] * p.inv_mass, g2 = p.mg[2] * p.inv_mass;
                 auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
