@@ -61,9 +61,9 @@ struct Cartpole {
         auto r0 = -(mpl * (s * sq_(qd1))) - get<0>(u);
         auto r1 = (mpl * p.g) * s;
         // qdd = -H \ r   (closed-form 2x2 solve, like StaticArrays)
-        auto idet = T(1) / (H00 * H11 - sq_(H01));
-        auto qdd0 = (H01 * r1 - H11 * r0) * idet;
-        auto qdd1 = (H01 * r0 - H00 * r1) * idet;
+        auto idet = T(1) / sqadd<T, -1>(H01, H00 * H11);
+        auto qdd0 = fmadd<T, -1>(H11, r0, H01 * r1) * idet;
+        auto qdd1 = fmadd<T, -1>(H00, r1, H01 * r0) * idet;
         return vec(qd0, qd1, qdd0, qdd1);
     }
 };
@@ -88,22 +88,22 @@ template <class T, class Q, class R>
 RDB_HD auto quat_rotate(const Q& q, const R& r) {
     const auto& w = get<0>(q);
     auto v = slice<1, 3>(q);
-    auto a = sq_(w) - norm2_3(v);
-    auto vr2 = T(2) * dot3(v, r);
+    auto a = sq_(w) - norm2_3<T>(v);
+    auto vr2 = T(2) * dot3<T>(v, r);
     auto w2 = T(2) * w;
-    auto c = cross3(v, r);
-    return vec(a * get<0>(r) + get<0>(v) * vr2 + w2 * get<0>(c),
-               a * get<1>(r) + get<1>(v) * vr2 + w2 * get<1>(c),
-               a * get<2>(r) + get<2>(v) * vr2 + w2 * get<2>(c));
+    auto c = cross3<T>(v, r);
+    return vec(fmadd<T>(w2, get<0>(c), fmadd<T>(get<0>(v), vr2, a * get<0>(r))),
+               fmadd<T>(w2, get<1>(c), fmadd<T>(get<1>(v), vr2, a * get<1>(r))),
+               fmadd<T>(w2, get<2>(c), fmadd<T>(get<2>(v), vr2, a * get<2>(r))));
 }
 // q * [0, 0, s]: s times the third column of the (un-normalised) rotation matrix — 4 squares + 4 + 3 products instead of the
 // 9 products the general formula spends on a vector with two structural zeros
 template <class T, class Q, class S>
 RDB_HD auto quat_rotate_z(const Q& q, const S& s) {
     const auto& w = get<0>(q); const auto& x = get<1>(q); const auto& y = get<2>(q); const auto& z = get<3>(q);
-    auto c0 = x * z + w * y;                         // half of R[0][2], R[1][2]: the 2 goes onto the scalar s (few partials)
-    auto c1 = y * z - w * x;
-    auto c2 = (sq_(w) + sq_(z)) - (sq_(x) + sq_(y));
+    auto c0 = fmadd<T>(w, y, x * z);                 // half of R[0][2], R[1][2]: the 2 goes onto the scalar s (few partials)
+    auto c1 = fmadd<T, -1>(w, x, y * z);
+    auto c2 = sqadd<T, -1>(y, sqadd<T, -1>(x, sqadd<T>(z, sq_(w))));
     auto s2 = T(2) * s;
     return vec(c0 * s2, c1 * s2, c2 * s);
 }
@@ -114,12 +114,12 @@ template <class T, int ROT, class P>
 RDB_HD auto to_quat(const P& p) {
     if constexpr (ROT == ROT_QUAT) return p;
     else if constexpr (ROT == ROT_MRP) {
-        auto n2 = norm2_3(p);
+        auto n2 = norm2_3<T>(p);
         auto i1 = T(1) / (T(1) + n2);
         auto M = T(2) * i1;
         return vec((T(1) - n2) * i1, M * get<0>(p), M * get<1>(p), M * get<2>(p));
     } else {
-        auto M = rsqrt_(T(1) + norm2_3(p));
+        auto M = rsqrt_(T(1) + norm2_3<T>(p));
         return vec(M, M * get<0>(p), M * get<1>(p), M * get<2>(p));
     }
 }
@@ -131,15 +131,15 @@ RDB_HD auto rot_kinematics(const P& p, const W& w) {
         const auto& qw = get<0>(p); const auto& qx = get<1>(p); const auto& qy = get<2>(p); const auto& qz = get<3>(p);
         // the factor 1/2 is applied to w once (3 scalars) rather than to the 4 results (exact: a power of two)
         auto w0 = T(0.5) * get<0>(w); auto w1 = T(0.5) * get<1>(w); auto w2 = T(0.5) * get<2>(w);
-        return vec(-(qx * w0 + qy * w1 + qz * w2),
-                   qw * w0 + qy * w2 - qz * w1,
-                   qw * w1 + qz * w0 - qx * w2,
-                   qw * w2 + qx * w1 - qy * w0);
+        return vec(fmadd<T, -1>(qz, w2, fmadd<T, -1>(qy, w1, -(qx * w0))),
+                   fmadd<T, -1>(qz, w1, fmadd<T>(qy, w2, qw * w0)),
+                   fmadd<T, -1>(qx, w2, fmadd<T>(qz, w0, qw * w1)),
+                   fmadd<T, -1>(qy, w0, fmadd<T>(qx, w1, qw * w2)));
     } else {
-        auto pw = dot3(p, w);
-        auto c = cross3(p, w);
+        auto pw = dot3<T>(p, w);
+        auto c = cross3<T>(p, w);
         if constexpr (ROT == ROT_MRP) {  // 1/4 [(1-|p|^2) I + 2 skew(p) + 2 p p'] w
-            auto a = T(1) - norm2_3(p);
+            auto a = T(1) - norm2_3<T>(p);
             return vec(T(0.25) * (a * get<0>(w) + T(2) * (get<0>(c) + get<0>(p) * pw)),
                        T(0.25) * (a * get<1>(w) + T(2) * (get<1>(c) + get<1>(p) * pw)),
                        T(0.25) * (a * get<2>(w) + T(2) * (get<2>(c) + get<2>(p) * pw)));
@@ -177,18 +177,18 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
         if constexpr (DIAG_INERTIA) {      // w x (J w) = ((J3-J2) wy wz, (J1-J3) wz wx, (J2-J1) wx wy): three products instead of six
             const auto& wx = get<0>(w); const auto& wy = get<1>(w); const auto& wz = get<2>(w);
             const T J1 = p.J[0], J2 = p.J[4], J3 = p.J[8];
-            return vec(p.Jinv[0] * (get<0>(tau) - (J3 - J2) * (wy * wz)),
-                       p.Jinv[4] * (get<1>(tau) - (J1 - J3) * (wz * wx)),
-                       p.Jinv[8] * (get<2>(tau) - (J2 - J1) * (wx * wy)));
+            return vec(p.Jinv[0] * fmadd<T, -1>((J3 - J2) * wy, wz, get<0>(tau)),
+                       p.Jinv[4] * fmadd<T, -1>((J1 - J3) * wz, wx, get<1>(tau)),
+                       p.Jinv[8] * fmadd<T, -1>((J2 - J1) * wx, wy, get<2>(tau)));
         } else {
-            return mat3_mul(p.Jinv, vsub(tau, cross3(w, mat3_mul(p.J, w))));
+            return mat3_mul(p.Jinv, vsub(tau, cross3<T>(w, mat3_mul(p.J, w))));
         }
     }();
     if constexpr (FRAME == FRAME_WORLD) {
         return cat(v, qdot, Fm, wdot);
     } else {
         auto rdot = quat_rotate<T>(q, v);
-        auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3(w, v));
+        auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, v));
         return cat(rdot, qdot, vdot, wdot);
     }
 }

@@ -195,6 +195,72 @@ template <class T, mask_t A> RDB_HD SD<T, A> operator/(ident_t<T> b, const SD<T,
     const T ib = T(1) / a.v; const T q = b * ib; return scale_parts<T, A>(a, q, -q * ib);
 }
 
+// ---- fused  c + SGN * a * b  and  c + SGN * a^2 ---------------------------------------------------------------------------
+// The rigid-body kernels are bound by FP32 instruction issue; a product followed by an add costs FMUL + FFMA + FADD per partial
+// through the operators above (IEEE forbids re-associating it into an FMA chain).  Written as ONE accumulation the same value
+// costs two FFMAs per partial (one for a square): dot and cross products, matrix-vector products and the model formulas use it.
+template <class T, class X> struct opnd {                        // plain scalar operand
+    static constexpr mask_t mask = 0;
+    RDB_HD static T v(const X& x) { return x; }
+};
+template <class T, mask_t M> struct opnd<T, SD<T, M>> {
+    static constexpr mask_t mask = M;
+    RDB_HD static T v(const SD<T, M>& x) { return x.v; }
+    template <int J> RDB_HD static typename PK<T>::vec slot(const SD<T, M>& x) { return x.d[cslot(smask<T>(M), J)]; }
+};
+template <class T, class A, class B, class C, mask_t R, int J = 0>
+RDB_HD void fmadd_parts(SD<T, R>& r, const A& a, const B& b, const C& c, typename PK<T>::vec sav, typename PK<T>::vec sbv) {
+    constexpr mask_t SA = smask<T>(opnd<T, A>::mask), SB = smask<T>(opnd<T, B>::mask), SC = smask<T>(opnd<T, C>::mask), SR = smask<T>(R);
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SR, J)) {
+            constexpr bool ha = chas(SA, J), hb = chas(SB, J), hc = chas(SC, J);
+            typename PK<T>::vec acc = PK<T>::zero();
+            if constexpr (hc) acc = opnd<T, C>::template slot<J>(c);
+            if constexpr (ha) { if constexpr (hc) acc = PK<T>::fma(opnd<T, A>::template slot<J>(a), sbv, acc); else acc = PK<T>::mul(opnd<T, A>::template slot<J>(a), sbv); }
+            if constexpr (hb) { if constexpr (hc || ha) acc = PK<T>::fma(opnd<T, B>::template slot<J>(b), sav, acc); else acc = PK<T>::mul(opnd<T, B>::template slot<J>(b), sav); }
+            r.d[cslot(SR, J)] = acc;
+        }
+        fmadd_parts<T, A, B, C, R, J + 1>(r, a, b, c, sav, sbv);
+    }
+}
+// c + SGN * a * b   (SGN = +1 or -1); operands: plain T, SD<T,.> or Zero
+template <class T, int SGN = 1, class A, class B, class C>
+RDB_HD auto fmadd(const A& a, const B& b, const C& c) {
+    if constexpr (rstd::is_same<A, Zero>::value || rstd::is_same<B, Zero>::value) return c;
+    else if constexpr (rstd::is_same<C, Zero>::value) { if constexpr (SGN > 0) return a * b; else return -(a * b); }
+    else {
+        constexpr mask_t R = opnd<T, A>::mask | opnd<T, B>::mask | opnd<T, C>::mask;
+        const T av = opnd<T, A>::v(a), bv = opnd<T, B>::v(b), cv = opnd<T, C>::v(c);
+        const T sav = SGN > 0 ? av : -av, sbv = SGN > 0 ? bv : -bv;
+        if constexpr (R == 0) return sav * bv + cv;
+        else { SD<T, R> r; r.v = sav * bv + cv; fmadd_parts<T, A, B, C, R>(r, a, b, c, PK<T>::splat(sav), PK<T>::splat(sbv)); return r; }
+    }
+}
+template <class T, class A, class C, mask_t R, int J = 0>
+RDB_HD void sqadd_parts(SD<T, R>& r, const A& a, const C& c, typename PK<T>::vec s2a) {
+    constexpr mask_t SA = smask<T>(opnd<T, A>::mask), SC = smask<T>(opnd<T, C>::mask), SR = smask<T>(R);
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SR, J)) {
+            if constexpr (chas(SA, J) && chas(SC, J)) r.d[cslot(SR, J)] = PK<T>::fma(opnd<T, A>::template slot<J>(a), s2a, opnd<T, C>::template slot<J>(c));
+            else if constexpr (chas(SA, J)) r.d[cslot(SR, J)] = PK<T>::mul(opnd<T, A>::template slot<J>(a), s2a);
+            else r.d[cslot(SR, J)] = opnd<T, C>::template slot<J>(c);
+        }
+        sqadd_parts<T, A, C, R, J + 1>(r, a, c, s2a);
+    }
+}
+// c + SGN * a^2
+template <class T, int SGN = 1, class A, class C>
+RDB_HD auto sqadd(const A& a, const C& c) {
+    if constexpr (rstd::is_same<A, Zero>::value) return c;
+    else {
+        constexpr mask_t R = opnd<T, A>::mask | opnd<T, C>::mask;
+        const T av = opnd<T, A>::v(a), cv = opnd<T, C>::v(c);
+        const T sa = SGN > 0 ? av : -av;
+        if constexpr (R == 0) return sa * av + cv;
+        else { SD<T, R> r; r.v = sa * av + cv; sqadd_parts<T, A, C, R>(r, a, c, PK<T>::splat(sa + sa)); return r; }
+    }
+}
+
 // ---- Zero algebra -------------------------------------------------------------------------------
 RDB_HD Zero operator+(Zero, Zero) { return {}; }
 RDB_HD Zero operator-(Zero, Zero) { return {}; }
@@ -313,7 +379,7 @@ template <class... As, class... Bs> RDB_HD auto cat(const Vec<As...>& a, const V
 template <class A, class B, class C, class... R> RDB_HD auto cat(const A& a, const B& b, const C& c, const R&... r) { return cat(cat(a, b), c, r...); }
 
 // elementwise a + s*b, a + b, s*a, a - b  (s scalar of any numeric kind)
-template <class A, class S, class B, size_t... Is> RDB_HD auto axpy_impl(const A& a, const S& s, const B& b, rstd::index_sequence<Is...>) { return vec((get<int(Is)>(a) + s * get<int(Is)>(b))...); }
+template <class A, class S, class B, size_t... Is> RDB_HD auto axpy_impl(const A& a, const S& s, const B& b, rstd::index_sequence<Is...>) { return vec(fmadd<S>(s, get<int(Is)>(b), get<int(Is)>(a))...); }
 template <class A, class S, class B> RDB_HD auto axpy(const A& a, const S& s, const B& b) { return axpy_impl(a, s, b, iseq<A>{}); }
 template <class A, class B, size_t... Is> RDB_HD auto vadd_impl(const A& a, const B& b, rstd::index_sequence<Is...>) { return vec((get<int(Is)>(a) + get<int(Is)>(b))...); }
 template <class A, class B> RDB_HD auto vadd(const A& a, const B& b) { return vadd_impl(a, b, iseq<A>{}); }
@@ -323,18 +389,20 @@ template <class S, class A, size_t... Is> RDB_HD auto vscale_impl(const S& s, co
 template <class S, class A> RDB_HD auto vscale(const S& s, const A& a) { return vscale_impl(s, a, iseq<A>{}); }
 
 // 3-vector algebra on heterogeneous triples
-template <class A, class B> RDB_HD auto dot3(const A& a, const B& b) { return get<0>(a) * get<0>(b) + get<1>(a) * get<1>(b) + get<2>(a) * get<2>(b); }
-template <class V> RDB_HD auto norm2_3(const V& a) { return sq_(get<0>(a)) + sq_(get<1>(a)) + sq_(get<2>(a)); }
-template <class A, class B> RDB_HD auto cross3(const A& a, const B& b) {
-    return vec(get<1>(a) * get<2>(b) - get<2>(a) * get<1>(b),
-               get<2>(a) * get<0>(b) - get<0>(a) * get<2>(b),
-               get<0>(a) * get<1>(b) - get<1>(a) * get<0>(b));
+template <class T, class A, class B> RDB_HD auto dot3(const A& a, const B& b) {
+    return fmadd<T>(get<2>(a), get<2>(b), fmadd<T>(get<1>(a), get<1>(b), get<0>(a) * get<0>(b)));
+}
+template <class T, class V> RDB_HD auto norm2_3(const V& a) { return sqadd<T>(get<2>(a), sqadd<T>(get<1>(a), sq_(get<0>(a)))); }
+template <class T, class A, class B> RDB_HD auto cross3(const A& a, const B& b) {
+    return vec(fmadd<T, -1>(get<2>(a), get<1>(b), get<1>(a) * get<2>(b)),
+               fmadd<T, -1>(get<0>(a), get<2>(b), get<2>(a) * get<0>(b)),
+               fmadd<T, -1>(get<1>(a), get<0>(b), get<0>(a) * get<1>(b)));
 }
 // y = M x for a row-major 3x3 of plain scalars
 template <class T, class A> RDB_HD auto mat3_mul(const T* M, const A& x) {
-    return vec(M[0] * get<0>(x) + M[1] * get<1>(x) + M[2] * get<2>(x),
-               M[3] * get<0>(x) + M[4] * get<1>(x) + M[5] * get<2>(x),
-               M[6] * get<0>(x) + M[7] * get<1>(x) + M[8] * get<2>(x));
+    return vec(fmadd<T>(M[2], get<2>(x), fmadd<T>(M[1], get<1>(x), M[0] * get<0>(x))),
+               fmadd<T>(M[5], get<2>(x), fmadd<T>(M[4], get<1>(x), M[3] * get<0>(x))),
+               fmadd<T>(M[8], get<2>(x), fmadd<T>(M[7], get<1>(x), M[6] * get<0>(x))));
 }
 
 // ---------------------------------------------------------------------------------------------
