@@ -62,8 +62,8 @@ struct Cartpole {
         auto r1 = (mpl * p.g) * s;
         // qdd = -H \ r   (closed-form 2x2 solve, like StaticArrays)
         auto idet = T(1) / sqadd<T, -1>(H01, H00 * H11);
-        auto qdd0 = fmadd<T, -1>(H11, r0, H01 * r1) * idet;
         auto qdd1 = fmadd<T, -1>(H00, r1, H01 * r0) * idet;
+        auto qdd0 = fmadd<T>(H01, qdd1, r0) * (T(-1) / H00);     // first row of H qdd = -r (H00 is a constant): one dual product fewer
         return vec(qd0, qd1, qdd0, qdd1);
     }
 };
