@@ -55,15 +55,15 @@ struct Cartpole {
         else sincos_near(val(th), th0, s0, c0, sv, cv);
         auto s = th, c = th;
         sincos_with(th, sv, cv, s, c);
-        // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s]
-        const T H00 = p.mc + p.mp, H11 = mpl * p.l;
-        auto H01 = mpl * c;
-        auto r0 = -(mpl * (s * sq_(qd1))) - get<0>(u);
-        auto r1 = (mpl * p.g) * s;
-        // qdd = -H \ r   (closed-form 2x2 solve, like StaticArrays)
-        auto idet = T(1) / sqadd<T, -1>(H01, H00 * H11);
-        auto qdd1 = fmadd<T, -1>(H00, r1, H01 * r0) * idet;
-        auto qdd0 = fmadd<T>(H01, qdd1, r0) * (T(-1) / H00);     // first row of H qdd = -r (H00 is a constant): one dual product fewer
+        // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s];  qdd = -H \\ r  (closed-form 2x2 solve,
+        // like StaticArrays).  Both sides are divided by mp*l first, so the off-diagonal of H is just c and no partial is ever
+        // multiplied by that constant:  H' = [(mc+mp)/(mp l)  c; c  l],  r' = [-s qd1^2 - u/(mp l), g s].
+        const T ia = T(1) / mpl, H00 = (p.mc + p.mp) * ia, H11 = p.l;
+        auto r0 = fmadd<T, -1>(ia, get<0>(u), -(s * sq_(qd1)));
+        auto r1 = p.g * s;
+        auto idet = T(1) / sqadd<T, -1>(c, H00 * H11);
+        auto qdd1 = fmadd<T, -1>(H00, r1, c * r0) * idet;
+        auto qdd0 = fmadd<T>(c, qdd1, r0) * (T(-1) / H00);       // first row of H' qdd = -r' (H00 is a constant)
         return vec(qd0, qd1, qdd0, qdd1);
     }
 };
