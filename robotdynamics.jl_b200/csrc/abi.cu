@@ -293,6 +293,7 @@ int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const doubl
         case RDB_CARTPOLE:
             if (np < 4) return RDB_ERR_ARG;
             p.mc = params[0]; p.mp = params[1]; p.l = params[2]; p.g = params[3];
+            p.cp_ia = 1.0 / (p.mp * p.l); p.cp_H00 = (p.mc + p.mp) * p.cp_ia; p.cp_nH00i = -1.0 / p.cp_H00;
             M.rot = RDB_ROT_NONE; M.frame = 0; M.n = 4; M.m = 1; M.nerr = 4;
             break;
         case RDB_QUADROTOR:

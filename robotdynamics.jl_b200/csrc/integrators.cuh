@@ -55,7 +55,7 @@ RDB_HD auto rk4_rolled(const Model& model, const X& x, const U& u, T h) {
         const T c = (s == 2) ? h : T(0.5) * h;                 // next stage point: x + h/2 f1, x + h/2 f2, x + h f3
         if (s < 3) Xs = axpy(x, c, f);
     }
-    return axpy(x, h / T(6), acc);
+    return axpy(x, h * T(1.0 / 6.0), acc);
 }
 
 // RK3 (k3 at x - k1 + 2 k2, weights (1,4,1)/6) with stages 2 and 3 rolled over the saturated types.  P = x - h f1 stays in
@@ -74,7 +74,7 @@ RDB_HD auto rk3_rolled(const Model& model, const X& x, const U& u, T h) {
         acc = axpy(acc, s == 0 ? T(4) : T(1), f);
         if (s == 0) Xs = widen_vec<XS>(axpy(P, T(2) * h, f));
     }
-    return axpy(x, h / T(6), acc);
+    return axpy(x, h * T(1.0 / 6.0), acc);
 }
 
 template <int Q, class T, int ROLL = 0, class Model, class X, class U>
@@ -96,7 +96,7 @@ RDB_HD auto integrate(const Model& model, const X& x, const U& u, T h) {
         auto f2 = model.f(axpy(x, T(0.5) * h, f1), u);
         auto f3 = model.f(axpy(axpy(x, -h, f1), T(2) * h, f2), u);
         auto acc = axpy(vadd(f1, f3), T(4), f2);
-        return axpy(x, h / T(6), acc);
+        return axpy(x, h * T(1.0 / 6.0), acc);
     } else {
         static_assert(Q == Q_RK4, "unknown quadrature rule");
         auto f1 = model.f(x, u);
@@ -105,7 +105,7 @@ RDB_HD auto integrate(const Model& model, const X& x, const U& u, T h) {
         auto f3 = model.f(axpy(x, T(0.5) * h, f2), u);
         auto acc2 = axpy(acc1, T(2), f3);
         auto f4 = model.f(axpy(x, h, f3), u);
-        return axpy(x, h / T(6), vadd(acc2, f4));
+        return axpy(x, h * T(1.0 / 6.0), vadd(acc2, f4));
     }
 }
 

@@ -176,6 +176,7 @@ template <class T>
 inline ModelParams<T> cast_params(const ModelParams<double>& p) {
     ModelParams<T> q;
     q.mc = T(p.mc); q.mp = T(p.mp); q.l = T(p.l); q.g = T(p.g);
+    q.cp_ia = T(p.cp_ia); q.cp_H00 = T(p.cp_H00); q.cp_nH00i = T(p.cp_nH00i);
     q.mass = T(p.mass); q.inv_mass = T(p.inv_mass);
     for (int i = 0; i < 9; ++i) { q.J[i] = T(p.J[i]); q.Jinv[i] = T(p.Jinv[i]); }
     for (int i = 0; i < 3; ++i) q.mg[i] = T(p.mg[i]);

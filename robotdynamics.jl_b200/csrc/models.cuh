@@ -23,8 +23,9 @@ enum QuadRule { Q_EULER = 0, Q_RK2 = 1, Q_RK3 = 2, Q_RK4 = 3, Q_CONTINUOUS = 4, 
 // Parameter block shared by host and device (passed to kernels by value).
 template <class T>
 struct ModelParams {
-    // cartpole
+    // cartpole (+ constants derived on the host so that no thread divides: 1/(mp l), (mc+mp)/(mp l), -(mp l)/(mc+mp))
     T mc, mp, l, g;
+    T cp_ia, cp_H00, cp_nH00i;
     // rigid bodies
     T mass, inv_mass;
     T J[9], Jinv[9];
@@ -46,7 +47,6 @@ struct Cartpole {
     RDB_HD void reset() const { cached = false; }
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const {
-        const T mpl = p.mp * p.l;
         const auto& qd0 = get<2>(x);
         const auto& qd1 = get<3>(x);
         auto th = get<1>(x);
@@ -58,12 +58,12 @@ struct Cartpole {
         // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s];  qdd = -H \\ r  (closed-form 2x2 solve,
         // like StaticArrays).  Both sides are divided by mp*l first, so the off-diagonal of H is just c and no partial is ever
         // multiplied by that constant:  H' = [(mc+mp)/(mp l)  c; c  l],  r' = [-s qd1^2 - u/(mp l), g s].
-        const T ia = T(1) / mpl, H00 = (p.mc + p.mp) * ia, H11 = p.l;
+        const T ia = p.cp_ia, H00 = p.cp_H00, H11 = p.l;
         auto r0 = fmadd<T, -1>(ia, get<0>(u), -(s * sq_(qd1)));
         auto r1 = p.g * s;
         auto idet = T(1) / sqadd<T, -1>(c, H00 * H11);
         auto qdd1 = fmadd<T, -1>(H00, r1, c * r0) * idet;
-        auto qdd0 = fmadd<T>(c, qdd1, r0) * (T(-1) / H00);       // first row of H' qdd = -r' (H00 is a constant)
+        auto qdd0 = fmadd<T>(c, qdd1, r0) * p.cp_nH00i;          // first row of H' qdd = -r' (H00 is a constant)
         return vec(qd0, qd1, qdd0, qdd1);
     }
 };

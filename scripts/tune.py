@@ -73,9 +73,10 @@ VARIANTS = {
     "cartpole": {
         "base": {},
         "t32_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16),
-        "t32_minb12": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=12),
-        "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
+        "t32_minb14": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=14),
+        "t32_minb10": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=10),
         "t64_minb6": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=6),
+        "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
     },
     "satellite": {
         "base": {},
