@@ -28,6 +28,10 @@ namespace rdb {
 
 enum Layout { LAYOUT_AOS = 0, LAYOUT_SOA = 1 };
 
+// CUtensorMap (cuda.h) by another name, so that this header also compiles under NVRTC: 128 opaque bytes the host encodes with
+// cuTensorMapEncodeTiled (launch.cuh: encode_jmap) and the TMA unit reads from the kernel's parameter space.
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };
+
 template <class T>
 struct KnotArgs {
     const T* Z;          // [x;u] per knot, knot-major (N, n+m)
@@ -37,6 +41,8 @@ struct KnotArgs {
                          // (error-state mode: nerr x (nerr+m) per knot instead)
     T* out;              // xdot or x+, (N, n);  may be nullptr
     long long N;
+    int use_jmap;        // jmap describes J as a 2-D tensor (E x N); used by the padded-image store of the n = 12 models
+    TensorMap jmap;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copies (TMA engine; SASS: UBLKCP / SYNCS) ------------------------
@@ -62,6 +68,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 }
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA store (SASS UTMASTG): the box is the whole PADDED smem image (row pitch PJ elements); the tensor's inner extent is
+// E < PJ, so the pad elements fall outside the tensor and the TMA unit drops them — dense rows in HBM from a conflict-free image,
+// one instruction per tile.
+__device__ __forceinline__ void tensor_store_2d(const TensorMap* tm, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -180,20 +193,38 @@ __device__ __forceinline__ void images_free_barrier(int tid) {
     asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
 }
 
+// this thread's [x;u] row from the smem image into registers.  Rows that are whole 16-byte units (n + m = 16, 18, ...) are read with
+// 16-byte loads: their pitch is a multiple of 4 words, so 4-byte loads put 8..16 lanes of a warp on one bank.
+__device__ __forceinline__ void ld16(const float* p, float* z) { const float4 v = *reinterpret_cast<const float4*>(p); z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w; }
+__device__ __forceinline__ void ld16(const double* p, double* z) { const double2 v = *reinterpret_cast<const double2*>(p); z[0] = v.x; z[1] = v.y; }
+template <class T, int NZ>
+__device__ __forceinline__ void read_row(const T* zrow, T (&z)[NZ]) {
+    constexpr int PER = int(16 / sizeof(T));
+    if constexpr (NZ % PER == 0) {
+#pragma unroll
+        for (int i = 0; i < NZ; i += PER) ld16(zrow + i, z + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) z[i] = zrow[i];
+    }
+}
+
 // One role: evaluate the map for one knot with partials for the columns in CHUNK; write this role's share.
 template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC>
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
     model.reset();                 // per-knot evaluation caches (e.g. Cartpole's stage-1 sincos) start empty
+    T zreg[NZ];
+    read_row<T, NZ>(zrow, zreg);
     if constexpr (ERR) {
-        auto zz = load_seeded_err<Model, T, CHUNK>(zrow, rstd::make_index_sequence<size_t(NZ)>{});
+        auto zz = load_seeded_err<Model, T, CHUNK>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         auto e = project_err<Model, T>(xn);
         images_free_barrier<NTHR, ISSUERS>(tid);
         put_cols<Model::nerr, CHUNK, VEC>(e, jrow, rstd::make_index_sequence<size_t(Model::nerr + m)>{});
         if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     } else {
-        auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zrow, rstd::make_index_sequence<size_t(NZ)>{});
+        auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         images_free_barrier<NTHR, ISSUERS>(tid);
         if constexpr (WITH_J) put_cols<n, CHUNK, VEC>(xn, jrow, rstd::make_index_sequence<size_t(NZ)>{});
@@ -244,8 +275,11 @@ __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(
 #ifndef RDB_TUNE_ROWSTORE
 #define RDB_TUNE_ROWSTORE 1      // 0: tuning experiments only (dense image even where it is bank-conflicted)
 #endif
+#ifndef RDB_ROWSTORE_MINWAY
+#define RDB_ROWSTORE_MINWAY 16   // pad the image when the dense one would put at least this many lanes of a warp on one bank
+#endif
 __host__ __device__ constexpr bool knot_rowstore(int jr, int jc, bool with_j, int es) {
-    return RDB_TUNE_ROWSTORE && with_j && jr >= 12 && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && cgcd(jr * jc * es / 4, 32) >= 16;
+    return RDB_TUNE_ROWSTORE && with_j && jr >= 12 && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && cgcd(jr * jc * es / 4, 32) >= RDB_ROWSTORE_MINWAY;
 }
 __host__ __device__ constexpr int knot_pitch(int jr, int jc, bool with_j, int es) {
     const int E = jr * jc, u = (E * es + 15) / 16;
@@ -288,7 +322,7 @@ struct KnotSmem {
 
 template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL, bool ERR = false>
 __global__ void __launch_bounds__(TILE * Chunks::count, MINB)
-knot_kernel(const Model model, const KnotArgs<T> a) {
+knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     using S = KnotSmem<Model, TILE, WITH_J, T, ERR>;
     constexpr int n = Model::n, NZ = Model::n + Model::m, E = S::E;
     constexpr int NTHR = TILE * Chunks::count;
@@ -350,7 +384,13 @@ knot_kernel(const Model model, const KnotArgs<T> a) {
             fence_proxy_async();
             __syncthreads();
             if constexpr (S::ROWSTORE) {
-                if (tid < TILE) {
+                if (a.use_jmap) {
+                    if (tid == 0) {
+                        if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), 0, int(k0));
+                        if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                        bulk_commit();
+                    }
+                } else if (tid < TILE) {
                     if (want_j) bulk_store(a.J + (k0 + tid) * E, smem_u32(j_img + tid * S::PJ), uint32_t(E * sizeof(T)));
                     if (tid == 0 && want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
                     bulk_commit();

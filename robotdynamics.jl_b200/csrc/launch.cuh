@@ -1,5 +1,6 @@
 // launch.cuh — per-(model, dtype) tiling configuration and the host-side launcher of knot_kernel.
 #pragma once
+#include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link dependency)
 #include "kernels.cuh"
 
 namespace rdb {
@@ -122,6 +123,43 @@ struct KnotConfig<Model, T, true, Q> {
 
 struct DeviceInfo { int device; int sm_count; int pdl; };   // pdl: launch with programmatic stream serialization
 
+// ---- tensor map of J for the padded-image store (kernels.cuh: tensor_store_2d) -------------------------------------------------
+// J is described as a 2-D tensor: inner extent E = rows x cols of one knot's Jacobian, outer extent N knots, dense.  The box is
+// pitch x tile with pitch > E: the pad of every smem row lies outside the tensor and is not written.
+#ifndef RDB_TUNE_JMAP
+#define RDB_TUNE_JMAP 1          // 0: tuning experiments only (one bulk store per knot row instead)
+#endif
+typedef CUresult (*rdb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline rdb_encode_tiled_fn encode_tiled_entry() {
+    static rdb_encode_tiled_fn fn = []() -> rdb_encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<rdb_encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) >= alignof(CUtensorMap), "TensorMap must mirror CUtensorMap");
+// returns 1 and fills *tm when J (16-byte aligned, at least one full tile) can leave through a tensor map, 0 otherwise
+inline int encode_jmap(TensorMap* tm, void* J, long long N, int E, int pitch, int tile, int es) {
+    if (!RDB_TUNE_JMAP || !J || N < tile || pitch > 256 || tile > 256 || (reinterpret_cast<uintptr_t>(J) & 15) != 0) return 0;
+    rdb_encode_tiled_fn enc = encode_tiled_entry();
+    if (!enc) return 0;
+    const cuuint64_t gdim[2] = {cuuint64_t(E), cuuint64_t(N)};
+    const cuuint64_t gstride[1] = {cuuint64_t(E) * cuuint64_t(es)};
+    const cuuint32_t box[2] = {cuuint32_t(pitch), cuuint32_t(tile)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = enc(reinterpret_cast<CUtensorMap*>(tm), es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, J,
+                            gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? 1 : 0;
+}
+
 // shape seen by the tiling rules in error-state mode: nerr rows, nerr + m columns (like an n = 12 model)
 template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m, rot = ROT_QUAT, frame = FRAME_WORLD; };
 
@@ -152,6 +190,11 @@ struct KnotLaunch {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = dev.pdl ? 1 : 0;
+        if constexpr (S::ROWSTORE) {
+            KnotArgs<T> b = a;
+            b.use_jmap = encode_jmap(&b.jmap, b.J, b.N, S::E, S::PJ, Cfg::TILE, int(sizeof(T)));
+            return int(cudaLaunchKernelEx(&cfg, kern, model, b));
+        }
         return int(cudaLaunchKernelEx(&cfg, kern, model, a));
     }
 };
@@ -189,7 +232,7 @@ inline int run_one(const KnotRequest& r) {
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
-    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N;
+    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
 template <template <class> class ModelT, class T>
@@ -198,7 +241,7 @@ inline int run_implicit(const KnotRequest& r) {
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
-    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N;
+    a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
     const unsigned grid = unsigned((r.N + 127) / 128);
     if (r.with_j) implicit_midpoint_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, a);

@@ -37,6 +37,7 @@ VARIANTS = {
     },
     "quaderr": {
         "base": {},
+        "rowbulk": dict(RDB_TUNE_JMAP=0),
         "dense": dict(RDB_TUNE_ROWSTORE=0),
         "3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
         "2r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0xF800u"),
@@ -59,6 +60,7 @@ VARIANTS = {
     },
     "quadmrp": {
         "base": {},
+        "rowbulk": dict(RDB_TUNE_JMAP=0),
         "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
         "2rb": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0xFE00u"),
         "roll2": dict(RDB_TUNE_ROLL=2),
@@ -80,6 +82,7 @@ VARIANTS = {
     },
     "satellite": {
         "base": {},
+        "rowbulk": dict(RDB_TUNE_JMAP=0),
         "t64_3c": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=1),
         "c2": dict(RDB_TUNE_C0="0x3u", RDB_TUNE_C1="0xCu", RDB_TUNE_C2="0x30u", RDB_TUNE_C3="0xC0u", RDB_TUNE_C4="0x300u", RDB_TUNE_C5="0xC00u", RDB_TUNE_C6="0x3000u", RDB_TUNE_C7="0xC000u", RDB_TUNE_C8="0x30000u", RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
         "c6": dict(RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0x3F000u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
@@ -87,7 +90,7 @@ VARIANTS = {
         "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
     },
 }
-VARIANTS["satellite32"] = {"base": {}, "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=3),
+VARIANTS["satellite32"] = {"base": {}, "pad8": dict(RDB_ROWSTORE_MINWAY=8), "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=3),
                            "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2)}
 
 
