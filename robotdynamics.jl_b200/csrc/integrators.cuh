@@ -29,6 +29,80 @@ struct saturate_impl {
 };
 template <class Model, class T, class X0, class U> using saturated_t = typename saturate_impl<Model, T, X0, U, X0>::type;
 
+// ---- stage increments ------------------------------------------------------------------------------------------------------
+// Models that can fold a scalar factor into their constants (Model::folds_scale, e.g. RigidBody::fs) are asked for the stage
+// INCREMENT G_s = (h a_s) f(X_s) directly: the next stage point is then x + G_s — no multiplication of a partial at all, where
+// x + (h a_s) f_s costs one multiply per partial — and x+ = x + sum_s (b_s / a_s) G_s.  The kernels are bound by FP32 instruction
+// issue, so the ~130 multiplies per stage of a rigid body count.  Models without fs() keep the
+// classical form below (for Cartpole the two forms cost the same).
+#ifndef RDB_INCREMENT_FORM
+#define RDB_INCREMENT_FORM 1     // 0: never; 1: straight-line rules only; 2: rolled stage loops too (tuning experiments)
+#endif
+template <class Model, class = void> struct folds_scale : rstd::false_type {};
+template <class Model> struct folds_scale<Model, rstd::void_t<decltype(Model::folds_scale)>> : rstd::integral_constant<bool, Model::folds_scale> {};
+
+// RK4 in increment form:  G1 = h/2 f(x), G2 = h/2 f(x+G1), G3 = h f(x+G2), G4 = h f(x+G3);  x+ = x + 1/3 (G1 + 2 G2 + G3 + 1/2 G4).
+// ROLL == 0: unrolled; 1: stage 1 on the sparse seed types, stages 2..4 rolled over the saturated types; 2: all four rolled.
+template <int ROLL, class T, class Model, class X, class U>
+RDB_HD auto rk4_increments(const Model& model, const X& x, const U& u, T h) {
+    const T hh = T(0.5) * h;
+    if constexpr (ROLL == 0) {
+        auto g1 = model.fs(x, u, hh);
+        auto g2 = model.fs(vadd(x, g1), u, hh);
+        auto g3 = model.fs(vadd(x, g2), u, h);
+        auto g4 = model.fs(vadd(x, g3), u, h);
+        return axpy(x, T(1.0 / 3.0), axpy(vadd(axpy(g1, T(2), g2), g3), T(0.5), g4));
+    } else {
+        using XS = saturated_t<Model, T, X, U>;
+        using FS = decltype(model.fs(rstd::declval<const XS&>(), u, h));
+        XS Xs;
+        FS acc;
+        int s0;
+        if constexpr (ROLL == 1) {
+            auto g1 = model.fs(x, u, hh);                          // stage 1 on the sparse seed types
+            Xs = widen_vec<XS>(vadd(x, g1));
+            acc = widen_vec<FS>(g1);
+            s0 = 1;
+        } else {
+            Xs = widen_vec<XS>(x);
+            acc = zero_vec<FS, T>();
+            s0 = 0;
+        }
+#pragma unroll 1
+        for (int s = s0; s < 4; ++s) {
+            const FS g = model.fs(Xs, u, s < 2 ? hh : h);
+            const T w = (s == 1) ? T(2) : (s == 3 ? T(0.5) : T(1));
+            acc = axpy(acc, w, g);
+            if (s < 3) Xs = widen_vec<XS>(vadd(x, g));
+        }
+        return axpy(x, T(1.0 / 3.0), acc);
+    }
+}
+
+// RK3 in increment form:  G1 = h/2 f(x), G2 = 2h f(x+G1), G3 = h f(x - 2 G1 + G2);  x+ = x + 1/3 (G1 + G2 + 1/2 G3).
+template <int ROLL, class T, class Model, class X, class U>
+RDB_HD auto rk3_increments(const Model& model, const X& x, const U& u, T h) {
+    const auto g1 = model.fs(x, u, T(0.5) * h);
+    const auto P = axpy(x, T(-2), g1);                              // x - h f1, stays in the sparse stage-1 types
+    if constexpr (ROLL == 0) {
+        auto g2 = model.fs(vadd(x, g1), u, T(2) * h);
+        auto g3 = model.fs(vadd(P, g2), u, h);
+        return axpy(x, T(1.0 / 3.0), axpy(vadd(g1, g2), T(0.5), g3));
+    } else {
+        using XS = saturated_t<Model, T, X, U>;
+        using FS = decltype(model.fs(rstd::declval<const XS&>(), u, h));
+        XS Xs = widen_vec<XS>(vadd(x, g1));
+        FS acc = widen_vec<FS>(g1);
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const FS g = model.fs(Xs, u, s == 0 ? T(2) * h : h);
+            acc = axpy(acc, s == 0 ? T(1) : T(0.5), g);
+            if (s == 0) Xs = widen_vec<XS>(vadd(P, g));
+        }
+        return axpy(x, T(1.0 / 3.0), acc);
+    }
+}
+
 // RK4 with stages 2..4 (ROLL == 1) or all four stages (ROLL == 2) rolled over the saturated types.
 template <int ROLL, class T, class Model, class X, class U>
 RDB_HD auto rk4_rolled(const Model& model, const X& x, const U& u, T h) {
@@ -79,7 +153,16 @@ RDB_HD auto rk3_rolled(const Model& model, const X& x, const U& u, T h) {
 
 template <int Q, class T, int ROLL = 0, class Model, class X, class U>
 RDB_HD auto integrate(const Model& model, const X& x, const U& u, T h) {
-    if constexpr (Q == Q_RK4 && ROLL != 0) {
+    if constexpr (Q == Q_CONTINUOUS) {
+        return model.f(x, u);
+    } else if constexpr (folds_scale<Model>::value && RDB_INCREMENT_FORM && (ROLL == 0 || RDB_INCREMENT_FORM > 1)) {
+        // (rolled stage loops keep the classical form: there the stage point x + G is a loop-carried copy of G, one MOV per partial
+        // where the classical form spends its one FMUL — measured no gain, profiles/tuning_r01.md)
+        if constexpr (Q == Q_EULER) return vadd(x, model.fs(x, u, h));
+        else if constexpr (Q == Q_RK2) return vadd(x, model.fs(vadd(x, model.fs(x, u, T(0.5) * h)), u, h));
+        else if constexpr (Q == Q_RK3) return rk3_increments<ROLL, T>(model, x, u, h);
+        else { static_assert(Q == Q_RK4, "unknown quadrature rule"); return rk4_increments<ROLL, T>(model, x, u, h); }
+    } else if constexpr (Q == Q_RK4 && ROLL != 0) {
         return rk4_rolled<ROLL, T>(model, x, u, h);
     } else if constexpr (Q == Q_RK3 && ROLL != 0) {
         return rk3_rolled<T>(model, x, u, h);

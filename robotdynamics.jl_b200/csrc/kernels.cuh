@@ -484,6 +484,122 @@ __global__ void __launch_bounds__(128) implicit_midpoint_kernel(const Model mode
     }
 }
 
+// ---- ImplicitMidpoint, warp-cooperative (rigid bodies: n >= 8) -----------------------------------------------------------------
+// The per-thread kernel above keeps ~600 words of matrices per knot in local memory.  Here a group of GS lanes (GS = 32 for the
+// rigid bodies: n + m = 16..19) shares ONE knot and lane j owns COLUMN j of every matrix, in registers:
+//   * [A B] by forward mode with a single runtime-seeded partial per lane (lane j seeds z_j): one evaluation of f yields the
+//     whole continuous Jacobian, one column per lane;
+//   * lane j < n holds column j of  M = h/2 A - I,  lane j < n+m column j of the right-hand side  [I + h/2 A, h B];  the Newton
+//     residual is replicated on every lane;
+//   * LU with partial pivoting runs across the lanes: lane k scans its column for the pivot and computes the multipliers, which
+//     reach the other lanes by warp shuffles; every lane eliminates its own column and its own right-hand side; in the back
+//     substitution the entries of U are broadcast from their owning lanes the same way.
+// Same arithmetic as the reference loop (src/integration.jl:620-694, 524-543): Newton from x2 = x1, at most 10 iterations, residual
+// and Jacobians evaluated before the test, Jacobian from the last evaluated iterate.
+template <class T> __device__ __forceinline__ SD<T, 1u> lane_dual(T v, bool mine) { SD<T, 1u> r; r.v = v; r.d[0] = PK<T>::splat(mine ? T(1) : T(0)); return r; }
+template <class T, size_t... Is>
+__device__ __forceinline__ auto load_lane_seeded(const T* z, int col, rstd::index_sequence<Is...>) { return vec(lane_dual<T>(z[Is], col == int(Is))...); }
+
+// B <- M^{-1} B where lane j < N_ of each GS-lane group holds column j of M in W (destroyed) and B is the lane's own vector
+template <class T, int N_, int GS>
+__device__ __forceinline__ void warp_lu_solve(T (&W)[N_], T (&B)[N_]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    T dinv[N_];
+#pragma unroll
+    for (int k = 0; k < N_; ++k) {
+        int p = k;                                  // pivot search in column k: meaningful on lane k, then broadcast
+        T best = fabs(W[k]);
+#pragma unroll
+        for (int i = k + 1; i < N_; ++i) { const T v = fabs(W[i]); if (v > best) { best = v; p = i; } }
+        p = __shfl_sync(FULL, p, k, GS);
+        {                                           // row swap k <-> p as selects (p is uniform within the group, rows are registers)
+            const T wk = W[k], bk = B[k];
+            T wp = wk, bp = bk;
+#pragma unroll
+            for (int i = k + 1; i < N_; ++i) {
+                const bool sw = (p == i);
+                wp = sw ? W[i] : wp; bp = sw ? B[i] : bp;
+                W[i] = sw ? wk : W[i]; B[i] = sw ? bk : B[i];
+            }
+            W[k] = wp; B[k] = bp;
+        }
+        dinv[k] = __shfl_sync(FULL, T(1) / W[k], k, GS);
+#pragma unroll
+        for (int i = k + 1; i < N_; ++i) {
+            const T l = __shfl_sync(FULL, W[i], k, GS) * dinv[k];
+            W[i] -= l * W[k];
+            B[i] -= l * B[k];
+        }
+    }
+#pragma unroll
+    for (int i = N_ - 1; i >= 0; --i) {           // back substitution: U(i,c) lives on lane c
+        T s = B[i];
+#pragma unroll
+        for (int c = i + 1; c < N_; ++c) s -= __shfl_sync(FULL, W[i], c, GS) * B[c];
+        B[i] = s * dinv[i];
+    }
+}
+
+template <class Model, class T, bool WITH_J, int GS>
+__global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model model, const KnotArgs<T> a) {
+    constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    static_assert(NZ <= GS && GS <= 32 && (32 % GS) == 0, "one lane per column of [x;u]");
+    constexpr unsigned FULL = 0xffffffffu;
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int col = int(threadIdx.x) % GS;                     // the column of [x;u] this lane owns
+    const bool valid = gtid / GS < a.N;
+    const long long k = valid ? gtid / GS : a.N - 1;           // lanes past the end shadow the last knot (shuffles stay convergent)
+    const T* zg = a.Z + k * NZ;
+    const T h = T(a.dt ? a.dt[k] : a.dt0);
+    const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
+    T z[NZ], zm[NZ], x2[n], Mf[n], Rf[n];
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) { z[i] = zg[i]; zm[i] = z[i]; }
+#pragma unroll
+    for (int i = 0; i < n; ++i) { x2[i] = z[i]; Mf[i] = T(0); Rf[i] = T(0); }
+    bool done = false;
+#pragma unroll 1
+    for (int iter = 0; iter < 10; ++iter) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) zm[i] = (z[i] + x2[i]) * T(0.5);
+        model.reset();
+        auto zz = load_lane_seeded<T>(zm, col, rstd::make_index_sequence<size_t(NZ)>{});
+        auto f = model.f(slice<0, n>(zz), slice<n, m>(zz));
+        T r[n], acol[n];
+        put_vals(f, r, rstd::make_index_sequence<size_t(n)>{});
+        put_cols<n, 1u, false>(f, acol, rstd::make_index_sequence<size_t(1)>{});     // column `col` of [A B]
+        T nrm = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { r[i] = z[i] + h * r[i] - x2[i]; nrm += r[i] * r[i]; }
+        T W[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const T ha = h * acol[i], hha = T(0.5) * ha, e = (i == col) ? T(1) : T(0);
+            W[i] = hha - e;                                    // column of  h/2 A - I            (col < n)
+            if (!done) { Mf[i] = W[i]; Rf[i] = col < n ? hha + e : ha; }     // column of  [I + h/2 A, h B]
+        }
+        const bool conv = sqrt(nrm) < tol;                     // the residual is replicated: uniform within the group
+        if (!done && conv) done = true;
+        if (__all_sync(FULL, done)) break;
+        warp_lu_solve<T, n, GS>(W, r);                         // all lanes take part; groups that are done discard the step
+        if (!done) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) x2[i] -= r[i];
+        }
+    }
+    if (valid && col == 0 && a.out) { T* o = a.out + k * n;
+#pragma unroll
+        for (int i = 0; i < n; ++i) o[i] = x2[i]; }
+    if constexpr (WITH_J) {
+        if (a.J) {                                             // uniform over the grid
+            warp_lu_solve<T, n, GS>(Mf, Rf);                   // J = -(h/2 A - I) \ [I + h/2 A, h B], one column per lane
+            if (valid && col < NZ) { T* Jo = a.J + k * (long long)(n * NZ) + n * col;
+#pragma unroll
+                for (int i = 0; i < n; ++i) Jo[i] = -Rf[i]; }
+        }
+    }
+}
+
 // rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
 // (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
 template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, rstd::index_sequence<Is...>) { return vec(p[Is]...); }

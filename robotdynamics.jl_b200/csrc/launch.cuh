@@ -235,6 +235,9 @@ inline int run_one(const KnotRequest& r) {
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
+#ifndef RDB_IMPLICIT_WARP_MIN_N
+#define RDB_IMPLICIT_WARP_MIN_N 8     // models with at least this many states use the warp-cooperative ImplicitMidpoint kernel
+#endif
 template <template <class> class ModelT, class T>
 inline int run_implicit(const KnotRequest& r) {
     if (r.op != OP_KNOT || r.err) return -2;
@@ -243,9 +246,16 @@ inline int run_implicit(const KnotRequest& r) {
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
-    const unsigned grid = unsigned((r.N + 127) / 128);
-    if (r.with_j) implicit_midpoint_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, a);
-    else implicit_midpoint_kernel<ModelT<T>, T, false><<<grid, 128, 0, r.stream>>>(model, a);
+    if constexpr (ModelT<T>::n >= RDB_IMPLICIT_WARP_MIN_N && ModelT<T>::n + ModelT<T>::m <= 32) {
+        // rigid bodies: one knot per 32-lane group, one column of [A B] per lane, LU across the lanes by warp shuffles
+        const unsigned grid = unsigned((r.N * 32 + 127) / 128);
+        if (r.with_j) implicit_midpoint_warp_kernel<ModelT<T>, T, true, 32><<<grid, 128, 0, r.stream>>>(model, a);
+        else implicit_midpoint_warp_kernel<ModelT<T>, T, false, 32><<<grid, 128, 0, r.stream>>>(model, a);
+    } else {
+        const unsigned grid = unsigned((r.N + 127) / 128);
+        if (r.with_j) implicit_midpoint_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, a);
+        else implicit_midpoint_kernel<ModelT<T>, T, false><<<grid, 128, 0, r.stream>>>(model, a);
+    }
     return int(cudaGetLastError());
 }
 template <template <class> class ModelT, class T, int Q>

@@ -124,29 +124,33 @@ RDB_HD auto to_quat(const P& p) {
     }
 }
 
-// Rotations.kinematics(R, w): time derivative of the attitude parameters for body rate w.
+// c * Rotations.kinematics(R, w): (c times) the time derivative of the attitude parameters for body rate w.  The factor goes
+// onto the constants / onto w (3 elements with few partials), never onto the results.
 template <class T, int ROT, class P, class W>
-RDB_HD auto rot_kinematics(const P& p, const W& w) {
+RDB_HD auto rot_kinematics(const P& p, const W& w, T c = T(1)) {
     if constexpr (ROT == ROT_QUAT) {   // 1/2 q (x) [0; w], bilinear, no normalisation (reference: test/liemodel.jl:13-20)
         const auto& qw = get<0>(p); const auto& qx = get<1>(p); const auto& qy = get<2>(p); const auto& qz = get<3>(p);
         // the factor 1/2 is applied to w once (3 scalars) rather than to the 4 results (exact: a power of two)
-        auto w0 = T(0.5) * get<0>(w); auto w1 = T(0.5) * get<1>(w); auto w2 = T(0.5) * get<2>(w);
+        const T hc = T(0.5) * c;
+        auto w0 = hc * get<0>(w); auto w1 = hc * get<1>(w); auto w2 = hc * get<2>(w);
         return vec(fmadd<T, -1>(qz, w2, fmadd<T, -1>(qy, w1, -(qx * w0))),
                    fmadd<T, -1>(qz, w1, fmadd<T>(qy, w2, qw * w0)),
                    fmadd<T, -1>(qx, w2, fmadd<T>(qz, w0, qw * w1)),
                    fmadd<T, -1>(qy, w0, fmadd<T>(qx, w1, qw * w2)));
     } else {
         auto pw = dot3<T>(p, w);
-        auto c = cross3<T>(p, w);
+        auto cr = cross3<T>(p, w);
         if constexpr (ROT == ROT_MRP) {  // 1/4 [(1-|p|^2) I + 2 skew(p) + 2 p p'] w
             auto a = T(1) - norm2_3<T>(p);
-            return vec(T(0.25) * (a * get<0>(w) + T(2) * (get<0>(c) + get<0>(p) * pw)),
-                       T(0.25) * (a * get<1>(w) + T(2) * (get<1>(c) + get<1>(p) * pw)),
-                       T(0.25) * (a * get<2>(w) + T(2) * (get<2>(c) + get<2>(p) * pw)));
+            const T qc = T(0.25) * c;
+            return vec(qc * (a * get<0>(w) + T(2) * (get<0>(cr) + get<0>(p) * pw)),
+                       qc * (a * get<1>(w) + T(2) * (get<1>(cr) + get<1>(p) * pw)),
+                       qc * (a * get<2>(w) + T(2) * (get<2>(cr) + get<2>(p) * pw)));
         } else {                          // 1/2 [I + skew(g) + g g'] w
-            return vec(T(0.5) * (get<0>(w) + get<0>(c) + get<0>(p) * pw),
-                       T(0.5) * (get<1>(w) + get<1>(c) + get<1>(p) * pw),
-                       T(0.5) * (get<2>(w) + get<2>(c) + get<2>(p) * pw));
+            const T hc = T(0.5) * c;
+            return vec(hc * (get<0>(w) + get<0>(cr) + get<0>(p) * pw),
+                       hc * (get<1>(w) + get<1>(cr) + get<1>(p) * pw),
+                       hc * (get<2>(w) + get<2>(cr) + get<2>(p) * pw));
         }
     }
 }
@@ -160,8 +164,12 @@ template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) 
 // The part every RigidBody{R} shares (reference: src/rigidbody.jl:213-236): kinematics, Newton and Euler equations around a
 // wrench supplied by the concrete model — `wrench(q, r, v, w, u)` returns vec(F/m in the world frame (3), tau in the body frame (3))
 // (reference: forces / moments / wrenches, src/rigidbody.jl:244-257).
-template <class T, int ROT, int FRAME, bool DIAG_INERTIA, class X, class U, class Wrench>
-RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const Wrench& wrench) {
+//
+// SCALED: return c * f(x,u) instead of f(x,u) (the integrators ask for the stage increment h a_s f(X_s) directly, integrators.cuh).
+// The factor is folded into constants and into elements with few partials — the inverse inertia, w before the kinematics, v before
+// a body-frame rotation — so that almost no partial is multiplied by it; the WRENCH MUST ALREADY RETURN c * F/m (and tau unscaled).
+template <class T, int ROT, int FRAME, bool DIAG_INERTIA, bool SCALED = false, class X, class U, class Wrench>
+RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const Wrench& wrench, T c = T(1)) {
     constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
     auto r = slice<0, 3>(x);
     auto att = slice<3, np>(x);
@@ -171,25 +179,39 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
     auto xi = wrench(q, r, v, w, u);
     auto Fm = slice<0, 3>(xi);
     auto tau = slice<3, 3>(xi);
-    auto qdot = rot_kinematics<T, ROT>(att, w);
+    auto qdot = [&]() { if constexpr (SCALED) return rot_kinematics<T, ROT>(att, w, c); else return rot_kinematics<T, ROT>(att, w); }();
     // omega_dot = Jinv (tau - w x (J w))
     auto wdot = [&]() {
         if constexpr (DIAG_INERTIA) {      // w x (J w) = ((J3-J2) wy wz, (J1-J3) wz wx, (J2-J1) wx wy): three products instead of six
             const auto& wx = get<0>(w); const auto& wy = get<1>(w); const auto& wz = get<2>(w);
             const T J1 = p.J[0], J2 = p.J[4], J3 = p.J[8];
-            return vec(p.Jinv[0] * fmadd<T, -1>((J3 - J2) * wy, wz, get<0>(tau)),
-                       p.Jinv[4] * fmadd<T, -1>((J1 - J3) * wz, wx, get<1>(tau)),
-                       p.Jinv[8] * fmadd<T, -1>((J2 - J1) * wx, wy, get<2>(tau)));
+            const T i0 = SCALED ? c * p.Jinv[0] : p.Jinv[0], i1 = SCALED ? c * p.Jinv[4] : p.Jinv[4], i2 = SCALED ? c * p.Jinv[8] : p.Jinv[8];
+            return vec(i0 * fmadd<T, -1>((J3 - J2) * wy, wz, get<0>(tau)),
+                       i1 * fmadd<T, -1>((J1 - J3) * wz, wx, get<1>(tau)),
+                       i2 * fmadd<T, -1>((J2 - J1) * wx, wy, get<2>(tau)));
         } else {
-            return mat3_mul(p.Jinv, vsub(tau, cross3<T>(w, mat3_mul(p.J, w))));
+            if constexpr (SCALED) {
+                T Ji[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Ji[i] = c * p.Jinv[i];
+                return mat3_mul(Ji, vsub(tau, cross3<T>(w, mat3_mul(p.J, w))));
+            } else {
+                return mat3_mul(p.Jinv, vsub(tau, cross3<T>(w, mat3_mul(p.J, w))));
+            }
         }
     }();
     if constexpr (FRAME == FRAME_WORLD) {
-        return cat(v, qdot, Fm, wdot);
+        if constexpr (SCALED) return cat(vscale(c, v), qdot, Fm, wdot);
+        else return cat(v, qdot, Fm, wdot);
     } else {
-        auto rdot = quat_rotate<T>(q, v);
-        auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, v));
-        return cat(rdot, qdot, vdot, wdot);
+        if constexpr (SCALED) {            // c (q*v) = q*(c v),  c (q\F/m - w x v) = q\(c F/m) - w x (c v)
+            auto cv = vscale(c, v);
+            return cat(quat_rotate<T>(q, cv), qdot, vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, cv)), wdot);
+        } else {
+            auto rdot = quat_rotate<T>(q, v);
+            auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, v));
+            return cat(rdot, qdot, vdot, wdot);
+        }
     }
 }
 
@@ -203,26 +225,32 @@ struct RigidBody {
     ModelParams<T> p;
     RDB_HD void reset() const {}
 
-    template <class X, class U>
-    RDB_HD auto f(const X& x, const U& u) const {
-        // wrench: F/m in the world frame (the 1/m of vdot = F/m is folded into the few scalars that build F, instead of
-        // scaling every partial of the rotated vector), tau in the body frame
-        return rigid_body_f<T, ROT, FRAME, diag_inertia>(p, x, u, [&](const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
+    // c * f(x,u) with the factor folded into the model's constants (integrators.cuh: stage increments)
+    static constexpr bool folds_scale = true;
+    template <class X, class U> RDB_HD auto f(const X& x, const U& u) const { return eval<false>(x, u, T(1)); }
+    template <class X, class U> RDB_HD auto fs(const X& x, const U& u, T c) const { return eval<true>(x, u, c); }
+
+    template <bool SCALED, class X, class U>
+    RDB_HD auto eval(const X& x, const U& u, T c) const {
+        // wrench: F/m in the world frame (the 1/m of vdot = F/m — and the stage factor c — are folded into the few scalars that
+        // build F, instead of scaling every partial of the rotated vector), tau in the body frame
+        const T im = SCALED ? c * p.inv_mass : p.inv_mass;
+        return rigid_body_f<T, ROT, FRAME, diag_inertia, SCALED>(p, x, u, [&](const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
             if constexpr (KIND == KIND_QUADROTOR) {
                 auto F1 = relu_(p.kf * get<0>(uu));
                 auto F2 = relu_(p.kf * get<1>(uu));
                 auto F3 = relu_(p.kf * get<2>(uu));
                 auto F4 = relu_(p.kf * get<3>(uu));
-                auto qF = quat_rotate_z<T>(q, p.inv_mass * (F1 + F2 + F3 + F4));
-                const T g0 = p.mg[0] * p.inv_mass, g1 = p.mg[1] * p.inv_mass, g2 = p.mg[2] * p.inv_mass;
+                auto qF = quat_rotate_z<T>(q, im * (F1 + F2 + F3 + F4));
+                const T g0 = p.mg[0] * im, g1 = p.mg[1] * im, g2 = p.mg[2] * im;
                 auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
                                p.km * (get<0>(uu) - get<1>(uu) + get<2>(uu) - get<3>(uu)));
                 return cat(Fm, tau);
             } else {
-                return cat(quat_rotate<T>(q, vscale(p.inv_mass, slice<0, 3>(uu))), slice<3, 3>(uu));
+                return cat(quat_rotate<T>(q, vscale(im, slice<0, 3>(uu))), slice<3, 3>(uu));
             }
-        });
+        }, c);
     }
 };
 

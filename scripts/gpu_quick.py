@@ -70,6 +70,33 @@ def bench_err(name, gm, Q, dtype, N, dt=0.01, iters=20):
     print(f"BENCH-ERR {name:20s} Q={Q} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
 
 
+def bench_value(name, gm, Q, dtype, N, dt=0.01, iters=20):
+    """dynamics() (Q < 0), discrete_dynamics() (value-only kernels K1/K2) and the continuous jacobian!() (Q = None)."""
+    rng = np.random.default_rng(2)
+    Z = torch.from_numpy(rand_inputs(gm._h, N, rng).astype(dtype)).cuda()
+    n, m = gm._h.n, gm._h.m
+    if Q is None:
+        J = torch.empty((N, n + m, n), dtype=Z.dtype, device='cuda')
+        f = lambda: gm._h.jacobian(Z, J=J)
+        nbytes, label = (n + m) + n * (n + m), "jacobian! (continuous)"
+    else:
+        out = torch.empty((N, n), dtype=Z.dtype, device='cuda')
+        f = (lambda: gm._h.dynamics(Z, out=out)) if Q < 0 else (lambda: gm._h.discrete_dynamics(Q, Z, dt, out=out))
+        nbytes, label = (n + m) + n, "dynamics" if Q < 0 else f"discrete_dynamics Q={Q}"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); f(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = np.median(ts) * 1e-3
+    gbs = N * Z.element_size() * nbytes / t / 1e9
+    print(f"BENCH-VAL {name:20s} {label:24s} {np.dtype(dtype).name} N={N}: {t*1e6:9.1f} us  {N/t:.3e} evals/s  {gbs:7.1f} GB/s algorithmic", flush=True)
+
+
 def bench_soa(name, gm, Q, dtype, N, dt=0.01, iters=10):
     rng = np.random.default_rng(2)
     n, m = gm._h.n, gm._h.m
@@ -135,6 +162,9 @@ if __name__ == "__main__":
     check("satellite mrp", rd.Satellite(rd.MRP), o.satellite(o.ROT_MRP), 1, np.float64, dt=0.1)
     check("double integrator 3", rd.DoubleIntegrator(3), o.double_integrator(3), 3, np.float64)
     bench_misc()
+    for Q in (-1, 3, None):
+        bench_value("cartpole", cp, Q, np.float64, 1 << 22)
+        bench_value("quadrotor", qd, Q, np.float32, 1 << 21)
     bench("cartpole implicit-midpoint", cp, 4, np.float64, 1 << 20)
     bench("quadrotor implicit-midpoint", qd, 4, np.float32, 262144)
     bench("quadrotor implicit-midpoint", qd, 4, np.float64, 262144)
