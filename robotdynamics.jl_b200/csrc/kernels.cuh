@@ -500,6 +500,19 @@ template <class T> __device__ __forceinline__ SD<T, 1u> lane_dual(T v, bool mine
 template <class T, size_t... Is>
 __device__ __forceinline__ auto load_lane_seeded(const T* z, int col, rstd::index_sequence<Is...>) { return vec(lane_dual<T>(z[Is], col == int(Is))...); }
 
+// (p == i) ? a : b as an opaque select: written with ?: the compiler recognises the chain over i as the dynamically indexed
+// access W[p] and moves the whole register array to local memory
+__device__ __forceinline__ float sel_eq(int p, int i, float a, float b) {
+    float r;
+    asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %3, %4;\n\tselp.f32 %0, %1, %2, q;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"(p), "r"(i));
+    return r;
+}
+__device__ __forceinline__ double sel_eq(int p, int i, double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %3, %4;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"(p), "r"(i));
+    return r;
+}
+
 // B <- M^{-1} B where lane j < N_ of each GS-lane group holds column j of M in W (destroyed) and B is the lane's own vector
 template <class T, int N_, int GS>
 __device__ __forceinline__ void warp_lu_solve(T (&W)[N_], T (&B)[N_]) {
@@ -507,19 +520,25 @@ __device__ __forceinline__ void warp_lu_solve(T (&W)[N_], T (&B)[N_]) {
     T dinv[N_];
 #pragma unroll
     for (int k = 0; k < N_; ++k) {
-        int p = k;                                  // pivot search in column k: meaningful on lane k, then broadcast
-        T best = fabs(W[k]);
+        // partial pivoting.  Common case first: the diagonal entry already has the largest magnitude of its column (M = h/2 A - I
+        // is close to -I) — one max per row on lane k, one shuffle and a warp-uniform branch; the full search and the row swap
+        // (selects over the register rows: p is only known at run time) run only when some group of the warp needs them.
+        T mx = T(0);
 #pragma unroll
-        for (int i = k + 1; i < N_; ++i) { const T v = fabs(W[i]); if (v > best) { best = v; p = i; } }
-        p = __shfl_sync(FULL, p, k, GS);
-        {                                           // row swap k <-> p as selects (p is uniform within the group, rows are registers)
+        for (int i = k + 1; i < N_; ++i) mx = fmax(mx, fabs(W[i]));
+        const int need = __shfl_sync(FULL, int(mx > fabs(W[k])), k, GS);
+        if (__any_sync(FULL, need)) {
+            int p = k;
+            T best = fabs(W[k]);
+#pragma unroll
+            for (int i = k + 1; i < N_; ++i) { const T v = fabs(W[i]); if (v > best) { best = v; p = i; } }
+            p = __shfl_sync(FULL, p, k, GS);
             const T wk = W[k], bk = B[k];
             T wp = wk, bp = bk;
 #pragma unroll
             for (int i = k + 1; i < N_; ++i) {
-                const bool sw = (p == i);
-                wp = sw ? W[i] : wp; bp = sw ? B[i] : bp;
-                W[i] = sw ? wk : W[i]; B[i] = sw ? bk : B[i];
+                wp = sel_eq(p, i, W[i], wp); bp = sel_eq(p, i, B[i], bp);
+                W[i] = sel_eq(p, i, wk, W[i]); B[i] = sel_eq(p, i, bk, B[i]);
             }
             W[k] = wp; B[k] = bp;
         }

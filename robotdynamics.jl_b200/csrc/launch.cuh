@@ -247,10 +247,11 @@ inline int run_implicit(const KnotRequest& r) {
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
     if constexpr (ModelT<T>::n >= RDB_IMPLICIT_WARP_MIN_N && ModelT<T>::n + ModelT<T>::m <= 32) {
-        // rigid bodies: one knot per 32-lane group, one column of [A B] per lane, LU across the lanes by warp shuffles
-        const unsigned grid = unsigned((r.N * 32 + 127) / 128);
-        if (r.with_j) implicit_midpoint_warp_kernel<ModelT<T>, T, true, 32><<<grid, 128, 0, r.stream>>>(model, a);
-        else implicit_midpoint_warp_kernel<ModelT<T>, T, false, 32><<<grid, 128, 0, r.stream>>>(model, a);
+        // rigid bodies: one knot per group of GS lanes, one column of [A B] per lane, LU across the lanes by warp shuffles
+        constexpr int GS = (ModelT<T>::n + ModelT<T>::m <= 16) ? 16 : 32;
+        const unsigned grid = unsigned((r.N * GS + 127) / 128);
+        if (r.with_j) implicit_midpoint_warp_kernel<ModelT<T>, T, true, GS><<<grid, 128, 0, r.stream>>>(model, a);
+        else implicit_midpoint_warp_kernel<ModelT<T>, T, false, GS><<<grid, 128, 0, r.stream>>>(model, a);
     } else {
         const unsigned grid = unsigned((r.N + 127) / 128);
         if (r.with_j) implicit_midpoint_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, a);
