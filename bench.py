@@ -199,8 +199,12 @@ def run_sweep(args):
         Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
         work.append((model._h, Q.code, Zs, dt, Js, cnt, np.dtype(dtn).itemsize * ((n + m) + n * (n + m))))
 
-    # the two model segments are independent: one stream each, so their (small, at 8 GPUs launch-bound) kernels overlap
-    streams = [torch.cuda.Stream() for _ in work]
+    # The two model segments are independent.  With big per-rank segments each kernel is a persistent grid that fills the GPU by
+    # itself, so two streams only add scheduling noise: one stream, back to back (programmatic dependent launch overlaps the
+    # prologues).  At 4-8 GPUs the segments are small and launch-bound: one stream each so they overlap.
+    nstreams = args.sweep_streams or (1 if world <= 2 else 2)
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    streams = [streams[i % nstreams] for i in range(len(work))]
     main = torch.cuda.current_stream()
 
     def step(i):
@@ -233,7 +237,8 @@ def run_sweep(args):
         line = {"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-                "config": {"workload": SWEEP_DESC, "l2": "6 rotating buffer sets per segment", "parallelism": f"trajectory-block sharded x{world}"},
+                "config": {"workload": SWEEP_DESC, "l2": "6 rotating buffer sets per segment", "parallelism": f"trajectory-block sharded x{world}",
+                           "streams": nstreams},
                 "roofline": {"bound": "hbm", "achieved": byts / (ms * 1e-3 / args.steps) / 1e9 / world, "peak": 6551.4, "unit": "GB/s per GPU",
                              "frac": byts / (ms * 1e-3 / args.steps) / 1e9 / world / 6551.4, "traffic": None},
                 "gpu_launches": 2 * args.steps}
@@ -366,6 +371,7 @@ def main():
     ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS) + ["sweep"])
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU time for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-streams", type=int, default=0, help="sweep workload: streams for the two model segments (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload == "sweep":
