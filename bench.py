@@ -199,10 +199,9 @@ def run_sweep(args):
         Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
         work.append((model._h, Q.code, Zs, dt, Js, cnt, np.dtype(dtn).itemsize * ((n + m) + n * (n + m))))
 
-    # The two model segments are independent.  With big per-rank segments each kernel is a persistent grid that fills the GPU by
-    # itself, so two streams only add scheduling noise: one stream, back to back (programmatic dependent launch overlaps the
-    # prologues).  At 4-8 GPUs the segments are small and launch-bound: one stream each so they overlap.
-    nstreams = args.sweep_streams or (1 if world <= 2 else 2)
+    # The two model segments are independent: one stream each, so the tail of one kernel overlaps the head of the other and, at
+    # 4-8 GPUs, the small launch-bound kernels overlap (measured at 1 GPU: two streams 122.6 us, one stream 131.9 us per sweep).
+    nstreams = args.sweep_streams or 2
     streams = [torch.cuda.Stream() for _ in range(nstreams)]
     streams = [streams[i % nstreams] for i in range(len(work))]
     main = torch.cuda.current_stream()
