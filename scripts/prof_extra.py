@@ -1,0 +1,26 @@
+"""Launches the error-state Jacobian kernel or the warp-cooperative ImplicitMidpoint kernel a few times (target of ncu captures).
+
+    python scripts/prof_extra.py err|implicit
+"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np
+import torch
+import rdb200 as rd
+import gpu_quick as g
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    qd = rd.Quadrotor()
+    N = 262144
+    Z = torch.from_numpy(g.rand_inputs(qd._h, N, np.random.default_rng(2)).astype(np.float32)).cuda()
+    if what == "err":
+        J = torch.empty((N, 16, 12), dtype=torch.float32, device="cuda")
+        for _ in range(8):
+            qd._h.discrete_error_jacobian(3, Z, 0.01, J=J)
+    else:
+        J = torch.empty((N, 17, 13), dtype=torch.float32, device="cuda")
+        for _ in range(4):
+            qd._h.discrete_jacobian(4, Z, 0.01, J=J)
+    torch.cuda.synchronize()
