@@ -584,7 +584,8 @@ def test_calls_are_cuda_graph_capturable(rd, torch_):
 
 @pytest.mark.parametrize("name", ["cartpole", "quad_quat_world", "body_mrp_body", "satellite_mrp", "di3"])
 def test_implicit_midpoint(rd, torch_, name):
-    """ImplicitMidpoint on the GPU (per-thread Newton + pivoted LU + implicit-function-theorem Jacobian) against the oracle."""
+    """ImplicitMidpoint on the GPU (Newton + pivoted LU + implicit-function-theorem Jacobian; warp-cooperative kernel for the rigid
+    bodies, per-thread kernel for the small models) against the oracle."""
     om, gm = zoo()[name][0](), zoo()[name][1](rd)
     N = 900
     Z = rand_inputs(om.n, om.m, N, np.random.default_rng(111))
