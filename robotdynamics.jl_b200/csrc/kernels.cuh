@@ -275,9 +275,6 @@ __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(
 #ifndef RDB_TUNE_ROWSTORE
 #define RDB_TUNE_ROWSTORE 1      // 0: tuning experiments only (dense image even where it is bank-conflicted)
 #endif
-#ifndef RDB_TUNE_ROLEMAP
-#define RDB_TUNE_ROLEMAP 0
-#endif
 #ifndef RDB_ROWSTORE_MINWAY
 #define RDB_ROWSTORE_MINWAY 16   // pad the image when the dense one would put at least this many lanes of a warp on one bank
 #endif
@@ -336,17 +333,8 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     const uint32_t bar0 = smem_u32(smem_raw + S::off_bar);
 
     const int tid = threadIdx.x;
-#if RDB_TUNE_ROLEMAP
-    // experiment: two roles x four warps — give both warps of an SM sub-partition (warp ids w and w + 4) the SAME role, so that
-    // they share instruction-cache lines:  role = (warp % 4) / 2,  warp within the role = (warp % 2) + 2 (warp / 4)
-    constexpr bool REMAP = (Chunks::count == 2 && TILE == 128);
-    const int warp_ = tid >> 5;
-    const int role = REMAP ? ((warp_ & 3) >> 1) : tid / TILE;
-    const int kt = REMAP ? ((((warp_ & 1) | ((warp_ >> 2) << 1)) << 5) | (tid & 31)) : tid - role * TILE;
-#else
     const int role = tid / TILE;            // warp-uniform (TILE % 32 == 0)
     const int kt = tid - role * TILE;
-#endif
     const long long N = a.N;
     const long long ntiles = (N + TILE - 1) / TILE;
     const bool want_j = WITH_J && a.J != nullptr;

@@ -84,27 +84,16 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long ntiles = (N + TILE - 1) / TILE;
-    // this thread's attitude for a tile, loaded one tile AHEAD: the global-load latency hides behind the previous tile's barriers
-    // and image stores instead of being paid once per tile (the loop is latency-bound, not bandwidth-bound, otherwise)
-    auto load_att = [&](long long tile, T (&pp)[4]) {
-        const long long k = tile * TILE + threadIdx.x;
-        if (tile < ntiles && k < N) {
-            const T* p = X + k * ldx + 3;
-            pp[0] = p[0]; pp[1] = p[1]; pp[2] = p[2]; pp[3] = NP == 4 ? p[NP - 1] : T(0);
-        } else { pp[0] = T(1); pp[1] = pp[2] = pp[3] = T(0); }
-    };
-    T nxt[4];
-    load_att(blockIdx.x, nxt);
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const long long k0 = tile * TILE;
         const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
         T* im = img[it & 1];
-        T pp[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-        load_att(tile + gridDim.x, nxt);
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this image is done reading
         __syncthreads();
         if (threadIdx.x < cnt) {
+            const T* p = X + (k0 + threadIdx.x) * ldx + 3;
+            T pp[4] = {p[0], p[1], p[2], NP == 4 ? p[NP - 1] : T(0)};
             T* row = im + threadIdx.x * PER;
 #pragma unroll
             for (int i = 0; i < NP; ++i)

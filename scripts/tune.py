@@ -31,8 +31,6 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
 VARIANTS = {
     "quadrotor": {
         "base": {},
-        "rolemap": dict(RDB_TUNE_ROLEMAP=1),
-        "rolemap_c": dict(RDB_TUNE_ROLEMAP=1, RDB_TUNE_C0="0x1FFFu", RDB_TUNE_C1="0x1E000u"),
         "split13": dict(RDB_TUNE_C0="0x1FFFu", RDB_TUNE_C1="0x1E000u"),
         "t64_minb2": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
         "t32_minb4": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=4),

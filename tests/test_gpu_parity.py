@@ -61,7 +61,8 @@ def test_discrete_jacobian_all_models(rd, torch_, name, dtype):
 
 
 # ---- layouts, pointer kinds, alignment, ragged sizes ----------------------------------------------------------------------------
-@pytest.mark.parametrize("name,dtype", [("cartpole", np.float64), ("quad_quat_world", np.float32), ("satellite_mrp", np.float64)])
+@pytest.mark.parametrize("name,dtype", [("cartpole", np.float64), ("quad_quat_world", np.float32), ("satellite_mrp", np.float64),
+                                        ("quad_mrp_world", np.float32)])   # the last two: padded image + 2-D tensor store, and its fallbacks
 def test_layouts_and_pointer_kinds_agree_bitwise(rd, torch_, name, dtype):
     om, gm = zoo()[name][0](), zoo()[name][1](rd)
     n, nz = om.n, om.n + om.m
