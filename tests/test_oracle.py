@@ -4,7 +4,9 @@ The reference ships no golden vectors and Julia is unavailable (SURVEY.md ยง4, ย
  (1) the relational assertions the reference's own tests make on this path, re-run here on the oracle;
  (2) an independent numpy complex-step restatement (oracle/independent.py) that shares no code with it;
  (3) the hand-verified known answers of SURVEY.md Appendix C;
- (4) the committed fixtures in tests/golden/ (regression pin).
+ (4) the committed fixtures in tests/golden/ (regression pin);
+ (5) sympy / 50-digit mpmath restatements (oracle/highprec.py): the symbolic Cartpole Jacobian, the reference's own hand-derived
+     analytic Jacobian (test/cartpole_model.jl:57-96), and high-precision differences of the composed RK maps.
 """
 import numpy as np
 import pytest
@@ -249,3 +251,53 @@ def test_implicit_midpoint_oracle_vs_independent():
                 assert np.abs(res).max() < 1e-12
                 assert np.abs(xn[k] - np.real(ind.implicit_midpoint_step(im, x, u, h))).max() < 1e-12
                 assert np.abs(J[k] - ind.discrete_jacobian(im, "implicit_midpoint", Z[k], h)).max() < 1e-10
+
+
+# ---- (5) symbolic / 50-digit pins (oracle/highprec.py; SURVEY.md ยง7 step 1 (ii), (iii)) ----------------------------------------------
+def test_cartpole_symbolic_jacobian_and_reference_analytic_jacobian():
+    """sympy d f / d z of the Cartpole written as the reference writes it  ==  the reference's hand-derived jacobian!
+    (test/cartpole_model.jl:57-96)  ==  the oracle's continuous Jacobian (mirrors test/integration_tests.jl:27-33)."""
+    import sympy as sp
+    from oracle import highprec as hp
+    z, f, Jf = hp.cartpole_symbolic()
+    fn, Jn = sp.lambdify(z, f, "numpy"), sp.lambdify(z, Jf, "numpy")
+    rng = np.random.default_rng(5)
+    Z = np.vstack([rng.random((6, 5)), 3.0 * rng.standard_normal((6, 5))])
+    m = o.cartpole()
+    Jo = o.as_matrix(o.jacobian(m, Z))
+    fo = o.dynamics(m, Z)
+    for k, zk in enumerate(Z):
+        Jsym = np.array(Jn(*zk), dtype=float)
+        scale = max(1.0, np.abs(Jsym).max())
+        assert np.abs(np.array(fn(*zk), dtype=float).ravel() - fo[k]).max() < 1e-12 * max(1.0, np.abs(fo[k]).max())
+        assert np.abs(Jsym - hp.cartpole_reference_analytic_jacobian(zk)).max() < 1e-11 * scale
+        assert np.abs(Jsym - Jo[k]).max() < 1e-11 * scale
+
+
+@pytest.mark.parametrize("Q", sorted(QS))
+def test_cartpole_discrete_jacobian_vs_50_digit_differences(Q):
+    """x+ and d x+ / d [x;u] of every explicit rule against 50-digit arithmetic differentiated by central differences."""
+    from oracle import highprec as hp
+    f = hp.cartpole_f_mp()
+    rng = np.random.default_rng(6)
+    Z = rng.random((4, 5))
+    Z[3] = [0.3, 2.9, -1.2, 4.0, -7.5]                                     # far from the bench distribution
+    m = o.cartpole()
+    for k, h in enumerate((0.01, 0.05, 0.1, 0.02)):
+        xn, J = hp.discrete_jacobian(f, QS[Q], Z[k], 4, h)
+        assert np.abs(o.discrete_dynamics(m, Q, Z[k:k + 1], h)[0] - xn).max() < 1e-13 * max(1.0, np.abs(xn).max())
+        assert np.abs(o.as_matrix(o.discrete_jacobian(m, Q, Z[k:k + 1], h))[0] - J).max() < 1e-12 * max(1.0, np.abs(J).max())
+
+
+def test_quadrotor_rk4_jacobian_vs_50_digit_differences():
+    """The n = 13 rigid body, including an off-manifold quaternion (the dynamics never renormalises)."""
+    from oracle import highprec as hp
+    f = hp.quadrotor_f()
+    Z = rand_inputs(13, 4, 3, np.random.default_rng(7))
+    Z[:, 13:] += 0.5                                                       # thrusts away from the max(0, .) kink
+    Z[2, 3:7] *= 1.2
+    m = o.quadrotor()
+    for k, (Q, h) in enumerate(((o.RK4, 0.01), (o.RK3, 0.05), (o.RK4, 0.1))):
+        xn, J = hp.discrete_jacobian(f, QS[Q], Z[k], 13, h)
+        assert np.abs(o.discrete_dynamics(m, Q, Z[k:k + 1], h)[0] - xn).max() < 1e-13 * max(1.0, np.abs(xn).max())
+        assert np.abs(o.as_matrix(o.discrete_jacobian(m, Q, Z[k:k + 1], h))[0] - J).max() < 1e-12 * max(1.0, np.abs(J).max())
