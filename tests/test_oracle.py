@@ -301,3 +301,33 @@ def test_quadrotor_rk4_jacobian_vs_50_digit_differences():
         xn, J = hp.discrete_jacobian(f, QS[Q], Z[k], 13, h)
         assert np.abs(o.discrete_dynamics(m, Q, Z[k:k + 1], h)[0] - xn).max() < 1e-13 * max(1.0, np.abs(xn).max())
         assert np.abs(o.as_matrix(o.discrete_jacobian(m, Q, Z[k:k + 1], h))[0] - J).max() < 1e-12 * max(1.0, np.abs(J).max())
+
+
+def test_mrp_and_rodrigues_formulas_from_the_quaternion_group():
+    """MRP / RodriguesParam `kinematics` and `∇differential` are restated from Rotations.jl's published formulas and no reference
+    test pins them.  First principles do: through p <-> q both must agree with the QUATERNION statements the
+    reference does pin (kinematics 1/2 L(q) H w, test/liemodel.jl:13-20; composition = Hamilton product):
+      kinematics(p, w) = d/dt param(q(t)) with qdot = 1/2 q (x) [0; w],     ∇differential(p) = d param(q(p) (x) q(delta)) / d delta at 0."""
+    def qmul(a, b):
+        return np.r_[a[0] * b[0] - a[1:] @ b[1:], a[0] * b[1:] + b[0] * a[1:] + np.cross(a[1:], b[1:])]
+    maps = {"mrp": (lambda p: np.r_[1 - p @ p, 2 * p] / (1 + p @ p), lambda q: q[1:] / (1 + q[0]), o.ROT_MRP),
+            "rp": (lambda g: np.r_[1.0, g] / np.sqrt(1 + g @ g), lambda q: q[1:] / q[0], o.ROT_RP)}
+    rng = np.random.default_rng(12)
+    eps = 1e-6
+    for name, (to_q, from_q, rc) in maps.items():
+        m = o.body(rc)
+        Z = rand_inputs(12, 6, 5, rng)
+        xd = o.dynamics(m, Z)
+        G = o.errstate_jacobian(m, Z[:, :12])                      # (N, nerr, n) column-major per knot: G[k].T is n x nerr
+        for k in range(5):
+            p, w = Z[k, 3:6], Z[k, 9:12]
+            q = to_q(p)
+            qd = 0.5 * qmul(q, np.r_[0.0, w])
+            unit = lambda v: v / np.linalg.norm(v)
+            pdot = (from_q(unit(q + eps * qd)) - from_q(unit(q - eps * qd))) / (2 * eps)
+            assert np.abs(xd[k, 3:6] - pdot).max() < 1e-8
+            D = np.zeros((3, 3))
+            for j in range(3):
+                d = np.zeros(3); d[j] = eps
+                D[:, j] = (from_q(qmul(q, to_q(d))) - from_q(qmul(q, to_q(-d)))) / (2 * eps)
+            assert np.abs(G[k].T[3:6, 3:6] - D).max() < 1e-8
