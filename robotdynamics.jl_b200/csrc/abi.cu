@@ -134,6 +134,15 @@ int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long 
     rdb_context* c = M->ctx;
     const size_t es = esize(dtype);
     const int n = M->n, NZ = M->n + M->m, E = r.err ? M->nerr * (M->nerr + M->m) : n * NZ;
+    // Built-in models: the kernel itself reads and writes component-major arrays through 2-D tensor maps (kernels.cuh, SOA = true)
+    // when the component rows are whole 16-byte units; everything else (odd row lengths, unaligned pointers, user models,
+    // ImplicitMidpoint) is transposed around the knot-major kernel.
+    if (M->kind != RDB_CUSTOM && r.Q != Q_IMPLICIT_MIDPOINT && soa_tma_ok(r.Z, r.J, r.out, ld, int(es))) {
+        KnotRequest q = r;
+        q.soa = 1; q.ld = ld;
+        const int rc = dispatch(M, dtype, &q);
+        if (rc != RDB_ERR_NOT_IMPLEMENTED) return rc;
+    }
     SoaScratch* sc;
     { std::lock_guard<std::mutex> lock(c->soa_mu); sc = &c->soa[r.stream]; }
     long long SOA_CHUNK = (long long)(SOA_SCRATCH_BYTES / (size_t(E) * es));

@@ -42,7 +42,9 @@ struct KnotArgs {
     T* out;              // xdot or x+, (N, n);  may be nullptr
     long long N;
     int use_jmap;        // jmap describes J as a 2-D tensor (E x N); used by the padded-image store of the n = 12 models
-    TensorMap jmap;
+    TensorMap jmap;      // (component-major kernels, SOA = true: J as the tensor N x E, inner extent = knots)
+    TensorMap zmap;      // component-major kernels only: Z as the tensor N x (n+m), out as N x n
+    TensorMap omap;
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copies (TMA engine; SASS: UBLKCP / SYNCS) ------------------------
@@ -76,6 +78,12 @@ __device__ __forceinline__ void tensor_store_2d(const TensorMap* tm, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(tm), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
 }
+// 2-D tiled TMA load (SASS UTMALDG): box lands densely in shared memory, elements outside the tensor arrive as zeros, the mbarrier
+// receives the byte count of the whole box
+__device__ __forceinline__ void tensor_load_2d(uint32_t dst_smem, const TensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -101,20 +109,23 @@ template <int N_, int J, class XN, size_t... Ks>
 __device__ __forceinline__ void put_col_v(const XN& xn, double* col, rstd::index_sequence<Ks...>) {
     (st16(col + 2 * int(Ks), partial<J>(get<2 * int(Ks)>(xn)), partial<J>(get<2 * int(Ks) + 1>(xn))), ...);
 }
-template <int N_, mask_t CHUNK, int J, bool VEC, class T, class XN, size_t... Is>
+// ES = element stride of the image: 1 for the knot-major images, TILE for the component-major ones (element e of knot kt at
+// e * TILE + kt: consecutive lanes on consecutive words)
+template <int N_, mask_t CHUNK, int J, bool VEC, int ES, class T, class XN, size_t... Is>
 __device__ __forceinline__ void put_col(const XN& xn, T* jrow, rstd::index_sequence<Is...>) {
     if constexpr (chas(CHUNK, J)) {
         if constexpr (VEC) put_col_v<N_, J>(xn, jrow + N_ * J, rstd::make_index_sequence<size_t(N_ * sizeof(T) / 16)>{});
-        else ((jrow[int(Is) + N_ * J] = partial<J>(get<int(Is)>(xn))), ...);
+        else ((jrow[(int(Is) + N_ * J) * ES] = partial<J>(get<int(Is)>(xn))), ...);
     }
 }
-template <int N_, mask_t CHUNK, bool VEC, class T, class XN, size_t... Js>
+template <int N_, mask_t CHUNK, bool VEC, int ES = 1, class T, class XN, size_t... Js>
 __device__ __forceinline__ void put_cols(const XN& xn, T* jrow, rstd::index_sequence<Js...>) {
-    (put_col<N_, CHUNK, int(Js), VEC>(xn, jrow, rstd::make_index_sequence<size_t(N_)>{}), ...);
+    static_assert(!VEC || ES == 1, "16-byte column stores need unit element stride");
+    (put_col<N_, CHUNK, int(Js), VEC, ES>(xn, jrow, rstd::make_index_sequence<size_t(N_)>{}), ...);
 }
-template <class T, class XN, size_t... Is>
+template <int ES = 1, class T, class XN, size_t... Is>
 __device__ __forceinline__ void put_vals(const XN& xn, T* orow, rstd::index_sequence<Is...>) {
-    ((orow[Is] = plain(get<int(Is)>(xn))), ...);
+    ((orow[int(Is) * ES] = plain(get<int(Is)>(xn))), ...);
 }
 
 // ---- error-state ("LieState") mode --------------------------------------------------------------------------------------
@@ -197,10 +208,13 @@ __device__ __forceinline__ void images_free_barrier(int tid) {
 // 16-byte loads: their pitch is a multiple of 4 words, so 4-byte loads put 8..16 lanes of a warp on one bank.
 __device__ __forceinline__ void ld16(const float* p, float* z) { const float4 v = *reinterpret_cast<const float4*>(p); z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w; }
 __device__ __forceinline__ void ld16(const double* p, double* z) { const double2 v = *reinterpret_cast<const double2*>(p); z[0] = v.x; z[1] = v.y; }
-template <class T, int NZ>
+template <class T, int NZ, int ES = 1>
 __device__ __forceinline__ void read_row(const T* zrow, T (&z)[NZ]) {
     constexpr int PER = int(16 / sizeof(T));
-    if constexpr (NZ % PER == 0) {
+    if constexpr (ES != 1) {
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) z[i] = zrow[i * ES];
+    } else if constexpr (NZ % PER == 0) {
 #pragma unroll
         for (int i = 0; i < NZ; i += PER) ld16(zrow + i, z + i);
     } else {
@@ -210,25 +224,25 @@ __device__ __forceinline__ void read_row(const T* zrow, T (&z)[NZ]) {
 }
 
 // One role: evaluate the map for one knot with partials for the columns in CHUNK; write this role's share.
-template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC>
+template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC, int ES>
 __device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
     model.reset();                 // per-knot evaluation caches (e.g. Cartpole's stage-1 sincos) start empty
     T zreg[NZ];
-    read_row<T, NZ>(zrow, zreg);
+    read_row<T, NZ, ES>(zrow, zreg);
     if constexpr (ERR) {
         auto zz = load_seeded_err<Model, T, CHUNK>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         auto e = project_err<Model, T>(xn);
         images_free_barrier<NTHR, ISSUERS>(tid);
-        put_cols<Model::nerr, CHUNK, VEC>(e, jrow, rstd::make_index_sequence<size_t(Model::nerr + m)>{});
-        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
+        put_cols<Model::nerr, CHUNK, VEC, ES>(e, jrow, rstd::make_index_sequence<size_t(Model::nerr + m)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals<ES>(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     } else {
         auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
         auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
         images_free_barrier<NTHR, ISSUERS>(tid);
-        if constexpr (WITH_J) put_cols<n, CHUNK, VEC>(xn, jrow, rstd::make_index_sequence<size_t(NZ)>{});
-        if constexpr (WRITE_OUT) { if (orow) put_vals(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
+        if constexpr (WITH_J) put_cols<n, CHUNK, VEC, ES>(xn, jrow, rstd::make_index_sequence<size_t(NZ)>{});
+        if constexpr (WRITE_OUT) { if (orow) put_vals<ES>(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     }
 }
 
@@ -236,13 +250,13 @@ template <int R, class L> struct list_at;
 template <int R, mask_t M0, mask_t... Ms> struct list_at<R, MaskList<M0, Ms...>> { static constexpr mask_t value = list_at<R - 1, MaskList<Ms...>>::value; };
 template <mask_t M0, mask_t... Ms> struct list_at<0, MaskList<M0, Ms...>> { static constexpr mask_t value = M0; };
 
-template <class Model, int Q, class T, bool WITH_J, bool ERR, class Chunks, int NTHR, int ROLL, int ISSUERS, bool VEC, int R = 0>
+template <class Model, int Q, class T, bool WITH_J, bool ERR, class Chunks, int NTHR, int ROLL, int ISSUERS, bool VEC, int ES, int R = 0>
 __device__ __forceinline__ void dispatch_role(int role, const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
     if constexpr (R + 1 == Chunks::count) {
-        role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC>(model, zrow, h, jrow, orow, tid);
+        role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, jrow, orow, tid);
     } else {
-        if (role == R) role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC>(model, zrow, h, jrow, orow, tid);
-        else dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, ISSUERS, VEC, R + 1>(role, model, zrow, h, jrow, orow, tid);
+        if (role == R) role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, jrow, orow, tid);
+        else dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, ISSUERS, VEC, ES, R + 1>(role, model, zrow, h, jrow, orow, tid);
     }
 }
 
@@ -320,7 +334,11 @@ struct KnotSmem {
 };
 
 
-template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL, bool ERR = false>
+// SOA = true: component-major caller arrays (Z (n+m, N), J (n(n+m), N), out (n, N); N * sizeof(T) a multiple of 16).  The layout
+// change is done by the TMA unit: the tile of Z arrives through a 2-D tensor map as the box TILE x (n+m) — image [component][knot],
+// read conflict-free — and the results, assembled as [entry][knot], leave through 2-D tensor stores of TILE x E / TILE x n boxes.
+// The ragged last tile needs no special case: loads beyond N arrive as zeros, stores beyond N are dropped.
+template <class Model, int Q, class T, int TILE, bool WITH_J, class Chunks, int MINB, int ROLL, bool ERR = false, bool SOA = false>
 __global__ void __launch_bounds__(TILE * Chunks::count, MINB)
 knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     using S = KnotSmem<Model, TILE, WITH_J, T, ERR>;
@@ -340,9 +358,14 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     const bool want_j = WITH_J && a.J != nullptr;
     const bool want_o = a.out != nullptr;
     // TMA path needs the reference's knot-major layout and 16-byte aligned streams
-    const bool tma_ok = ((reinterpret_cast<uintptr_t>(a.Z) | reinterpret_cast<uintptr_t>(a.J) |
-                                                    reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
-    auto tile_tma = [&](long long tile) { return tma_ok && (tile + 1) * TILE <= N; };
+    const bool tma_ok = SOA || ((reinterpret_cast<uintptr_t>(a.Z) | reinterpret_cast<uintptr_t>(a.J) |
+                                                           reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
+    auto tile_tma = [&](long long tile) { return tma_ok && (SOA || (tile + 1) * TILE <= N); };
+    auto load_tile = [&](long long tile, int buf) {           // thread 0: one TMA copy of the tile's [x;u] rows into image `buf`
+        mbar_expect_tx(bar0 + 8 * buf, uint32_t(S::in_bytes));
+        if constexpr (SOA) tensor_load_2d(smem_u32(in_img[buf]), &a.zmap, int(tile * TILE), 0, bar0 + 8 * buf);
+        else bulk_load(smem_u32(in_img[buf]), a.Z + tile * TILE * NZ, uint32_t(S::in_bytes), bar0 + 8 * buf);
+    };
 
     if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
     __syncthreads();
@@ -352,10 +375,7 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     long long tile = blockIdx.x;
-    if (tile < ntiles && tile_tma(tile) && tid == 0) {
-        mbar_expect_tx(bar0, uint32_t(S::in_bytes));
-        bulk_load(smem_u32(in_img[0]), a.Z + tile * TILE * NZ, uint32_t(S::in_bytes), bar0);
-    }
+    if (tile < ntiles && tile_tma(tile) && tid == 0) load_tile(tile, 0);
     uint32_t phase[2] = {0, 0};
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
@@ -363,27 +383,32 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
         const long long nxt = tile + gridDim.x;
         // (1) prefetch the next tile's [x;u] rows (buffer s^1 was last read before the previous iteration's barriers)
-        if (tid == 0 && nxt < ntiles && tile_tma(nxt)) {
-            mbar_expect_tx(bar0 + 8 * (s ^ 1), uint32_t(S::in_bytes));
-            bulk_load(smem_u32(in_img[s ^ 1]), a.Z + nxt * TILE * NZ, uint32_t(S::in_bytes), bar0 + 8 * (s ^ 1));
-        }
+        if (tid == 0 && nxt < ntiles && tile_tma(nxt)) load_tile(nxt, s ^ 1);
         // (2) this tile's inputs
         const bool tma = tile_tma(tile);
         if (tma) { mbar_wait(bar0 + 8 * s, phase[s]); phase[s] ^= 1; }
         else { coop_load(in_img[s], NZ, a.Z, k0, cnt, NZ, tid, NTHR); __syncthreads(); }
         // (3) compute in registers
-        const T* zrow = in_img[s] + kt * NZ;
+        const T* zrow = SOA ? in_img[s] + kt : in_img[s] + kt * NZ;
+        constexpr int ES = SOA ? TILE : 1;                     // element stride of the images
         T h = T(0);
         if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? (kt < cnt ? a.dt[k0 + kt] : 0.0) : a.dt0);
         (void)cnt;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
-        dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, S::ISSUERS, S::ROWSTORE>(role, model, zrow, h, j_img + kt * S::PJ, want_o ? o_img + kt * n : nullptr, tid);
+        dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, S::ISSUERS, S::ROWSTORE && !SOA, ES>(
+            role, model, zrow, h, SOA ? j_img + kt : j_img + kt * S::PJ, want_o ? (SOA ? o_img + kt : o_img + kt * n) : nullptr, tid);
         // (5) publish
         if (tma) {
             fence_proxy_async();
             __syncthreads();
-            if constexpr (S::ROWSTORE) {
+            if constexpr (SOA) {
+                if (tid == 0) {
+                    if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), int(k0), 0);
+                    if (want_o) tensor_store_2d(&a.omap, smem_u32(o_img), int(k0), 0);
+                    bulk_commit();
+                }
+            } else if constexpr (S::ROWSTORE) {
                 if (a.use_jmap) {
                     if (tid == 0) {
                         if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), 0, int(k0));

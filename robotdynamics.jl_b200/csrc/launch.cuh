@@ -126,6 +126,9 @@ struct DeviceInfo { int device; int sm_count; int pdl; };   // pdl: launch with 
 // ---- tensor map of J for the padded-image store (kernels.cuh: tensor_store_2d) -------------------------------------------------
 // J is described as a 2-D tensor: inner extent E = rows x cols of one knot's Jacobian, outer extent N knots, dense.  The box is
 // pitch x tile with pitch > E: the pad of every smem row lies outside the tensor and is not written.
+#ifndef RDB_SOA_KERNELS
+#define RDB_SOA_KERNELS 1        // component-major kernels (tensor-map loads / stores); 0 leaves only the transposing path
+#endif
 #ifndef RDB_TUNE_JMAP
 #define RDB_TUNE_JMAP 1          // 0: tuning experiments only (one bulk store per knot row instead)
 #endif
@@ -145,31 +148,42 @@ inline rdb_encode_tiled_fn encode_tiled_entry() {
     return fn;
 }
 static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) >= alignof(CUtensorMap), "TensorMap must mirror CUtensorMap");
-// returns 1 and fills *tm when J (16-byte aligned, at least one full tile) can leave through a tensor map, 0 otherwise
-inline int encode_jmap(TensorMap* tm, void* J, long long N, int E, int pitch, int tile, int es) {
-    if (!RDB_TUNE_JMAP || !J || N < tile || pitch > 256 || tile > 256 || (reinterpret_cast<uintptr_t>(J) & 15) != 0) return 0;
+// a dense 2-D tensor (inner extent d0 contiguous, outer extent d1 at a pitch of ld elements) with a box of b0 x b1 elements
+inline int encode_map2d(TensorMap* tm, const void* base, long long d0, long long d1, long long ld, int b0, int b1, int es) {
+    if (!base || b0 > 256 || b1 > 256 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * es) % 16 != 0) return 0;
     rdb_encode_tiled_fn enc = encode_tiled_entry();
     if (!enc) return 0;
-    const cuuint64_t gdim[2] = {cuuint64_t(E), cuuint64_t(N)};
-    const cuuint64_t gstride[1] = {cuuint64_t(E) * cuuint64_t(es)};
-    const cuuint32_t box[2] = {cuuint32_t(pitch), cuuint32_t(tile)};
+    const cuuint64_t gdim[2] = {cuuint64_t(d0), cuuint64_t(d1)};
+    const cuuint64_t gstride[1] = {cuuint64_t(ld) * cuuint64_t(es)};
+    const cuuint32_t box[2] = {cuuint32_t(b0), cuuint32_t(b1)};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = enc(reinterpret_cast<CUtensorMap*>(tm), es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, J,
-                            gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUresult rc = enc(reinterpret_cast<CUtensorMap*>(tm), es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                            const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return rc == CUDA_SUCCESS ? 1 : 0;
+}
+// returns 1 and fills *tm when J (16-byte aligned, at least one full tile) can leave through a tensor map, 0 otherwise
+inline int encode_jmap(TensorMap* tm, void* J, long long N, int E, int pitch, int tile, int es) {
+    if (!RDB_TUNE_JMAP || N < tile) return 0;
+    return encode_map2d(tm, J, E, N, E, pitch, tile, es);
+}
+// can component-major arrays of leading dimension ld (knots per component row) go through the tensor-map kernels?
+inline bool soa_tma_ok(const void* Z, const void* J, const void* out, long long ld, int es) {
+    return encode_tiled_entry() != nullptr && (ld * es) % 16 == 0 &&
+           ((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(J) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
 }
 
 // shape seen by the tiling rules in error-state mode: nerr rows, nerr + m columns (like an n = 12 model)
 template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m, rot = ROT_QUAT, frame = FRAME_WORLD; };
 
-template <class Model, int Q, class T, bool WITH_J, bool ERR = false>
+template <class Model, int Q, class T, bool WITH_J, bool ERR = false, bool SOA = false>
 struct KnotLaunch {
     using Cfg = KnotConfig<std::conditional_t<ERR, ErrShape<Model>, Model>, T, WITH_J, Q>;
     using S = KnotSmem<Model, Cfg::TILE, WITH_J, T, ERR>;
     static constexpr int NTHR = Cfg::TILE * Cfg::Chunks::count;
-    static int run(const Model& model, const KnotArgs<T>& a, const DeviceInfo& dev, cudaStream_t st) {
-        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL, ERR>;
+    // ld: knots per component row of the caller's arrays (component-major kernels only)
+    static int run(const Model& model, const KnotArgs<T>& a, const DeviceInfo& dev, cudaStream_t st, long long ld = 0) {
+        auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL, ERR, SOA>;
         static int occ_cache[64];   // CTAs/SM per device id; 0 = not yet configured on that device
         const int d = dev.device & 63;
         if (occ_cache[d] == 0) {
@@ -190,7 +204,15 @@ struct KnotLaunch {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = dev.pdl ? 1 : 0;
-        if constexpr (S::ROWSTORE) {
+        if constexpr (SOA) {
+            KnotArgs<T> b = a;
+            constexpr int es = int(sizeof(T));
+            int ok = encode_map2d(&b.zmap, b.Z, b.N, S::NZ, ld, Cfg::TILE, S::NZ, es);
+            if (b.J) ok &= encode_map2d(&b.jmap, b.J, b.N, S::E, ld, Cfg::TILE, S::E, es);
+            if (b.out) ok &= encode_map2d(&b.omap, b.out, b.N, S::n, ld, Cfg::TILE, S::n, es);
+            if (!ok) return -2;
+            return int(cudaLaunchKernelEx(&cfg, kern, model, b));
+        } else if constexpr (S::ROWSTORE) {
             KnotArgs<T> b = a;
             b.use_jmap = encode_jmap(&b.jmap, b.J, b.N, S::E, S::PJ, Cfg::TILE, int(sizeof(T)));
             return int(cudaLaunchKernelEx(&cfg, kern, model, b));
@@ -208,7 +230,8 @@ struct KnotRequest {
     int with_j;
     int err;             // error-state Jacobian  G(x+)' [A B] blkdiag(G(x), I)  (rigid bodies; needs with_j)
     ModelParams<double> params;
-    const void* Z; const double* dt; double dt0; void* J; void* out; long long N;   // knot-major (component-major is handled in abi.cu)
+    const void* Z; const double* dt; double dt0; void* J; void* out; long long N;   // knot-major, or component-major when soa != 0
+    int soa; long long ld;   // component-major arrays with ld knots per component row, served by the tensor-map kernels
     // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)
     const void* x0; const void* U; void* X; long long ntraj; int K;
     DeviceInfo dev;
@@ -233,6 +256,10 @@ inline int run_one(const KnotRequest& r) {
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
+    if (r.soa) {
+        if constexpr (RDB_SOA_KERNELS) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, true>::run(model, a, r.dev, r.stream, r.ld);
+        else return -2;
+    }
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
 #ifndef RDB_IMPLICIT_WARP_MIN_N

@@ -84,6 +84,12 @@ def test_layouts_and_pointer_kinds_agree_bitwise(rd, torch_, name, dtype):
         assert Js.shape == (n * nz, N) and np.array_equal(Js.T.reshape(N, nz, n), J_dev)
         Jsh = gm._h.discrete_jacobian(o.RK4, Zs, dt, layout=rd.SOA)
         assert np.array_equal(Jsh, Js)
+        # value-only operations in the component-major layout (tensor-map kernels when N * sizeof(T) is a multiple of 16,
+        # transposes around the knot-major kernel otherwise: both must reproduce the knot-major results bit for bit)
+        xs = gm._h.discrete_dynamics(o.RK4, dev(torch_, Zs), dt, layout=rd.SOA).cpu().numpy()
+        assert xs.shape == (n, N) and np.array_equal(xs.T, gm._h.discrete_dynamics(o.RK4, Zd, dt).cpu().numpy())
+        fs = gm._h.dynamics(dev(torch_, Zs), layout=rd.SOA).cpu().numpy()
+        assert np.array_equal(fs.T, gm._h.dynamics(Zd).cpu().numpy())
         # deliberately mis-aligned device buffers (element offset 1): cooperative-copy path instead of TMA
         if N > 1:
             esz = np.dtype(dtype).itemsize
