@@ -16,7 +16,9 @@
  *   - layout RDB_AOS is the reference's own memory image: Z is the Julia Matrix{T}(n+m, N) of `getdata(z)` columns,
  *     J the Array{T,3}(n, n+m, N) of column-major [A B] DynamicsJacobian data (src/jacobian.jl:26-37), x+ the
  *     Matrix{T}(n, N).  RDB_SOA is component-major: Z is (N, n+m) as a Julia matrix, i.e. each component of [x;u] is a
- *     unit-stride stream of N values; J has n*(n+m) such streams (entry i + n*j), x+ has n.
+ *     unit-stride stream of N values; J has n*(n+m) such streams (entry i + n*j), x+ has n.  Both layouts run at the same
+ *     speed when N * sizeof(T) is a multiple of 16 (the kernel reads and writes component-major arrays through 2-D TMA
+ *     tensor maps); other N are transposed around the knot-major kernel.
  *   - t may be NULL (all shipped models are time-invariant, src/dynamics.jl:83); dt may be NULL (then dt0 is
  *     used for every knot point).  Knot points with dt == 0 (terminal, src/knotpoint.jl:57-67) yield J = [I 0].
  */

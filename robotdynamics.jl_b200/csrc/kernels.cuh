@@ -16,8 +16,11 @@
 //     are assembled as the exact output image in shared memory and leave by one TMA bulk store per tile that
 //     drains while the next tile computes.  No per-element global address arithmetic exists on that path.
 //   * unaligned pointers and the ragged last tile use a cooperative coalesced copy between the same shared-memory images
-//     and global memory; component-major ("SoA") callers are served by coalesced transposes around this kernel (layout.cu):
-//     one contiguous stream per tile is what HBM and the TMA engine like, 221 streams a megabyte apart are not.
+//     and global memory.
+//   * component-major ("SoA") callers are served by the same kernel with SOA = true: 2-D tensor maps let the TMA unit load the
+//     tile as the image [component][knot] and store the results from [entry][knot] images — the layout change costs nothing
+//     (coalesced transposes around the knot-major kernel, layout.cu, remain as the fallback for rows that are not whole
+//     16-byte units).
 #pragma once
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
@@ -261,7 +264,7 @@ __device__ __forceinline__ void dispatch_role(int role, const Model& model, cons
 }
 
 // cooperative copies between a knot-major smem image [cnt][W] (row pitch P >= W) and knot-major global memory: the fallback for
-// unaligned pointers and the ragged last tile (component-major callers are transposed outside the kernel, layout.cu)
+// unaligned pointers and the ragged last tile
 template <class T>
 __device__ __forceinline__ void coop_load(T* img, int P, const T* g, long long k0, int cnt, int W, int tid, int nthr) {
     if (P == W) {

@@ -1,4 +1,5 @@
-// layout.cu — coalesced transposes between the component-major ("SoA") caller layout and the knot-major layout the kernels use.
+// layout.cu — coalesced transposes between the component-major ("SoA") caller layout and the knot-major layout: the FALLBACK for
+// component-major calls the tensor-map kernels cannot take (rows that are not whole 16-byte units, user models, ImplicitMidpoint).
 // SoA: W unit-stride streams of N values (stream c starts at base + c*ld);  knot-major: [cnt][W].  Classic 32x32 shared-memory
 // tile transpose: both sides read and write full 128-byte lines.
 #include "layout.h"
