@@ -317,7 +317,8 @@ struct KnotSmem {
     // of 32 words puts all lanes of a warp on ONE bank (E = 192 for n=12, m=4).  The quaternion models have odd E (221, 247):
     // dense image, conflict-free, leaves by ONE TMA bulk store per tile.  The n = 12 models (E even, columns = whole 16-byte
     // units) get a pitch of an ODD number of 16-byte units, write their columns with 16-byte stores (conflict-free) and leave
-    // by one TMA bulk store PER KNOT ROW, issued by TILE threads in parallel.
+    // by ONE 2-D tensor store per tile whose box is the padded image (the pad lies outside the tensor and is dropped);
+    // fallback when no tensor map could be encoded: one 1-D bulk store PER KNOT ROW, issued by TILE threads in parallel.
     // (only when the dense image would be badly conflicted: >= 16 lanes per bank; the 8-way case E = 216 fp32 measured faster dense)
     static constexpr bool ROWSTORE = knot_rowstore(JR, JC, WITH_J, int(sizeof(T)));
     static constexpr int PJ = knot_pitch(JR, JC, WITH_J, int(sizeof(T)));
