@@ -1,6 +1,6 @@
 """Launches the error-state Jacobian kernel or the warp-cooperative ImplicitMidpoint kernel a few times (target of ncu captures).
 
-    python scripts/prof_extra.py err|implicit
+    python scripts/prof_extra.py err|implicit|soa
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,7 +15,14 @@ if __name__ == "__main__":
     qd = rd.Quadrotor()
     N = 262144
     Z = torch.from_numpy(g.rand_inputs(qd._h, N, np.random.default_rng(2)).astype(np.float32)).cuda()
-    if what == "err":
+    if what == "soa":                    # C2 in the component-major layout (2-D tensor-map loads and stores)
+        cp = rd.Cartpole()
+        Nc = 1 << 20
+        Zc = torch.rand((5, Nc), dtype=torch.float64, device="cuda")
+        Jc = torch.empty((20, Nc), dtype=torch.float64, device="cuda")
+        for _ in range(8):
+            cp._h.discrete_jacobian(3, Zc, 0.01, J=Jc, layout=rd.SOA)
+    elif what == "err":
         J = torch.empty((N, 16, 12), dtype=torch.float32, device="cuda")
         for _ in range(8):
             qd._h.discrete_error_jacobian(3, Z, 0.01, J=J)

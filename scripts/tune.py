@@ -75,6 +75,7 @@ VARIANTS = {
     },
     "cartpole": {
         "base": {},
+        "dense": dict(RDB_TUNE_ROWSTORE=0),
         "t32_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16),
         "t32_minb14": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=14),
         "t32_minb10": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=10),
