@@ -11,7 +11,8 @@ differentiation at a handful of points.  Nothing here shares code with oracle/rd
                             midpoint) composed in mpmath at 50 digits, differentiated by mpmath's high-precision central differences
                             (no derivative formula of any kind is involved);
   * `quadrotor_f()`         RigidBody{QuatRotation} with the Quadrotor wrench (reference: src/rigidbody.jl:213-236,
-                            test/quadrotor.jl:56-96; rotation formulas of SURVEY.md §8c) in plain mpmath arithmetic.
+                            test/quadrotor.jl:56-96; rotation formulas of SURVEY.md §8c) in plain mpmath arithmetic;
+  * `satellite_mrp_f()`     RigidBody{MRP} with the Satellite wrench (examples/single_satellite.jl:17-35), BASELINE config C4.
 """
 import mpmath as mp
 import numpy as np
@@ -93,6 +94,27 @@ def quadrotor_f(mass="0.5", J=("0.0023", "0.0023", "0.004"), gz="-9.81", L="0.17
         wxJw = [w[1] * Jw[2] - w[2] * Jw[1], w[2] * Jw[0] - w[0] * Jw[2], w[0] * Jw[1] - w[1] * Jw[0]]
         wdot = [(tau[i] - wxJw[i]) / J[i] for i in range(3)]
         return list(v) + qdot + [Fw[i] / mass for i in range(3)] + wdot
+    return f
+
+
+def satellite_mrp_f(mass="1.0", J=("1.0", "1.0", "1.0")):
+    """RigidBody{MRP} with the Satellite / Body wrench F_world = q*u[1:3], M_body = u[4:6] (reference: src/rigidbody.jl:213-236,
+    examples/single_satellite.jl:17-35); state [r(3) p(3) v(3) w(3)], world-frame velocity, diagonal inertia."""
+    mass = mp.mpf(mass)
+    J = [mp.mpf(v) for v in J]
+
+    def f(x, u):
+        p, v, w = x[3:6], x[6:9], x[9:12]
+        n2 = sum(a * a for a in p)
+        q = [(1 - n2) / (1 + n2)] + [2 * a / (1 + n2) for a in p]                 # the unit quaternion of the MRP
+        F = _rotate(q, list(u[0:3]))
+        pw = sum(a * b for a, b in zip(p, w))
+        cr = [p[1] * w[2] - p[2] * w[1], p[2] * w[0] - p[0] * w[2], p[0] * w[1] - p[1] * w[0]]
+        pdot = [((1 - n2) * w[i] + 2 * cr[i] + 2 * p[i] * pw) / 4 for i in range(3)]   # 1/4 [(1-|p|^2) I + 2 skew(p) + 2 p p'] w
+        Jw = [J[i] * w[i] for i in range(3)]
+        wxJw = [w[1] * Jw[2] - w[2] * Jw[1], w[2] * Jw[0] - w[0] * Jw[2], w[0] * Jw[1] - w[1] * Jw[0]]
+        wdot = [(u[3 + i] - wxJw[i]) / J[i] for i in range(3)]
+        return list(v) + pdot + [F[i] / mass for i in range(3)] + wdot
     return f
 
 

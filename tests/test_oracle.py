@@ -331,3 +331,15 @@ def test_mrp_and_rodrigues_formulas_from_the_quaternion_group():
                 d = np.zeros(3); d[j] = eps
                 D[:, j] = (from_q(qmul(q, to_q(d))) - from_q(qmul(q, to_q(-d)))) / (2 * eps)
             assert np.abs(G[k].T[3:6, 3:6] - D).max() < 1e-8
+
+
+def test_satellite_mrp_rk2_jacobian_vs_50_digit_differences():
+    """BASELINE config C4: Satellite RigidBody{MRP}, RK2 (explicit midpoint), dt = 0.1 (examples/single_satellite.jl:39)."""
+    from oracle import highprec as hp
+    f = hp.satellite_mrp_f()
+    Z = rand_inputs(12, 6, 3, np.random.default_rng(8))
+    m = o.satellite(o.ROT_MRP)
+    for k, (Q, h) in enumerate(((o.RK2, 0.1), (o.RK2, 0.01), (o.RK4, 0.1))):
+        xn, J = hp.discrete_jacobian(f, QS[Q], Z[k], 12, h)
+        assert np.abs(o.discrete_dynamics(m, Q, Z[k:k + 1], h)[0] - xn).max() < 1e-13 * max(1.0, np.abs(xn).max())
+        assert np.abs(o.as_matrix(o.discrete_jacobian(m, Q, Z[k:k + 1], h))[0] - J).max() < 1e-12 * max(1.0, np.abs(J).max())
