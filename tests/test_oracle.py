@@ -343,3 +343,33 @@ def test_satellite_mrp_rk2_jacobian_vs_50_digit_differences():
         xn, J = hp.discrete_jacobian(f, QS[Q], Z[k], 12, h)
         assert np.abs(o.discrete_dynamics(m, Q, Z[k:k + 1], h)[0] - xn).max() < 1e-13 * max(1.0, np.abs(xn).max())
         assert np.abs(o.as_matrix(o.discrete_jacobian(m, Q, Z[k:k + 1], h))[0] - J).max() < 1e-12 * max(1.0, np.abs(J).max())
+
+
+def test_implicit_midpoint_vs_50_digit_root_and_differences():
+    """DiscretizedDynamics{L, ImplicitMidpoint} (src/integration.jl:620-694): x2 solves x1 + h f((x1 + x2)/2, u) - x2 = 0.  The root is
+    found here at 50 digits (mpmath.findroot) and the Jacobian of the solution map by central differences — no Newton loop of ours, no
+    implicit-function-theorem formula."""
+    import mpmath as mpm
+    from oracle import highprec as hp
+    f = hp.cartpole_f_mp()
+    m = o.cartpole()
+    rng = np.random.default_rng(13)
+    Z = rng.random((3, 5))
+
+    def solve(z, h):
+        x1, u = z[:4], z[4:]
+        g = lambda *x2: [a + h * fi - b for a, fi, b in zip(x1, f([(a + b) / 2 for a, b in zip(x1, x2)], u), x2)]
+        return list(mpm.findroot(g, x1, tol=mpm.mpf(10) ** -40))
+
+    for k, h in enumerate((0.01, 0.05, 0.1)):
+        zz, hh = [mpm.mpf(float(v)) for v in Z[k]], mpm.mpf(h)
+        xn = np.array([float(v) for v in solve(zz, hh)])
+        J = np.zeros((4, 5))
+        eps = mpm.mpf(10) ** -15
+        for j in range(5):
+            zp, zm = list(zz), list(zz)
+            zp[j] += eps
+            zm[j] -= eps
+            J[:, j] = [float((a - b) / (2 * eps)) for a, b in zip(solve(zp, hh), solve(zm, hh))]
+        assert np.abs(o.discrete_dynamics(m, o.IMPLICIT_MIDPOINT, Z[k:k + 1], h)[0] - xn).max() < 1e-12
+        assert np.abs(o.as_matrix(o.discrete_jacobian(m, o.IMPLICIT_MIDPOINT, Z[k:k + 1], h))[0] - J).max() < 1e-10
