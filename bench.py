@@ -1,26 +1,36 @@
 #!/usr/bin/env python
 """bench.py — knot-point Jacobian evals/sec (discrete_jacobian! RK4), the BASELINE.json metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|quadrotor|satellite]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cartpole|quadrotor|satellite|sweep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one batched discrete_jacobian! call over one batch of synthetic knot points (default workload: BASELINE
 configs[1], Cartpole RK4, 2^20 knot points, fp64).  One process per GPU; every rank evaluates its own batch of the full
-size (weak scaling, no data-path collective: knot points are independent), the timed region is bracketed by a barrier
-and a device synchronize, timed with CUDA events on the launching stream, and the MAX over ranks is reported.
+size (weak scaling, no data-path collective: knot points are independent).  The timed region is EXACTLY K steps, bracketed by a
+barrier and a device synchronize on both sides, timed with CUDA events on the launching stream; the MAX over ranks is reported
+and every rank's own time is listed (`per_rank_ms_per_step`).
 
-  value      evals/s with inputs and outputs resident in HBM (kernel path through the C ABI with device pointers)
-  e2e        the same metric through the same C-ABI call with HOST (pinned) buffers: H2D of [x;u], kernel, D2H of J inside
-             the timed region, every step
+  value      evals/s with inputs and outputs resident in HBM (one pre-validated C-ABI launch per step, rdb_plan_launch)
+  e2e        the same metric through the C-ABI call with HOST (pinned) buffers: H2D of [x;u], kernel, D2H of J inside the timed
+             region, every step
   roofline   algorithmic bytes (read [x;u], write J: SURVEY.md §8d) / measured launch duration vs the measured HBM peak
   cpu_baseline  the CPU oracle (a port of the reference's ForwardAD path; Julia is not installed) on the host cores
+  extra      the other BASELINE configurations measured the same way in the same process: configs[2] (Quadrotor RK4 fp32, plus its
+             error-state form), configs[3] (Satellite{MRP} RK2 fp64) — weak, one full batch per GPU — and configs[4], the mixed
+             4096 x 256 sweep, STRONG-scaled over the ranks by contiguous trajectory blocks
 
-`--impl reference` times that CPU path alone, as the reference arm (the reference is pure Julia and cannot run here).
-The oracle is only ever the baseline / checker here, never the measured product path.
+Launch gate: before the first event a ~2 ms device-side sleep is enqueued, so that the host has queued all K launches before the
+GPU reaches the timed region — the events then bracket K back-to-back kernel executions and no host launch latency (the quantity
+the metric names; without the gate a 20-step region of 0.8 ms carries ~2 % of host latency of the first launch).
+
+`--impl reference` times the reference's own CPU path alone (a Julia installation with RobotDynamics.jl if the box has one, else
+the C++ port of its ForwardAD path).  The oracle is only ever the baseline / checker here, never the measured product path.
 """
 import argparse
 import json
 import os
+import shutil
+import subprocess
 import sys
 import threading
 import time
@@ -41,6 +51,7 @@ WORKLOADS = {
 }
 SWEEP_DESC = ("BASELINE configs[4]: mixed trajectory sweep, 4096 trajectories x 256 knot points, first half Cartpole (fp64), second half "
               "Quadrotor (fp32), RK4, per-trajectory dt, contiguous trajectory blocks per rank (strong scaling)")
+GATE_CYCLES = 4_000_000          # ~2 ms of device-side sleep in front of the timed region (see module docstring)
 
 
 def make_inputs(n, m, N, dtype, seed):
@@ -96,41 +107,73 @@ def cpu_rate(name, budget_s, threads):
     return per_step * reps / el, f"{reps} passes over {per_step} of the workload's knot points ({el:.1f} s of CPU time), method=ForwardAD port", per_step
 
 
+def julia_reference(name, steps, warmup):
+    """The REAL reference on this box, if it has one: `julia` on PATH and RobotDynamics.jl loadable in oracle/ref_julia's project
+    (or a driver-installed copy under baseline/_ref).  Returns the parsed JSON of oracle/ref_julia/bench_ref.jl or None."""
+    exe = shutil.which("julia")
+    if not exe:
+        return None
+    env = dict(os.environ)
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref):
+        env["RD_REF"] = ref
+    try:
+        p = subprocess.run([exe, "--project=" + os.path.join(ROOT, "oracle", "ref_julia"), "-t", "auto",
+                            os.path.join(ROOT, "oracle", "ref_julia", "bench_ref.jl"), name, str(steps), str(warmup)],
+                           capture_output=True, text=True, timeout=900, env=env)
+        for ln in reversed(p.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+    except Exception:
+        return None
+    return None
+
+
 def run_reference(args):
-    """Reference arm: the reference's own algorithm on the host CPU (oracle port; Julia absent), all host threads."""
+    """Reference arm: the reference's own algorithm on the host CPU, all host threads.  Probes for a Julia installation first (the
+    real RobotDynamics.jl, `kind: reference`); the images used so far have none, then the C++ port of its ForwardAD path is timed."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
-    from oracle import rd_oracle as o
     name = args.workload
     desc, n, m, N, dtn, dt = WORKLOADS[name]
     threads = host_cores()
-    mk, Q = oracle_model(name)
-    model = mk()
-    # size one step so that (steps + warmup) passes stay within ~2 minutes
-    rate, _, _ = cpu_rate(name, 2.0, threads)
-    per_step = int(min(N, max(1 << 12, rate * min(1.0, 100.0 / max(1, args.steps + args.warmup)))))
-    Z = make_inputs(n, m, per_step, "float64", 100)
-    out = np.empty((per_step, n + m, n))
-    for _ in range(args.warmup):
-        o.discrete_jacobian(model, Q, Z, dt, nthreads=threads, out=out)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        o.discrete_jacobian(model, Q, Z, dt, nthreads=threads, out=out)
-    el = time.perf_counter() - t0
-    val = per_step * args.steps / el
-    sample = f"each step = {per_step} of the workload's {N} knot points, fp64, ForwardAD (Dual<{n + m}>) port of the reference path"
+    jl = julia_reference(name, args.steps, args.warmup)
+    if jl and "value" in jl:
+        val, ms, kind, cores = float(jl["value"]), float(jl["ms_per_step"]), "reference", int(jl.get("threads", threads))
+        sample = jl.get("sample", "RobotDynamics.jl jacobian!(StaticReturn(), ForwardAD(), ...) loop, Threads.@threads")
+        note = "RobotDynamics.jl v0.4.8 run in Julia on the host cores"
+    else:
+        from oracle import rd_oracle as o
+        mk, Q = oracle_model(name)
+        model = mk()
+        # size one step so that (steps + warmup) passes stay within ~2 minutes
+        rate, _, _ = cpu_rate(name, 2.0, threads)
+        per_step = int(min(N, max(1 << 12, rate * min(1.0, 100.0 / max(1, args.steps + args.warmup)))))
+        Z = make_inputs(n, m, per_step, "float64", 100)
+        out = np.empty((per_step, n + m, n))
+        for _ in range(args.warmup):
+            o.discrete_jacobian(model, Q, Z, dt, nthreads=threads, out=out)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            o.discrete_jacobian(model, Q, Z, dt, nthreads=threads, out=out)
+        el = time.perf_counter() - t0
+        val, ms, kind, cores = per_step * args.steps / el, el / args.steps * 1e3, "port", threads
+        sample = f"each step = {per_step} of the workload's {N} knot points, fp64, ForwardAD (Dual<{n + m}>) port of the reference path"
+        note = "reference is pure Julia (probed: no `julia` on this box); CPU oracle port timed on host cores"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "note": "reference is pure Julia (not installed); CPU oracle port timed on host cores"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": desc, "note": note},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
 
 
 class ClockSampler(threading.Thread):
-    """Polls SM clock and clock-event reasons through NVML while the timed region runs."""
+    """Polls SM clock and clock-event reasons through NVML from before the pre-roll until after the post-roll; every sample carries a
+    host timestamp so that the ones taken inside the timed region can be told apart from the ones taken under the identical load
+    around it."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, index):
@@ -149,19 +192,25 @@ class ClockSampler(threading.Thread):
     def run(self):
         while self.ok and not self.stop_flag:
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz))
                 for bit, nm in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
-    def summary(self):
-        if not self.ok or not self.samples:
+    def summary(self, load_window, timed_window):
+        under = [m for (ts, m) in self.samples if load_window[0] <= ts <= load_window[1]]
+        timed = [m for (ts, m) in self.samples if timed_window[0] <= ts <= timed_window[1]]
+        if not self.ok or not under:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(under)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(under),
+                "samples_in_timed_region": len(timed), "sm_mhz_min": float(min(under)),
+                "how": "NVML polled every ~1 ms from the start of the pre-roll (the identical kernel, untimed, >= 60 ms) to the end of the "
+                       "post-roll; the timed region lies inside that window"}
 
 
 def physical_gpu_index(local):
@@ -174,190 +223,271 @@ def physical_gpu_index(local):
     return local
 
 
-def run_sweep(args):
-    """BASELINE configs[4]: the 4096 x 256 mixed sweep, sharded by contiguous trajectory blocks (strong scaling: total work fixed)."""
-    import torch
-    import torch.distributed as dist
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import rdb200 as rd
-    from rdb200 import sharding as sh
-    ntraj, K = 4096, 256
-    segs = sh.partition_segments({"cartpole": ntraj // 2, "quadrotor": ntraj // 2}, world, rank)
-    work = []
-    for name, (lo, hi) in segs.items():
-        _, n, m, _, dtn, _ = WORKLOADS[name]
+class Bench:
+    """Shared plumbing of the timed regions: rank / world, barrier, gate, per-rank gather."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device visible — the product path has no CPU fallback")
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import rdb200 as rd
+        self.rd = rd
+        self.launches = 0
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def gather(self, x):
+        """every rank's value of a python float, as a list (rank order)"""
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def timed(self, step, steps, warmup, streams=None):
+        """W untimed + EXACTLY `steps` timed calls of step(i); returns (local ms, host window of the timed region).  `streams`: side
+        streams the step uses (forked from / joined into the current stream around the timed region)."""
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        for i in range(max(warmup, 3)):
+            step(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(GATE_CYCLES)                    # launch gate: the GPU sleeps while the host queues the whole timed region
+        t_host0 = time.perf_counter()
+        e0.record(main)
+        for st in streams or ():
+            st.wait_stream(main)
+        for i in range(steps):
+            step(i)
+        for st in streams or ():
+            main.wait_stream(st)
+        e1.record(main)
+        self.barrier()
+        t_host1 = time.perf_counter()
+        return e0.elapsed_time(e1), (t_host0, t_host1)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+class KnotWorkload:
+    """One BASELINE configuration on this rank: rotating device buffer sets (more bytes between two uses of a set than the 126 MB L2
+    holds several times over) and one pre-validated plan per set."""
+
+    def __init__(self, B, name, N=None, error_state=False, seed0=0):
+        rd, torch = B.rd, B.torch
+        self.B, self.name = B, name
+        self.desc, self.n, self.m, Nw, self.dtn, self.dt = WORKLOADS[name]
+        self.N = Nw if N is None else N
         mk, Q = gpu_model(name, rd)
-        model = mk()
-        cnt = (hi - lo) * K
-        nsets = 6
-        Zs = [torch.from_numpy(make_inputs(n, m, cnt, dtn, 17 * rank + i)).cuda() for i in range(nsets)]
-        dt = torch.from_numpy(np.repeat(0.01 * (1 + np.arange(lo, hi) % 4), K)).cuda()
-        Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
-        work.append((model._h, Q.code, Zs, dt, Js, cnt, np.dtype(dtn).itemsize * ((n + m) + n * (n + m))))
+        self.model, self.Q = mk(), Q
+        h = self.model._h
+        self.es = np.dtype(self.dtn).itemsize
+        jr, jc = (h.nerr, h.nerr + h.m) if error_state else (h.n, h.n + h.m)
+        self.alg_bytes = self.es * ((h.n + h.m) + jr * jc)                      # SURVEY.md §8d: read z, write J
+        tdt = torch.float64 if self.dtn == "float64" else torch.float32
+        self.nsets = max(2, int(np.ceil(600e6 / (self.N * self.alg_bytes))) + 1)
+        self.Zs = [torch.from_numpy(make_inputs(self.n, self.m, self.N, self.dtn, seed0 + 1000 * B.rank + i)).cuda() for i in range(self.nsets)]
+        self.Js = [torch.empty((self.N, jc, jr), dtype=tdt, device="cuda") for _ in range(self.nsets)]
+        op = rd._abi.OP_DISCRETE_ERROR_JACOBIAN if error_state else rd._abi.OP_DISCRETE_JACOBIAN
+        self.plans = [rd._abi.Plan(h, op, Q.code, Z, self.dt, J=J) for Z, J in zip(self.Zs, self.Js)]
 
-    # The two model segments are independent: one stream each, so the tail of one kernel overlaps the head of the other and, at
-    # 4-8 GPUs, the small launch-bound kernels overlap (measured at 1 GPU: two streams 122.6 us, one stream 131.9 us per sweep).
-    nstreams = args.sweep_streams or 2
-    streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    streams = [streams[i % nstreams] for i in range(len(work))]
-    main = torch.cuda.current_stream()
+    def step(self, i):
+        self.plans[i % self.nsets].launch()
+        self.B.launches += 1
 
-    def step(i):
-        for (h, qc, Zs, dt, Js, _, _), st in zip(work, streams):
-            with torch.cuda.stream(st):
-                h.discrete_jacobian(qc, Zs[i % len(Zs)], dt, J=Js[i % len(Zs)])
+    def measure(self, steps, warmup, peak):
+        ms, window = self.B.timed(self.step, steps, warmup)
+        per_rank = self.B.gather(ms / steps)
+        ms_step = max(per_rank)
+        achieved = self.N * self.alg_bytes / (ms_step * 1e-3) / 1e9
+        return {"ms_per_step": ms_step, "per_rank_ms_per_step": per_rank, "value": self.B.world * self.N / (ms_step * 1e-3),
+                "achieved_GBs": achieved, "frac": achieved / peak, "algorithmic_bytes_per_eval": self.alg_bytes,
+                "knot_points_per_gpu": self.N, "buffer_sets": self.nsets}, window
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    for st in streams:
-        st.wait_stream(main)
-    for i in range(args.steps):
-        step(i)
-    for st in streams:
-        main.wait_stream(st)
-    e1.record(main)
-    barrier()
-    ms = sh.barrier_max_ms(e0.elapsed_time(e1), device=torch.device("cuda", local))
-    if rank == 0:
-        total = ntraj * K
-        byts = sum(c * b for *_, c, b in work) * world        # every rank holds an equal share of both segments
-        line = {"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-                "config": {"workload": SWEEP_DESC, "l2": "6 rotating buffer sets per segment", "parallelism": f"trajectory-block sharded x{world}",
-                           "streams": nstreams},
-                "roofline": {"bound": "hbm", "achieved": byts / (ms * 1e-3 / args.steps) / 1e9 / world, "peak": 6551.4, "unit": "GB/s per GPU",
-                             "frac": byts / (ms * 1e-3 / args.steps) / 1e9 / world / 6551.4, "traffic": None},
-                "gpu_launches": 2 * args.steps}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+class SweepWorkload:
+    """BASELINE configs[4]: 4096 trajectories x 256 knot points, first half Cartpole fp64, second half Quadrotor fp32, per-trajectory
+    dt; STRONG scaling — every rank takes its contiguous share of both segments (sharding.partition_segments).  The two segments are
+    independent: each runs on its own stream, joined at the end of the timed region."""
+
+    def __init__(self, B):
+        rd, torch = B.rd, B.torch
+        from rdb200 import sharding as sh
+        self.B = B
+        self.ntraj, self.K = 4096, 256
+        segs = sh.partition_segments({"cartpole": self.ntraj // 2, "quadrotor": self.ntraj // 2}, B.world, B.rank)
+        self.work, self.bytes_local, self.knots_local = [], 0, 0
+        for name, (lo, hi) in segs.items():
+            _, n, m, _, dtn, _ = WORKLOADS[name]
+            mk, Q = gpu_model(name, rd)
+            model = mk()
+            cnt = (hi - lo) * self.K
+            if cnt == 0:
+                continue
+            per = np.dtype(dtn).itemsize * ((n + m) + n * (n + m))
+            nsets = max(2, int(np.ceil(600e6 / (cnt * per))) + 1)
+            nsets = min(nsets, 48)
+            Zs = [torch.from_numpy(make_inputs(n, m, cnt, dtn, 17 * B.rank + i)).cuda() for i in range(nsets)]
+            dt = torch.from_numpy(np.repeat(0.01 * (1 + np.arange(lo, hi) % 4), self.K)).cuda()
+            Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
+            plans = [rd._abi.Plan(model._h, rd._abi.OP_DISCRETE_JACOBIAN, Q.code, Z, dt, J=J) for Z, J in zip(Zs, Js)]
+            self.work.append((model, plans, torch.cuda.Stream()))
+            self.bytes_local += cnt * per
+            self.knots_local += cnt
+        self.streams = [w[2] for w in self.work]
+
+    def step(self, i):
+        for _, plans, st in self.work:
+            plans[i % len(plans)].launch(st.cuda_stream)
+            self.B.launches += 1
+
+    def measure(self, steps, warmup, peak):
+        ms, _ = self.B.timed(self.step, steps, warmup, streams=self.streams)
+        per_rank = self.B.gather(ms / steps)
+        ms_step = max(per_rank)
+        tot_bytes = sum(self.B.gather(self.bytes_local))
+        achieved = tot_bytes / self.B.world / (ms_step * 1e-3) / 1e9
+        return {"workload": SWEEP_DESC, "scaling": "strong", "ms_per_step": ms_step, "per_rank_ms_per_step": per_rank,
+                "value": self.ntraj * self.K / (ms_step * 1e-3), "achieved_GBs_per_gpu": achieved, "frac": achieved / peak,
+                "launches_per_step_per_rank": len(self.work), "streams": len(self.streams)}
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device visible — the product path has no CPU fallback")
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import rdb200 as rd
-
+    B = Bench()
+    torch, rd = B.torch, B.rd
+    peak, peak_src = hbm_peak()
     name = args.workload
-    desc, n, m, N, dtn, dt = WORKLOADS[name]
-    mk, Q = gpu_model(name, rd)
-    model = mk()
-    h = model._h
-    es = np.dtype(dtn).itemsize
-    alg_bytes = es * ((n + m) + n * (n + m))                     # SURVEY.md §8d: read z, write J
-    tdt = torch.float64 if dtn == "float64" else torch.float32
-    # rotate over enough buffer sets that the bytes touched between two uses of a set exceed the 126 MB L2 several times
-    nsets = max(2, int(np.ceil(600e6 / (N * alg_bytes))) + 1)
-    Zs = [torch.from_numpy(make_inputs(n, m, N, dtn, 1000 * rank + i)).cuda() for i in range(nsets)]
-    Js = [torch.empty((N, n + m, n), dtype=tdt, device="cuda") for _ in range(nsets)]
-    qc = Q.code
+    if name == "sweep":
+        sw = SweepWorkload(B)
+        res = sw.measure(args.steps, args.warmup, peak)
+        if B.rank == 0:
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": B.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                    "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+f32",
+                    "data": "synthetic", "config": {"workload": SWEEP_DESC, "parallelism": f"trajectory-block sharded x{B.world}"},
+                    "roofline": {"bound": "hbm", "achieved": res["achieved_GBs_per_gpu"], "peak": peak, "unit": "GB/s per GPU", "frac": res["frac"], "traffic": None},
+                    "per_rank_ms_per_step": res["per_rank_ms_per_step"], "gpu_launches": B.launches}
+            print(json.dumps(line), flush=True)
+        B.close()
+        return 0
 
-    def step(i):
-        h.discrete_jacobian(qc, Zs[i % nsets], dt, J=Js[i % nsets])
+    W = KnotWorkload(B, name)
+    h, qc, N, n, m, dtn, dt, es = W.model._h, W.Q.code, W.N, W.n, W.m, W.dtn, W.dt, W.es
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(physical_gpu_index(local))
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
+    # ---- clocks: sample from the start of a pre-roll of the identical kernel to the end of a post-roll ------------------------------
+    sampler = ClockSampler(physical_gpu_index(B.local))
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # keep the identical kernel running a little longer (untimed) if the timed region was too short for the clock sampler
-    t_extra = time.perf_counter()
-    while sampler.ok and len(sampler.samples) < 20 and time.perf_counter() - t_extra < 2.0:
-        for i in range(50):
-            step(i)
+    t_load0 = time.perf_counter()
+    while time.perf_counter() - t_load0 < 0.08:           # pre-roll >= 80 ms, untimed
+        for i in range(32):
+            W.step(i)
         torch.cuda.synchronize()
+    launches_before = B.launches
+    main_res, timed_window = W.measure(args.steps, args.warmup, peak)
+    timed_launches = B.launches - launches_before - max(args.warmup, 3)
+    t_post = time.perf_counter()
+    while time.perf_counter() - t_post < 0.03:            # post-roll
+        for i in range(32):
+            W.step(i)
+        torch.cuda.synchronize()
+    t_load1 = time.perf_counter()
     sampler.stop_flag = True
-    from rdb200 import sharding as sh
-    ms_max = sh.barrier_max_ms(ms, device=torch.device("cuda", local))
-    value = world * N * args.steps / (ms_max * 1e-3)
+    clocks = sampler.summary((t_load0, t_load1), timed_window)
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region ----------
+    from rdb200 import sharding as sh
     Zp = rd.PinnedArray((N, n + m), dtn); Jp = rd.PinnedArray((N, n + m, n), dtn)
-    Zp.array[...] = make_inputs(n, m, N, dtn, 7 + rank)
+    Zp.array[...] = make_inputs(n, m, N, dtn, 7 + B.rank)
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
         h.discrete_jacobian(qc, Zp.array, dt, J=Jp.array)
-    barrier()
+    B.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         h.discrete_jacobian(qc, Zp.array, dt, J=Jp.array)
         _ = float(Jp.array[-1, 0, 0])                            # read a result on the host
     t_e2e = time.perf_counter() - t0
-    t_e2e = sh.barrier_max_ms(t_e2e * 1e3, device=torch.device("cuda", local)) * 1e-3
-    e2e_val = world * N * e2e_steps / t_e2e
+    e2e_per_rank = B.gather(t_e2e * 1e3 / e2e_steps)
+    e2e_val = B.world * N / (max(e2e_per_rank) * 1e-3)
+    e2e_launches = e2e_steps * int(np.ceil(N / 65536))           # the host pipeline evaluates 65536-knot chunks
     # light parity guard on what was just timed (device vs host path agree bit-for-bit on the same inputs)
     Jd = h.discrete_jacobian(qc, torch.from_numpy(Zp.array).cuda(), dt)
     assert np.array_equal(Jd.cpu().numpy(), Jp.array), "device and host paths disagree"
+    del Zp, Jp, Jd
 
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        launch_s = ms_max * 1e-3 / args.steps
-        achieved = N * alg_bytes / launch_s / 1e9
-        traffic = None
+    # ---- the other BASELINE configurations, same process, same method --------------------------------------------------------------
+    extra = {}
+    if not args.no_extra and name == "cartpole":
+        del W.plans, W.Zs, W.Js
+        torch.cuda.empty_cache()
+        for key, wl, err in (("quadrotor_c3", "quadrotor", False), ("quadrotor_c3_error_state", "quadrotor", True), ("satellite_c4", "satellite", False)):
+            X = KnotWorkload(B, wl, error_state=err, seed0=50)
+            r, _ = X.measure(args.steps, args.warmup, peak)
+            r["workload"] = WORKLOADS[wl][0] + (" — error-state form G(x+)' [A B] blkdiag(G(x), I), 12 x 16 per knot" if err else "")
+            r["scaling"] = "weak"
+            extra[key] = r
+            del X
+            torch.cuda.empty_cache()
+        sw = SweepWorkload(B)
+        extra["sweep_c5"] = sw.measure(args.steps, args.warmup, peak)
+        del sw
+        torch.cuda.empty_cache()
+
+    if B.rank == 0:
+        traffic, tsrc = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(name)
+            tj = json.load(open(tp))
+            traffic, tsrc = tj.get(name), tj.get("_source", "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (not measured in this run)")
         cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": "skipped (N>1)"}
-        if world == 1 and not args.no_cpu_baseline:
+        if B.world == 1 and not args.no_cpu_baseline:
             r, sample, _ = cpu_rate(name, args.cpu_budget, host_cores())
             cpu = {"value": r, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": B.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if dtn == "float64" else "f32", "data": "synthetic",
-            "config": {"workload": desc, "knot_points_per_gpu": N, "layout": "reference AoS (Z (n+m,N), J (n,n+m,N) column-major)",
-                       "l2": f"inputs larger than L2: {nsets} rotating buffer sets x {N * alg_bytes / 1e6:.0f} MB", "parallelism": f"knot-sharded x{world}"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "rdb::knot_kernel", "algorithmic_bytes_per_eval": alg_bytes, "peak_source": peak_src},
+            "config": {"workload": W.desc, "knot_points_per_gpu": N, "layout": "reference AoS (Z (n+m,N), J (n,n+m,N) column-major)",
+                       "l2": f"inputs larger than L2: {main_res['buffer_sets']} rotating buffer sets x {N * W.alg_bytes / 1e6:.0f} MB",
+                       "parallelism": f"knot-sharded x{B.world}",
+                       "launch": "one rdb_plan_launch per step; ~2 ms device-side launch gate before the first event (all K launches queued "
+                                 "before the timed region starts)"},
+            "per_rank_ms_per_step": main_res["per_rank_ms_per_step"],
+            "roofline": {"bound": "hbm", "achieved": main_res["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": main_res["frac"],
+                         "traffic": traffic, "traffic_source": tsrc, "kernel": "rdb::knot_kernel", "algorithmic_bytes_per_eval": W.alg_bytes,
+                         "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": N * (n + m) * es, "d2h_bytes_per_step": N * n * (n + m) * es,
-                    "steps": e2e_steps, "path": "rdb_discrete_jacobian with pinned host pointers (3-stream chunked pipeline)"},
-            "gpu_launches": args.steps,
-            "clocks": sampler.summary(),
+                    "steps": e2e_steps, "per_rank_ms_per_step": e2e_per_rank, "gpu_launches": e2e_launches,
+                    "path": "rdb_discrete_jacobian with pinned host pointers (3-stream chunked pipeline)"},
+            "gpu_launches": timed_launches,
+            "gpu_launches_total": B.launches + e2e_launches,
+            "clocks": clocks,
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    B.close()
     return 0
 
 
@@ -370,7 +500,7 @@ def main():
     ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS) + ["sweep"])
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU time for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-streams", type=int, default=0, help="sweep workload: streams for the two model segments (0 = auto)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations (extra)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload == "sweep":
@@ -379,12 +509,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when called directly with --gpus N
-        import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    if args.workload == "sweep":
-        return run_sweep(args)
     return run_ours(args)
 
 

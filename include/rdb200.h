@@ -19,8 +19,15 @@
  *     unit-stride stream of N values; J has n*(n+m) such streams (entry i + n*j), x+ has n.  Both layouts run at the same
  *     speed when N * sizeof(T) is a multiple of 16 (the kernel reads and writes component-major arrays through 2-D TMA
  *     tensor maps); other N are transposed around the knot-major kernel.
- *   - t may be NULL (all shipped models are time-invariant, src/dynamics.jl:83); dt may be NULL (then dt0 is
- *     used for every knot point).  Knot points with dt == 0 (terminal, src/knotpoint.jl:57-67) yield J = [I 0].
+ *   - t (KnotPoint.t per knot point) may be NULL (= 0).  It reaches dynamics(model, x, u, t) (src/dynamics.jl:81-83) of models that
+ *     can depend on it — user models (rdb_model_create_custom*), whose body may read `t` — with the reference's stage times
+ *     t, t+h/2, t+h/2, t+h for RK4 (src/integration.jl:281-284), t, t+h/2, t+h for RK3 (:131-133), t, t+h/2 for the midpoint rules;
+ *     it is never differentiated.  The shipped model families are time-invariant (src/dynamics.jl:83): for them t is ignored and
+ *     not even transferred.  dt may be NULL (then dt0 is used for every knot point).  Knot points with dt == 0 (terminal,
+ *     src/knotpoint.jl:57-67) yield J = [I 0].
+ *   - a call changes neither the caller's current CUDA device nor anything else outside its arguments; device pointers must
+ *     belong to the context's GPU (RDB_ERR_POINTER_MIX otherwise).  Inputs may be device-resident while outputs are HOST arrays
+ *     (RDB_AOS only): the kernel reads Z in place and only J / x+ cross PCIe.
  */
 #ifndef RDB200_H
 #define RDB200_H
@@ -34,6 +41,8 @@ extern "C" {
 
 typedef struct rdb_context rdb_context; /* one per (process, GPU): device id, SM count, staging pipeline */
 typedef struct rdb_model rdb_model;     /* immutable model description; replaces an AbstractModel instance */
+typedef struct rdb_trajectory rdb_trajectory; /* persistent device mirror of (a batch of) SampledTrajectory, src/trajectories.jl:40-50 */
+typedef struct rdb_plan rdb_plan;       /* a validated knot operation on device pointers: launching it is one kernel launch */
 
 typedef enum { RDB_F32 = 0, RDB_F64 = 1 } rdb_dtype;
 typedef enum { RDB_AOS = 0, RDB_SOA = 1 } rdb_layout;
@@ -48,6 +57,10 @@ typedef enum { RDB_CARTPOLE = 0, RDB_QUADROTOR = 1, RDB_BODY = 2, RDB_DOUBLE_INT
 /* rotation parameterisation R of RigidBody{R} (src/liestate.jl:42-46) and velocity_frame (src/rigidbody.jl:258) */
 typedef enum { RDB_ROT_NONE = 0, RDB_ROT_QUAT = 1, RDB_ROT_MRP = 2, RDB_ROT_RP = 3 } rdb_rot;
 typedef enum { RDB_FRAME_WORLD = 0, RDB_FRAME_BODY = 1 } rdb_frame;
+
+/* operations a plan can hold (the batch entry points below, in order) */
+typedef enum { RDB_OP_DYNAMICS = 0, RDB_OP_DISCRETE_DYNAMICS = 1, RDB_OP_JACOBIAN = 2, RDB_OP_DISCRETE_JACOBIAN = 3,
+               RDB_OP_DISCRETE_ERROR_JACOBIAN = 4 } rdb_op;
 
 typedef enum {
     RDB_OK = 0,
@@ -76,7 +89,8 @@ int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const doubl
 /* User-defined model: any `dynamics(model, x, u)` (src/dynamics.jl:81-83), differentiated exactly by forward mode like the
  * reference's `@autodiff`-generated ForwardAD methods (src/jacobian_gen.jl:485-529).  f_body is the BODY of
  *     template <class X, class U> auto f(const X& x, const U& u) const
- * in CUDA C++ against csrc/sdual.cuh: read inputs with get<i>(x), get<j>(u), parameters with p[k], write constants as T(0.5),
+ * in CUDA C++ against csrc/sdual.cuh: read inputs with get<i>(x), get<j>(u), the time with `t` (a plain scalar: dynamics(model, x,
+ * u, t), src/dynamics.jl:81-83), parameters with p[k], write constants as T(0.5),
  * use sin_/cos_/sincos_/exp_/sqrt_/relu_ and + - * /, and `return vec(xdot_0, ..., xdot_{n-1});`.  EuclideanState only
  * (errstate maps are identities), n + m <= 32.  Compiled with NVRTC for sm_100a at creation (syntax) and on first use per
  * (operation, integrator, dtype); works with every batch entry point below except rdb_discrete_error_jacobian's G-seeding
@@ -134,6 +148,52 @@ int rdb_state_diff(const rdb_model* model, int dtype, int64_t N, const void* X, 
  * x0 (n, ntraj); U (m, K-1, ntraj); t, dt (K, ntraj) or NULL; X (n, K, ntraj) out.  Parallel over trajectories. */
 int rdb_rollout(const rdb_model* model, int integrator, int dtype, int64_t ntraj, int K, const void* x0, const void* U,
                 const double* t, const double* dt, double dt0, void* X, void* stream);
+
+/* ---- pre-validated launches --------------------------------------------------------------------------------------------------
+ * A solver evaluates the SAME batch (same buffers, 10^2..10^3 knot points) every iteration; there the per-call host work (pointer
+ * classification, argument checks, tensor-map encoding) costs more than the kernel.  A plan does that work once:
+ * rdb_plan_create validates one of the batch operations above on DEVICE pointers (op = rdb_op; J / out as for that entry point;
+ * integrator ignored by the continuous ops), rdb_plan_launch enqueues it on `stream` — one kernel launch, nothing else — any
+ * number of times (it reads whatever the buffers hold at execution time), also under CUDA-graph capture.  The reference has no
+ * counterpart: its per-knot calls are plain Julia method calls (src/discretized_dynamics.jl:129-136). */
+int rdb_plan_create(const rdb_model* model, int op, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
+                    const double* dt, double dt0, void* J, void* out, rdb_plan** plan);
+int rdb_plan_launch(const rdb_plan* plan, void* stream);
+int rdb_plan_destroy(rdb_plan* plan);
+
+/* ---- persistent device trajectory -------------------------------------------------------------------------------------------------
+ * The device mirror of SampledTrajectory (src/trajectories.jl:40-50) for `ntraj` independent trajectories of K knot points each,
+ * stored knot-major across the batch: row k * ntraj + j holds z = [x;u] of knot k of trajectory j; times and steps (double) are
+ * stored the same way, the terminal knot has dt = 0 and zero controls (src/trajectories.jl:82-83,110; src/knotpoint.jl:57-67).
+ * For ntraj == 1 — one solve of Altro / TrajectoryOptimization — this is exactly the gathered Matrix{T}(n+m, K) of the host's
+ * Vector{KnotPoint} (an array of pointers to mutable structs, src/knotpoint.jl:213-217), uploaded once instead of every call.
+ * All setters / getters take HOST or DEVICE pointers of dense arrays in the same knot-major order:
+ *   X (n, ntraj, K) as a Julia array == rows k * ntraj + j of n values;  U (m, ntraj, K-1 or K);  dt (ntraj, K) doubles. */
+int rdb_trajectory_create(const rdb_model* model, int dtype, int64_t ntraj, int K, rdb_trajectory** traj);
+int rdb_trajectory_destroy(rdb_trajectory* traj);
+int rdb_trajectory_dims(const rdb_trajectory* traj, int64_t* ntraj, int* K, int* n, int* m, int* dtype);
+/* device pointers of the mirror itself (zero-copy: wrap them as CuArrays / tensors): Z (n+m, ntraj, K), t and dt (ntraj, K) */
+int rdb_trajectory_data(const rdb_trajectory* traj, void** Z, double** t, double** dt);
+/* setstates!(Z, X) / setcontrols!(Z, U) / setinitialstate / settimes   src/trajectories.jl:215-250 */
+int rdb_trajectory_set_states(rdb_trajectory* traj, const void* X, void* stream);
+int rdb_trajectory_set_initial_state(rdb_trajectory* traj, const void* x0 /* (n, ntraj) */, void* stream);
+int rdb_trajectory_set_controls(rdb_trajectory* traj, const void* U, int knots /* K-1 (terminal control := 0) or K */, void* stream);
+/* steps dt (ntraj, K) or NULL (every step dt0); the terminal step is forced to 0 and t[k] = t0 + sum_{i<k} dt[i] */
+int rdb_trajectory_set_timesteps(rdb_trajectory* traj, const double* dt, double dt0, double t0, void* stream);
+/* states(Z) / controls(Z)   src/trajectories.jl:181-199 */
+int rdb_trajectory_get_states(rdb_trajectory* traj, void* X, void* stream);
+int rdb_trajectory_get_controls(rdb_trajectory* traj, void* U, void* stream);
+/* rollout!(sig, dmodel, Z, x0): x_{k+1} = discrete_dynamics(dmodel, Z[k]) from the state of knot 0 and the stored controls, times
+ * and steps   src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235 */
+int rdb_trajectory_rollout(rdb_trajectory* traj, int integrator, void* stream);
+/* jacobian!(sig, diff, dmodel, J[k], y[k], Z[k]) for every knot of every trajectory (src/discretized_dynamics.jl:129-136):
+ * J (n, n+m, ntraj, K) — or, error_state != 0, Jbar (nerr, nerr+m, ntraj, K) as rdb_discrete_error_jacobian — host or device;
+ * xn (n, ntraj, K) or NULL.  Terminal knots (dt = 0) give [I 0]. */
+int rdb_trajectory_linearize(rdb_trajectory* traj, int integrator, int error_state, void* J, void* xn, void* stream);
+/* Forward pass + linearisation in one call, pipelined on two internal streams: the rollout — sequential in k —
+ * runs in `chunks` (0 = default 8) chunks of knots; the Jacobians of a finished chunk (a contiguous row range of the knot-major
+ * batch) are evaluated at full-GPU rate while the next chunk is rolled out.  Joined back into `stream`; graph-capturable. */
+int rdb_trajectory_rollout_linearize(rdb_trajectory* traj, int integrator, int error_state, int chunks, void* J, void* stream);
 
 #ifdef __cplusplus
 }

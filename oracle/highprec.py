@@ -83,7 +83,7 @@ def quadrotor_f(mass="0.5", J=("0.0023", "0.0023", "0.004"), gz="-9.81", L="0.17
 
     def f(x, u):
         q, v, w = x[3:7], x[7:10], x[10:13]
-        F = [kf * ui if ui > 0 else mp.mpf(0) for ui in u]                      # max(0, kf w_i), test/quadrotor.jl:67-70
+        F = [mp.mpf(0) if ui < 0 else kf * ui for ui in u]                      # max(0, kf w_i), test/quadrotor.jl:67-70
         Fw = _rotate(q, [mp.mpf(0), mp.mpf(0), sum(F)])
         Fw[2] += mass * gz
         tau = [L * (F[1] - F[3]), L * (F[2] - F[0]), km * (u[0] - u[1] + u[2] - u[3])]   # moments use the unclamped inputs

@@ -48,7 +48,7 @@ def kinematics(rot, p, w):
 
 
 def relu(a):
-    return a if np.real(a) > 0 else 0 * a
+    return 0 * a if np.real(a) < 0 else a          # Base.max(0, a) = ifelse(a < 0, 0, a): the tie a == 0 returns a (partials kept)
 
 
 class Cartpole:

@@ -58,14 +58,16 @@ template <int NP> inline Dual<NP> operator/(double a, const Dual<NP>& b) { retur
 inline double sin_(double a) { return std::sin(a); }
 inline double cos_(double a) { return std::cos(a); }
 inline double sqrt_(double a) { return std::sqrt(a); }
-inline double relu_(double a) { return a > 0 ? a : 0.0; }           // max(0, a)
+// max(0, a): under ForwardDiff the 0 is promoted and Base.max(x, y) = ifelse(isless(y, x), x, y) returns y = a unless a < 0, so at the
+// tie a == 0 the partials of a are KEPT (DiffRules' max rule agrees: d/dy = x > y ? 0 : 1)   (reference: test/quadrotor.jl:67-70)
+inline double relu_(double a) { return a < 0 ? 0.0 : a; }
 inline double val(double a) { return a; }
 template <int NP> inline Dual<NP> sin_(const Dual<NP>& a) { Dual<NP> r; r.v = std::sin(a.v); double c = std::cos(a.v); for (int i = 0; i < NP; ++i) r.d[i] = c * a.d[i]; return r; }
 template <int NP> inline Dual<NP> cos_(const Dual<NP>& a) { Dual<NP> r; r.v = std::cos(a.v); double s = -std::sin(a.v); for (int i = 0; i < NP; ++i) r.d[i] = s * a.d[i]; return r; }
 template <int NP> inline Dual<NP> sqrt_(const Dual<NP>& a) { Dual<NP> r; r.v = std::sqrt(a.v); double s = 0.5 / r.v; for (int i = 0; i < NP; ++i) r.d[i] = s * a.d[i]; return r; }
 // ForwardDiff: max(0, Dual) compares values; derivative is 0 when the clamp is active or at exactly 0
 // (test/quadrotor.jl:67-70).
-template <int NP> inline Dual<NP> relu_(const Dual<NP>& a) { return a.v > 0 ? a : Dual<NP>(0.0); }
+template <int NP> inline Dual<NP> relu_(const Dual<NP>& a) { return a.v < 0 ? Dual<NP>(0.0) : a; }
 template <int NP> inline double val(const Dual<NP>& a) { return a.v; }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,7 +33,12 @@ SYMBOLS = (
     "rdb_model_create", "rdb_model_create_custom", "rdb_model_create_custom_rigid", "rdb_custom_check", "rdb_custom_rigid_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
+    "rdb_plan_create", "rdb_plan_launch", "rdb_plan_destroy",
+    "rdb_trajectory_create", "rdb_trajectory_destroy", "rdb_trajectory_dims", "rdb_trajectory_data", "rdb_trajectory_set_states",
+    "rdb_trajectory_set_initial_state", "rdb_trajectory_set_controls", "rdb_trajectory_set_timesteps", "rdb_trajectory_get_states",
+    "rdb_trajectory_get_controls", "rdb_trajectory_rollout", "rdb_trajectory_linearize", "rdb_trajectory_rollout_linearize",
 )
+OP_DYNAMICS, OP_DISCRETE_DYNAMICS, OP_JACOBIAN, OP_DISCRETE_JACOBIAN, OP_DISCRETE_ERROR_JACOBIAN = 0, 1, 2, 3, 4
 
 
 class RDBError(RuntimeError):
@@ -83,6 +88,22 @@ def lib():
         L.rdb_grad_errstate_jacobian.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
         L.rdb_state_diff.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
         L.rdb_rollout.argtypes = [vp, i32, i32, i64, i32, vp, vp, vp, vp, dbl, vp, vp]
+        L.rdb_plan_create.argtypes = [vp, i32, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp, ctypes.POINTER(vp)]
+        L.rdb_plan_launch.argtypes = [vp, vp]
+        L.rdb_plan_destroy.argtypes = [vp]
+        L.rdb_trajectory_create.argtypes = [vp, i32, i64, i32, ctypes.POINTER(vp)]
+        L.rdb_trajectory_destroy.argtypes = [vp]
+        L.rdb_trajectory_dims.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.rdb_trajectory_data.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+        L.rdb_trajectory_set_states.argtypes = [vp, vp, vp]
+        L.rdb_trajectory_set_initial_state.argtypes = [vp, vp, vp]
+        L.rdb_trajectory_set_controls.argtypes = [vp, vp, i32, vp]
+        L.rdb_trajectory_set_timesteps.argtypes = [vp, vp, dbl, dbl, vp]
+        L.rdb_trajectory_get_states.argtypes = [vp, vp, vp]
+        L.rdb_trajectory_get_controls.argtypes = [vp, vp, vp]
+        L.rdb_trajectory_rollout.argtypes = [vp, i32, vp]
+        L.rdb_trajectory_linearize.argtypes = [vp, i32, i32, vp, vp, vp]
+        L.rdb_trajectory_rollout_linearize.argtypes = [vp, i32, i32, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -157,6 +178,28 @@ def empty_like_kind(ref, shape):
         import torch
         return torch.empty(shape, dtype=ref.dtype, device=ref.device)
     return np.empty(shape, dtype=ref.dtype)
+
+
+def check_buffer(name, a, shape, like):
+    """Caller-supplied output / auxiliary arrays are handed to the C ABI as bare pointers: the library reads or writes exactly
+    prod(shape) * sizeof(dtype) bytes there, so anything that does not match is refused HERE (ValueError / TypeError) instead of
+    becoming an out-of-bounds access in host or device memory."""
+    if a is None:
+        return None
+    if _is_torch(a) != _is_torch(like):
+        raise RDBError(ERR_POINTER_MIX, f"{name}: host (numpy) and device (torch) arrays mixed in one call")
+    if _is_torch(a):
+        if a.device != like.device:
+            raise ValueError(f"{name} lives on {a.device}, the inputs on {like.device}")
+        if not a.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    elif not isinstance(a, np.ndarray) or not a.flags.c_contiguous:
+        raise ValueError(f"{name} must be a C-contiguous numpy array")
+    if a.dtype != like.dtype:
+        raise TypeError(f"{name} has dtype {a.dtype}, the inputs {like.dtype}: the C ABI computes and stores in ONE type per call")
+    if tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
 
 
 def as_f64(a, like):
@@ -236,6 +279,7 @@ class ModelHandle:
         self.ctx = context(device)
         self.kind, self.rot, self.frame = int(kind), int(rot), int(frame)
         self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self.time_varying = custom is not None          # user models may define dynamics(model, x, u, t)
         self._h = ctypes.c_void_p()
         pp = self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         if custom is not None and len(custom) == 3:    # (n, m, body of f): NVRTC-compiled user model
@@ -282,87 +326,317 @@ class ModelHandle:
         return (N, self.n) if layout == AOS else (self.n, N)
 
     @staticmethod
-    def _dt(dt, Z):
+    def _dt(dt, Z, count=None):
+        """scalar -> (None, dt0); vector -> (Float64 array where Z lives, 0.0), which must hold one step per knot point."""
         if dt is None:
             raise ValueError("dt is required")
         if np.ndim(dt) == 0:
             return None, float(dt)
-        return as_f64(dt, Z), 0.0
+        v = as_f64(dt, Z)
+        if count is not None and int(np.prod(tuple(v.shape))) != int(count):
+            raise ValueError(f"dt must be a scalar or hold {count} steps (one per knot point), got shape {tuple(v.shape)}")
+        return v, 0.0
+
+    def _t(self, t, Z, count):
+        """KnotPoint.t per knot point (Float64).  Only time-varying (user) models read it; for the shipped time-invariant families the
+        vector is not even transferred (reference: dynamics(model, x, u, t) ignores t unless the model defines it, src/dynamics.jl:81-83)."""
+        if t is None or not self.time_varying:
+            return None
+        v = as_f64(np.full(count, float(t)) if np.ndim(t) == 0 else t, Z)
+        if int(np.prod(tuple(v.shape))) != int(count):
+            raise ValueError(f"t must hold {count} times (one per knot point), got shape {tuple(v.shape)}")
+        return v
 
     # ---- batch operations -------------------------------------------------------------------------
+    def _zcheck(self, Z):
+        if not (_is_torch(Z) or isinstance(Z, np.ndarray)):
+            raise TypeError("Z must be a numpy array or a torch tensor")
+        dtype_code(Z)
+
     def dynamics(self, Z, t=None, out=None, layout=AOS):
+        self._zcheck(Z)
         N = self._count(Z, layout)
-        out = empty_like_kind(Z, self._oshape(N, layout)) if out is None else out
-        pz, _ = ptr(Z); po, _ = ptr(out)
-        check(lib().rdb_dynamics(self._h, dtype_code(Z), layout, N, pz, None, po, current_stream(Z)), "rdb_dynamics")
+        out = empty_like_kind(Z, self._oshape(N, layout)) if out is None else check_buffer("out", out, self._oshape(N, layout), Z)
+        tv = self._t(t, Z, N)
+        pz, _ = ptr(Z); po, _ = ptr(out); pt, _ = ptr(tv)
+        check(lib().rdb_dynamics(self._h, dtype_code(Z), layout, N, pz, pt, po, current_stream(Z)), "rdb_dynamics")
         return out
 
     def discrete_dynamics(self, Q, Z, dt, t=None, out=None, layout=AOS):
+        self._zcheck(Z)
         N = self._count(Z, layout)
-        out = empty_like_kind(Z, self._oshape(N, layout)) if out is None else out
-        dtv, dt0 = self._dt(dt, Z)
-        pz, _ = ptr(Z); po, _ = ptr(out); pd, _ = ptr(dtv)
-        check(lib().rdb_discrete_dynamics(self._h, int(Q), dtype_code(Z), layout, N, pz, None, pd, dt0, po,
+        out = empty_like_kind(Z, self._oshape(N, layout)) if out is None else check_buffer("out", out, self._oshape(N, layout), Z)
+        dtv, dt0 = self._dt(dt, Z, N)
+        tv = self._t(t, Z, N)
+        pz, _ = ptr(Z); po, _ = ptr(out); pd, _ = ptr(dtv); pt, _ = ptr(tv)
+        check(lib().rdb_discrete_dynamics(self._h, int(Q), dtype_code(Z), layout, N, pz, pt, pd, dt0, po,
                                           current_stream(Z)), "rdb_discrete_dynamics")
         return out
 
     def jacobian(self, Z, t=None, J=None, xdot=None, layout=AOS):
+        self._zcheck(Z)
         N = self._count(Z, layout)
-        J = empty_like_kind(Z, self._jshape(N, layout)) if J is None else J
-        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xdot)
-        check(lib().rdb_jacobian(self._h, dtype_code(Z), layout, N, pz, None, pj, po, current_stream(Z)), "rdb_jacobian")
+        J = empty_like_kind(Z, self._jshape(N, layout)) if J is None else check_buffer("J", J, self._jshape(N, layout), Z)
+        check_buffer("xdot", xdot, self._oshape(N, layout), Z)
+        tv = self._t(t, Z, N)
+        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xdot); pt, _ = ptr(tv)
+        check(lib().rdb_jacobian(self._h, dtype_code(Z), layout, N, pz, pt, pj, po, current_stream(Z)), "rdb_jacobian")
         return J
 
     def discrete_jacobian(self, Q, Z, dt, t=None, J=None, xn=None, layout=AOS):
+        self._zcheck(Z)
         N = self._count(Z, layout)
-        J = empty_like_kind(Z, self._jshape(N, layout)) if J is None else J
-        dtv, dt0 = self._dt(dt, Z)
-        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv)
-        check(lib().rdb_discrete_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, None, pd, dt0, pj, po,
+        J = empty_like_kind(Z, self._jshape(N, layout)) if J is None else check_buffer("J", J, self._jshape(N, layout), Z)
+        check_buffer("xn", xn, self._oshape(N, layout), Z)
+        dtv, dt0 = self._dt(dt, Z, N)
+        tv = self._t(t, Z, N)
+        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv); pt, _ = ptr(tv)
+        check(lib().rdb_discrete_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, pt, pd, dt0, pj, po,
                                           current_stream(Z)), "rdb_discrete_jacobian")
         return J
 
     def discrete_error_jacobian(self, Q, Z, dt, t=None, J=None, xn=None, layout=AOS):
         """Jbar = G(x+)' [A B] blkdiag(G(x), I): AOS (N, nerr+m, nerr) C-order, i.e. per knot a column-major nerr x (nerr+m)."""
+        self._zcheck(Z)
         N = self._count(Z, layout)
         nc = self.nerr + self.m
-        J = empty_like_kind(Z, (N, nc, self.nerr) if layout == AOS else (self.nerr * nc, N)) if J is None else J
-        dtv, dt0 = self._dt(dt, Z)
-        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv)
-        check(lib().rdb_discrete_error_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, None, pd, dt0, pj, po,
+        jshape = (N, nc, self.nerr) if layout == AOS else (self.nerr * nc, N)
+        J = empty_like_kind(Z, jshape) if J is None else check_buffer("Jbar", J, jshape, Z)
+        check_buffer("xn", xn, self._oshape(N, layout), Z)
+        dtv, dt0 = self._dt(dt, Z, N)
+        tv = self._t(t, Z, N)
+        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(xn); pd, _ = ptr(dtv); pt, _ = ptr(tv)
+        check(lib().rdb_discrete_error_jacobian(self._h, int(Q), dtype_code(Z), layout, N, pz, pt, pd, dt0, pj, po,
                                                 current_stream(Z)), "rdb_discrete_error_jacobian")
         return J
 
+    def _xcheck(self, name, X):
+        if X.ndim != 2 or X.shape[1] < self.n:
+            raise ValueError(f"{name} must be (N, ld) with ld >= {self.n}, got {tuple(X.shape)}")
+        dtype_code(X)
+        return int(X.shape[0]), int(X.shape[1])
+
     def errstate_jacobian(self, X, G=None):
         """X (N, ld) with ld >= n (pass Z itself to read the states in place).  G (N, nerr, n) C-order."""
-        N, ld = int(X.shape[0]), int(X.shape[1])
-        G = empty_like_kind(X, (N, self.nerr, self.n)) if G is None else G
+        N, ld = self._xcheck("X", X)
+        G = empty_like_kind(X, (N, self.nerr, self.n)) if G is None else check_buffer("G", G, (N, self.nerr, self.n), X)
         px, _ = ptr(X); pg, _ = ptr(G)
         check(lib().rdb_errstate_jacobian(self._h, dtype_code(X), N, px, ld, pg, current_stream(X)), "rdb_errstate_jacobian")
         return G
 
     def grad_errstate_jacobian(self, X, Xbar, H=None):
-        N = int(X.shape[0])
-        H = empty_like_kind(X, (N, self.nerr, self.nerr)) if H is None else H
+        N, ld = self._xcheck("X", X)
+        Nb, ldb = self._xcheck("Xbar", Xbar)
+        check_buffer("Xbar", Xbar, (N, ldb), X)
+        H = empty_like_kind(X, (N, self.nerr, self.nerr)) if H is None else check_buffer("H", H, (N, self.nerr, self.nerr), X)
         px, _ = ptr(X); pb, _ = ptr(Xbar); ph, _ = ptr(H)
-        check(lib().rdb_grad_errstate_jacobian(self._h, dtype_code(X), N, px, int(X.shape[1]), pb, int(Xbar.shape[1]), ph,
+        check(lib().rdb_grad_errstate_jacobian(self._h, dtype_code(X), N, px, ld, pb, ldb, ph,
                                                current_stream(X)), "rdb_grad_errstate_jacobian")
         return H
 
     def state_diff(self, X, X0, dX=None):
-        N = int(X.shape[0])
-        dX = empty_like_kind(X, (N, self.nerr)) if dX is None else dX
+        N, ld = self._xcheck("X", X)
+        _, ld0 = self._xcheck("X0", X0)
+        check_buffer("X0", X0, (N, ld0), X)
+        dX = empty_like_kind(X, (N, self.nerr)) if dX is None else check_buffer("dX", dX, (N, self.nerr), X)
         px, _ = ptr(X); p0, _ = ptr(X0); pd, _ = ptr(dX)
-        check(lib().rdb_state_diff(self._h, dtype_code(X), N, px, int(X.shape[1]), p0, int(X0.shape[1]), pd,
+        check(lib().rdb_state_diff(self._h, dtype_code(X), N, px, ld, p0, ld0, pd,
                                    current_stream(X)), "rdb_state_diff")
         return dX
 
-    def rollout(self, Q, x0, U, dt, X=None):
-        """x0 (ntraj, n); U (ntraj, K-1, m); dt scalar or (ntraj, K).  Returns X (ntraj, K, n)."""
-        ntraj, K = int(x0.shape[0]), int(U.shape[1]) + 1
-        X = empty_like_kind(x0, (ntraj, K, self.n)) if X is None else X
-        dtv, dt0 = self._dt(dt, x0)
-        p0, _ = ptr(x0); pu, _ = ptr(U); pd, _ = ptr(dtv); pX, _ = ptr(X)
-        check(lib().rdb_rollout(self._h, int(Q), dtype_code(x0), ntraj, K, p0, pu, None, pd, dt0, pX,
+    def rollout(self, Q, x0, U, dt, X=None, t=None):
+        """x0 (ntraj, n); U (ntraj, K-1, m); dt scalar or (ntraj, K); t None or (ntraj, K).  Returns X (ntraj, K, n)."""
+        dtype_code(x0)
+        if x0.ndim != 2 or x0.shape[1] != self.n:
+            raise ValueError(f"x0 must be (ntraj, {self.n}), got {tuple(x0.shape)}")
+        ntraj = int(x0.shape[0])
+        if U.ndim != 3 or U.shape[0] != ntraj or U.shape[2] != self.m:
+            raise ValueError(f"U must be ({ntraj}, K-1, {self.m}), got {tuple(U.shape)}")
+        K = int(U.shape[1]) + 1
+        check_buffer("U", U, (ntraj, K - 1, self.m), x0)
+        X = empty_like_kind(x0, (ntraj, K, self.n)) if X is None else check_buffer("X", X, (ntraj, K, self.n), x0)
+        dtv, dt0 = self._dt(dt, x0, ntraj * K)
+        tv = self._t(t, x0, ntraj * K)
+        p0, _ = ptr(x0); pu, _ = ptr(U); pd, _ = ptr(dtv); pX, _ = ptr(X); pt, _ = ptr(tv)
+        check(lib().rdb_rollout(self._h, int(Q), dtype_code(x0), ntraj, K, p0, pu, pt, pd, dt0, pX,
                                 current_stream(x0)), "rdb_rollout")
         return X
+
+
+class Plan:
+    """rdb_plan: one validated knot operation on DEVICE tensors; launch() is a single kernel launch on the current stream (or under
+    CUDA-graph capture).  The tensors are kept alive by the plan; it evaluates whatever they hold at execution time."""
+
+    def __init__(self, handle, op, Q, Z, dt, t=None, J=None, out=None, layout=AOS):
+        if not (_is_torch(Z) and Z.is_cuda):
+            raise RDBError(ERR_POINTER_MIX, "a plan needs device tensors")
+        handle._zcheck(Z)
+        N = handle._count(Z, layout)
+        with_j = op in (OP_JACOBIAN, OP_DISCRETE_JACOBIAN, OP_DISCRETE_ERROR_JACOBIAN)
+        if op == OP_DISCRETE_ERROR_JACOBIAN:
+            nc = handle.nerr + handle.m
+            jshape = (N, nc, handle.nerr) if layout == AOS else (handle.nerr * nc, N)
+        else:
+            jshape = handle._jshape(N, layout)
+        if with_j:
+            J = empty_like_kind(Z, jshape) if J is None else check_buffer("J", J, jshape, Z)
+        else:
+            out = empty_like_kind(Z, handle._oshape(N, layout)) if out is None else out
+        check_buffer("out", out, handle._oshape(N, layout), Z)
+        dtv, dt0 = (None, 0.0) if op in (OP_DYNAMICS, OP_JACOBIAN) else handle._dt(dt, Z, N)
+        tv = handle._t(t, Z, N)
+        self.handle, self.Z, self.J, self.out, self._keep = handle, Z, J, out, (dtv, tv)
+        self._p = ctypes.c_void_p()
+        pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(out); pd, _ = ptr(dtv); pt, _ = ptr(tv)
+        check(lib().rdb_plan_create(handle._h, int(op), int(Q), dtype_code(Z), layout, N, pz, pt, pd, dt0, pj, po, ctypes.byref(self._p)),
+              "rdb_plan_create")
+        self._launch = lib().rdb_plan_launch
+        import torch
+        self._stream = torch.cuda.current_stream
+
+    def launch(self, stream=None):
+        rc = self._launch(self._p, self._stream().cuda_stream if stream is None else stream)
+        if rc:
+            check(rc, "rdb_plan_launch")
+        return self.J if self.J is not None else self.out
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib().rdb_plan_destroy(self._p)
+                self._p = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class Trajectory:
+    """rdb_trajectory: persistent device mirror of `ntraj` trajectories x K knot points, knot-major across the batch (row k * ntraj + j).
+    Arrays passed to the setters / getters are dense (K, ntraj, width) host (numpy) or device (torch) arrays."""
+
+    def __init__(self, handle, ntraj, K, dtype=np.float64):
+        self.handle, self.ntraj, self.K = handle, int(ntraj), int(K)
+        self.dtype = np.dtype(dtype)
+        self.code = F32 if self.dtype == np.float32 else F64
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError(f"rdb200 computes in float32 or float64, got {dtype}")
+        self._p = ctypes.c_void_p()
+        check(lib().rdb_trajectory_create(handle._h, self.code, self.ntraj, self.K, ctypes.byref(self._p)), "rdb_trajectory_create")
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib().rdb_trajectory_destroy(self._p)
+                self._p = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def _arr(self, name, a, shape, f64=False):
+        want = np.dtype(np.float64) if f64 else self.dtype
+        if _is_torch(a):
+            if str(a.dtype).replace("torch.", "") != want.name:
+                raise TypeError(f"{name} has dtype {a.dtype}, the trajectory stores {want.name}")
+            if not a.is_contiguous():
+                raise ValueError(f"{name} must be contiguous")
+        else:
+            a = np.ascontiguousarray(a, dtype=want)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(a.shape)}")
+        return a
+
+    @staticmethod
+    def _stream(a):
+        s = current_stream(a)
+        if s is None:
+            try:
+                import torch
+                s = torch.cuda.current_stream().cuda_stream
+            except ImportError:
+                s = None
+        return s
+
+    def views(self):
+        """Zero-copy torch views of the mirror itself: Z (K, ntraj, n+m), t and dt (K, ntraj) — the memory the kernels read."""
+        import torch
+        pz, pt, pd = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().rdb_trajectory_data(self._p, ctypes.byref(pz), ctypes.byref(pt), ctypes.byref(pd)), "rdb_trajectory_data")
+
+        class _Mem:                      # __cuda_array_interface__ v2: lets torch wrap a raw device pointer without copying
+            def __init__(self, p, shape, typestr, owner):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(p), False), "version": 2}
+                self._owner = owner
+        ts = "<f4" if self.code == F32 else "<f8"
+        nz = self.handle.n + self.handle.m
+        dev = torch.device("cuda", self.handle.ctx.device)
+        Z = torch.as_tensor(_Mem(pz.value, (self.K, self.ntraj, nz), ts, self), device=dev)
+        t = torch.as_tensor(_Mem(pt.value, (self.K, self.ntraj), "<f8", self), device=dev)
+        dt = torch.as_tensor(_Mem(pd.value, (self.K, self.ntraj), "<f8", self), device=dev)
+        return Z, t, dt
+
+    def set_states(self, X):
+        X = self._arr("X", X, (self.K, self.ntraj, self.handle.n))
+        check(lib().rdb_trajectory_set_states(self._p, ptr(X)[0], self._stream(X)), "rdb_trajectory_set_states")
+
+    def set_initial_state(self, x0):
+        x0 = self._arr("x0", x0, (self.ntraj, self.handle.n))
+        check(lib().rdb_trajectory_set_initial_state(self._p, ptr(x0)[0], self._stream(x0)), "rdb_trajectory_set_initial_state")
+
+    def set_controls(self, U):
+        knots = int(U.shape[0])
+        U = self._arr("U", U, (knots, self.ntraj, self.handle.m))
+        check(lib().rdb_trajectory_set_controls(self._p, ptr(U)[0], knots, self._stream(U)), "rdb_trajectory_set_controls")
+
+    def set_timesteps(self, dt, t0=0.0):
+        if np.ndim(dt) == 0:
+            check(lib().rdb_trajectory_set_timesteps(self._p, None, float(dt), float(t0), self._stream(None)), "rdb_trajectory_set_timesteps")
+        else:
+            dt = self._arr("dt", dt, (self.K, self.ntraj), f64=True)
+            check(lib().rdb_trajectory_set_timesteps(self._p, ptr(dt)[0], 0.0, float(t0), self._stream(dt)), "rdb_trajectory_set_timesteps")
+
+    def _get(self, fn, width, out, device):
+        shape = (self.K, self.ntraj, width)
+        if out is None:
+            if device:
+                import torch
+                out = torch.empty(shape, dtype=getattr(torch, self.dtype.name), device="cuda")
+            else:
+                out = np.empty(shape, dtype=self.dtype)
+        else:
+            out = self._arr("out", out, shape)
+        check(fn(self._p, ptr(out)[0], self._stream(out)), fn.__name__)
+        return out
+
+    def states(self, out=None, device=False):
+        return self._get(lib().rdb_trajectory_get_states, self.handle.n, out, device)
+
+    def controls(self, out=None, device=False):
+        return self._get(lib().rdb_trajectory_get_controls, self.handle.m, out, device)
+
+    def rollout(self, Q):
+        check(lib().rdb_trajectory_rollout(self._p, int(Q), self._stream(None)), "rdb_trajectory_rollout")
+
+    def _jout(self, J, error_state, device):
+        h = self.handle
+        rows, cols = (h.nerr, h.nerr + h.m) if (error_state and h.rot != ROT_NONE) else (h.n, h.n + h.m)
+        shape = (self.K, self.ntraj, cols, rows)
+        if J is None:
+            if device:
+                import torch
+                return torch.empty(shape, dtype=getattr(torch, self.dtype.name), device="cuda")
+            return np.empty(shape, dtype=self.dtype)
+        return self._arr("J", J, shape)
+
+    def linearize(self, Q, error_state=False, J=None, xn=None, device=True):
+        J = self._jout(J, error_state, device)
+        if xn is not None:
+            xn = self._arr("xn", xn, (self.K, self.ntraj, self.handle.n))
+            if _is_torch(xn) != _is_torch(J):
+                raise RDBError(ERR_POINTER_MIX, "J and xn must both be host or both be device arrays")
+        check(lib().rdb_trajectory_linearize(self._p, int(Q), int(bool(error_state)), ptr(J)[0], ptr(xn)[0], self._stream(J)),
+              "rdb_trajectory_linearize")
+        return J
+
+    def rollout_linearize(self, Q, error_state=False, J=None, chunks=0, device=True):
+        J = self._jout(J, error_state, device)
+        check(lib().rdb_trajectory_rollout_linearize(self._p, int(Q), int(bool(error_state)), int(chunks), ptr(J)[0], self._stream(J)),
+              "rdb_trajectory_rollout_linearize")
+        return J

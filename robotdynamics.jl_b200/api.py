@@ -213,39 +213,55 @@ class SampledTrajectory:
 
 
 class DeviceTrajectory:
-    """Persistent device mirror of a SampledTrajectory: `data` (N, n+m), `dts` (N,) live in HBM as torch
-    tensors, so repeated linearisations never re-gather the host's Vector{KnotPoint} (an array of pointers to mutable structs,
-    src/knotpoint.jl:213-217) and never cross PCIe.  setstates_/setcontrols_ are sliced H2D copies (src/trajectories.jl:215-250);
-    jacobian_ / discrete_error_jacobian_ / discrete_dynamics accept it wherever a SampledTrajectory is accepted and write into
-    device outputs."""
+    """Persistent device mirror of a SampledTrajectory — an `rdb_trajectory` of the C ABI (include/rdb200.h):
+    data, times and steps live in HBM, so repeated linearisations never re-gather the host's Vector{KnotPoint} (an array of pointers
+    to mutable structs, src/knotpoint.jl:213-217) and never move the inputs across PCIe.  setstates_/setcontrols_ are the reference's
+    setstates!/setcontrols! (src/trajectories.jl:215-250) as H2D column-block updates; jacobian_ / discrete_error_jacobian_ /
+    discrete_dynamics accept it wherever a SampledTrajectory is accepted; rollout_ rolls it out on the device.
+    `data` (K, n+m), `dts`, `times_dev` are zero-copy torch views of the mirror."""
 
-    def __init__(self, Z, device=None, dtype=None):
-        import torch
-        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.n, self.m = Z.n, Z.m
-        host = Z.data if dtype is None else Z.data.astype(dtype)
-        self.data = torch.from_numpy(np.ascontiguousarray(host)).to(dev)
-        self.dts = torch.from_numpy(np.ascontiguousarray(Z.dts)).to(dev)
+    def __init__(self, model, Z, dtype=None):
+        h = model._h
+        self.model, self.n, self.m = model, Z.n, Z.m
+        if (h.n, h.m) != (Z.n, Z.m):
+            raise ValueError(f"trajectory dimensions {(Z.n, Z.m)} do not match the model's {(h.n, h.m)}")
+        dtype = Z.data.dtype if dtype is None else np.dtype(dtype)
+        K = len(Z)
+        self._t = _abi.Trajectory(h, 1, K, dtype)
+        self._t.set_states(np.ascontiguousarray(Z.data[:, None, :Z.n], dtype=dtype))
+        self._t.set_controls(np.ascontiguousarray(Z.data[:, None, Z.n:], dtype=dtype))
+        self._t.set_timesteps(np.ascontiguousarray(Z.dts[:, None]), t0=float(Z.times[0]))
+        Zv, tv, dv = self._t.views()
+        self.data, self.times_dev, self.dts = Zv[:, 0, :], tv[:, 0], dv[:, 0]
         self.times = Z.times.copy()
 
     def __len__(self): return self.data.shape[0]
 
     def to_host(self):
         Z = SampledTrajectory.__new__(SampledTrajectory)
-        Z.n, Z.m, Z.data, Z.dts, Z.times = self.n, self.m, self.data.cpu().numpy(), self.dts.cpu().numpy(), self.times.copy()
+        Z.n, Z.m, Z.data, Z.dts, Z.times = self.n, self.m, self.data.cpu().numpy(), self.dts.cpu().numpy(), self.times_dev.cpu().numpy()
         return Z
 
 
 def states(Z): return Z.data[:, :Z.n]
 def controls(Z): return Z.data[:, Z.n:]
 def gettimes(Z): return Z.times
-def _like(Z, A):
-    if isinstance(Z, DeviceTrajectory) and not _abi._is_torch(A):
-        import torch
-        return torch.as_tensor(np.asarray(A), dtype=Z.data.dtype, device=Z.data.device)
-    return A
-def setstates_(Z, X): Z.data[:, :Z.n] = _like(Z, X)
-def setcontrols_(Z, U): Z.data[:len(U), Z.n:] = _like(Z, U)
+def setstates_(Z, X):
+    """setstates!(Z, X)  (src/trajectories.jl:215-230); on a DeviceTrajectory one H2D copy + a column-block update."""
+    if isinstance(Z, DeviceTrajectory):
+        X = X if _abi._is_torch(X) else np.asarray(X)
+        Z._t.set_states(X.reshape(len(Z), 1, Z.n))
+    else:
+        Z.data[:, :Z.n] = X
+
+
+def setcontrols_(Z, U):
+    """setcontrols!(Z, U)  (src/trajectories.jl:232-250): K-1 controls (the terminal one stays zero) or K."""
+    if isinstance(Z, DeviceTrajectory):
+        U = U if _abi._is_torch(U) else np.asarray(U)
+        Z._t.set_controls(U.reshape(U.shape[0], 1, Z.m))
+    else:
+        Z.data[:len(U), Z.n:] = U
 
 
 class DynamicsJacobian:
@@ -285,6 +301,9 @@ def _write(dst, src, single):
     if dst is None:
         return src[0] if single else src
     if isinstance(dst, DynamicsJacobian):
+        if not single:
+            raise TypeError("a single DynamicsJacobian cannot hold the Jacobians of a whole trajectory: pass an (N, n+m, n) array "
+                            "(the memory of N DynamicsJacobians, src/jacobian.jl:26-37) or evaluate one KnotPoint")
         dst.data[...] = src[0]
     elif single:
         dst[...] = src[0].T if src[0].ndim == 2 else src[0]
@@ -299,11 +318,12 @@ def _write(dst, src, single):
 def dynamics(model, *args, out=None):
     """dynamics(model, z) | dynamics(model, x, u[, t]) | dynamics(model, Z::SampledTrajectory) -> xdot."""
     if len(args) == 1:
-        Z, _, _, single = _batch(args[0])
+        Z, t, _, single = _batch(args[0])
     else:
         x, u = np.asarray(args[0]), np.asarray(args[1])
         Z, single = np.ascontiguousarray(np.concatenate([x, u])[None, :]), True
-    r = model._h.dynamics(Z, out=None if single else out)
+        t = np.array([float(args[2])]) if len(args) > 2 else None
+    r = model._h.dynamics(Z, t=t, out=None if single else out)
     return r[0] if single else r
 
 
@@ -322,11 +342,12 @@ def discrete_dynamics(*args, out=None):
         args = (DiscretizedDynamics(args[1], args[0]),) + tuple(args[2:])
     dmodel = args[0]
     if len(args) == 2:
-        Z, _, dt, single = _batch(args[1])
+        Z, t, dt, single = _batch(args[1])
     else:
-        x, u, _, h = args[1:5]
+        x, u, t, h = args[1:5]
         Z, dt, single = np.ascontiguousarray(np.concatenate([np.asarray(x), np.asarray(u)])[None, :]), np.array([float(h)]), True
-    r = dmodel._h.discrete_dynamics(_qcode(dmodel.integrator), Z, dt, out=None if single else out)
+        t = np.array([float(t)])
+    r = dmodel._h.discrete_dynamics(_qcode(dmodel.integrator), Z, dt, t=t, out=None if single else out)
     return r[0] if single else r
 
 
@@ -341,15 +362,17 @@ def jacobian_(sig, diff, fun, J, y, z):
     the GPU path is exact forward mode (== ForwardAD == UserDefined chain rule to rounding, test/integration_tests.jl:13-17)."""
     if isinstance(diff, FiniteDifference) or diff is FiniteDifference:
         raise NotImplementedModelError(_abi.ERR_NOT_IMPLEMENTED, "jacobian!(::FiniteDifference) on the B200 path")
-    Z, _, dt, single = _batch(z)
+    Z, t, dt, single = _batch(z)
     h = fun._h
+    if isinstance(J, DynamicsJacobian) and not single:
+        _write(J, None, single)                                   # raises: one DynamicsJacobian cannot hold a trajectory's Jacobians
     yb = None
     if y is not None:
         yb = _abi.empty_like_kind(Z, (Z.shape[0], h.n)) if single or not hasattr(y, "shape") else y
     if isinstance(fun, DiscretizedDynamics):
-        Jb = h.discrete_jacobian(_qcode(fun.integrator), Z, dt, J=None if single or isinstance(J, DynamicsJacobian) else J, xn=yb)
+        Jb = h.discrete_jacobian(_qcode(fun.integrator), Z, dt, t=t, J=None if single or isinstance(J, DynamicsJacobian) else J, xn=yb)
     else:
-        Jb = h.jacobian(Z, J=None if single or isinstance(J, DynamicsJacobian) else J, xdot=yb)
+        Jb = h.jacobian(Z, t=t, J=None if single or isinstance(J, DynamicsJacobian) else J, xdot=yb)
     _write(J, Jb, single)
     if y is not None and yb is not y:
         y[...] = yb[0] if single else yb
@@ -365,10 +388,10 @@ def discrete_error_jacobian_(dmodel, Jbar, y, z):
     """Error-state expansion of the discrete dynamics for RotationState models:  Jbar <- G(x+)' [A B] blkdiag(G(x), I)
     (nerr x (nerr+m)), y <- x+.  The product Altro / TrajectoryOptimization build from jacobian! and errstate_jacobian!
     (src/liestate.jl:262-298, src/functionbase.jl:135), fused into the Jacobian kernel."""
-    Z, _, dt, single = _batch(z)
+    Z, t, dt, single = _batch(z)
     h = dmodel._h
     yb = None if y is None else (np.empty((Z.shape[0], h.n), dtype=Z.dtype) if single else y)
-    Jb = h.discrete_error_jacobian(_qcode(dmodel.integrator), Z, dt, J=None if single else Jbar, xn=yb)
+    Jb = h.discrete_error_jacobian(_qcode(dmodel.integrator), Z, dt, t=t, J=None if single else Jbar, xn=yb)
     if single:
         Jbar[...] = Jb[0].T
         if y is not None:
@@ -415,29 +438,62 @@ def state_diff(model, x, x0):
 
 
 def rollout_(sig, dmodel, Z, x0=None):
-    """rollout!(sig, dmodel, Z, x0): overwrite the states of Z with the simulated trajectory (one trajectory)."""
+    """rollout!(sig, dmodel, Z, x0): overwrite the states of Z with the simulated trajectory (src/trajectories.jl:436-441).  A
+    DeviceTrajectory is rolled out in place on the device (rdb_trajectory_rollout)."""
+    if isinstance(Z, DeviceTrajectory):
+        if x0 is not None:
+            Z._t.set_initial_state(np.asarray(x0)[None, :] if not _abi._is_torch(x0) else x0[None, :])
+        Z._t.rollout(_qcode(dmodel.integrator))
+        return None
     x0 = states(Z)[0] if x0 is None else np.asarray(x0)
     X = dmodel._h.rollout(_qcode(dmodel.integrator), np.ascontiguousarray(x0[None, :], dtype=Z.data.dtype),
-                          np.ascontiguousarray(controls(Z)[None, :-1]), np.ascontiguousarray(Z.dts[None, :]))
+                          np.ascontiguousarray(controls(Z)[None, :-1]), np.ascontiguousarray(Z.dts[None, :]),
+                          t=np.ascontiguousarray(Z.times[None, :]))
     setstates_(Z, X[0])
     return None
 
 
+class TrajectoryBatch:
+    """`ntraj` independent trajectories of K knot points on the device (rdb_trajectory, knot-major across the batch): the container of
+    the forward pass + linearisation of sampling-based / multi-shooting solvers.  Arrays are (K, ntraj, width)."""
+
+    def __init__(self, dmodel, ntraj, K, dtype=np.float64):
+        self.dmodel, self.Q = dmodel, _qcode(dmodel.integrator)
+        self._t = _abi.Trajectory(dmodel._h, ntraj, K, dtype)
+        self.ntraj, self.K = int(ntraj), int(K)
+
+    def set_initial_state(self, x0): self._t.set_initial_state(x0)
+    def set_states(self, X): self._t.set_states(X)
+    def set_controls(self, U): self._t.set_controls(U)
+    def set_timesteps(self, dt, t0=0.0): self._t.set_timesteps(dt, t0)
+    def states(self, device=False): return self._t.states(device=device)
+    def controls(self, device=False): return self._t.controls(device=device)
+    def views(self): return self._t.views()
+    def rollout(self): self._t.rollout(self.Q)
+    def linearize(self, error_state=False, J=None, xn=None, device=True): return self._t.linearize(self.Q, error_state, J, xn, device)
+
+    def rollout_linearize(self, error_state=False, J=None, chunks=0, device=True):
+        """x_{k+1} for every knot AND the (error-state) Jacobians of every knot, as one pipelined unit of device work."""
+        return self._t.rollout_linearize(self.Q, error_state, J, chunks, device)
+
+
 def rollout_and_linearize(dmodel, x0, U, dt, error_state=False):
-    """Forward pass + linearisation of many trajectories without leaving the device: X = rollout(x0, U),
-    then the (error-state) discrete Jacobians at every non-terminal knot (x_k, u_k).  x0 (ntraj, n), U (ntraj, K-1, m), scalar dt.
-    Returns X (ntraj, K, n) and J (ntraj, K-1, n+m, n) [or (ntraj, K-1, nerr+m, nerr)]; two kernel launches, no host round trip
-    when the inputs are CUDA tensors."""
-    h, Q = dmodel._h, _qcode(dmodel.integrator)
-    X = h.rollout(Q, x0, U, dt)
-    ntraj, K = X.shape[0], X.shape[1]
-    if _abi._is_torch(X):
-        import torch
-        Z = torch.cat([X[:, :-1, :], U], dim=2).reshape(ntraj * (K - 1), h.n + h.m).contiguous()
-    else:
-        Z = np.ascontiguousarray(np.concatenate([X[:, :-1, :], U], axis=2).reshape(ntraj * (K - 1), h.n + h.m))
-    J = (h.discrete_error_jacobian if error_state else h.discrete_jacobian)(Q, Z, float(dt))
-    return X, J.reshape(ntraj, K - 1, J.shape[1], J.shape[2])
+    """Forward pass + linearisation of many trajectories without leaving the device: x0 (ntraj, n), U (ntraj, K-1, m),
+    scalar dt.  Returns X (ntraj, K, n) and J (ntraj, K-1, n+m, n) [or (ntraj, K-1, nerr+m, nerr)] at the non-terminal knots, host
+    arrays for host inputs and CUDA tensors for CUDA inputs.  One call of rdb_trajectory_rollout_linearize: the rollout kernel writes
+    z = [x;u] rows in place, the Jacobian kernel streams them chunk by chunk on a second stream."""
+    ntraj, K = int(x0.shape[0]), int(U.shape[1]) + 1
+    on_dev = _abi._is_torch(x0)
+    dtype = np.dtype(str(x0.dtype).replace("torch.", ""))
+    tb = TrajectoryBatch(dmodel, ntraj, K, dtype)
+    tb.set_initial_state(x0)
+    tb.set_controls(U.permute(1, 0, 2).contiguous() if on_dev else np.ascontiguousarray(np.transpose(U, (1, 0, 2))))
+    tb.set_timesteps(float(dt))
+    J = tb.rollout_linearize(error_state=error_state, device=on_dev)
+    X = tb.states(device=on_dev)
+    if on_dev:
+        return X.permute(1, 0, 2).contiguous(), J[:-1].permute(1, 0, 2, 3).contiguous()
+    return np.ascontiguousarray(np.transpose(X, (1, 0, 2))), np.ascontiguousarray(np.transpose(J[:-1], (1, 0, 2, 3)))
 
 
 def rollout_batch(dmodel, x0, U, dt):

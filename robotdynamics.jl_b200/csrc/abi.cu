@@ -13,18 +13,19 @@
 #include "custom.h"
 #include "layout.h"
 #include <map>
+#include <vector>
 
 using namespace rdb;
 
 namespace {
 constexpr int NSLOT = 3;                 // pipeline depth of the host-pointer path
 constexpr long long HOST_CHUNK_DEFAULT = 1 << 16;  // knot points per pipelined chunk (RDB200_HOST_CHUNK overrides, for experiments)
-enum { B_Z = 0, B_DT = 1, B_J = 2, B_OUT = 3, B_AUX = 4, NBUF = 5 };
+enum { B_Z = 0, B_DT = 1, B_J = 2, B_OUT = 3, B_AUX = 4, B_T = 5, NBUF = 6 };
 
 struct Slot {
     cudaStream_t st = nullptr;
-    void* buf[NBUF] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[NBUF] = {0, 0, 0, 0, 0};
+    void* buf[NBUF] = {};
+    size_t cap[NBUF] = {};
 };
 }  // namespace
 
@@ -39,6 +40,7 @@ struct rdb_context {
     int pdl = 1;     // programmatic dependent launch of the knot kernels (RDB200_PDL=0 disables)
     long long host_chunk = HOST_CHUNK_DEFAULT;
     Slot slot[NSLOT];
+    cudaEvent_t ev_in = nullptr;   // device-resident inputs + host outputs: the slot streams wait for the caller's stream here
     std::mutex mu;   // the staging slots are shared by all host-pointer calls on this context
 };
 
@@ -50,9 +52,50 @@ struct rdb_model {
     CustomModel* custom;   // kind == RDB_CUSTOM: NVRTC-compiled user model (custom.cu)
 };
 
+// Persistent device mirror of a batch of SampledTrajectories (reference: src/trajectories.jl:40-50), knot-major across the batch:
+// row k * ntraj + j of Z holds z = [x;u] of knot k of trajectory j; t and dt are stored the same way.  With this order the knots of a
+// time chunk [kb, ke] of ALL trajectories are one contiguous range (what the Jacobian kernel streams), a warp of the rollout kernel
+// (adjacent trajectories) reads and writes one contiguous range per step, and for ntraj == 1 the image is exactly the gathered
+// Matrix(n+m, K) of a Vector{KnotPoint}.
+struct rdb_trajectory {
+    const rdb_model* M = nullptr;
+    int dtype = RDB_F64;
+    long long ntraj = 0;
+    int K = 0;
+    void* Z = nullptr;
+    double* t = nullptr;
+    double* dt = nullptr;
+    void* stage = nullptr; size_t stage_cap = 0;        // dense device staging of the host-pointer setters / getters
+    cudaStream_t aux[2] = {nullptr, nullptr};           // rollout / linearisation pipeline of rdb_trajectory_rollout_linearize
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_chunk;
+    std::mutex mu;
+};
+
+// A validated, pre-dispatched knot operation on device pointers: launching it is one kernel launch and nothing else.
+struct rdb_plan {
+    const rdb_model* M = nullptr;
+    int dtype = RDB_F64, layout = RDB_AOS;
+    KnotRequest r;
+};
+
 namespace {
 
 int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : int(e); }
+
+// Every entry point runs on its context's device and puts the caller's current device back before returning: in a multi-GPU
+// process (one torch process driving several devices) the library must not change where the caller's next allocation lands.
+struct DeviceGuard {
+    int prev = -1; bool changed = false; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != d) { err = cudaSetDevice(d); changed = (err == cudaSuccess) && prev >= 0; }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define RDB_ON_DEVICE(ctx) DeviceGuard guard__((ctx)->device); if (guard__.err != cudaSuccess) return int(guard__.err)
 #define RDB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return int(e__); } while (0)
 
 void inv3(const double* A, double* Ai) {
@@ -64,19 +107,22 @@ void inv3(const double* A, double* Ai) {
     Ai[6] = (d * h - e * g) * id; Ai[7] = (b * g - a * h) * id; Ai[8] = (a * e - b * d) * id;
 }
 
-// 0 = null, 1 = host (pinned, registered or pageable), 2 = device / managed
-int ptr_kind(const void* p) {
+// 0 = null, 1 = host (pinned, registered or pageable), 2 = device / managed, RDB_ERR_POINTER_MIX = memory of ANOTHER device
+int ptr_kind(const void* p, int device = -1) {
     if (!p) return 0;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 1; }
+    if (at.type == cudaMemoryTypeDevice && device >= 0 && at.device != device) return RDB_ERR_POINTER_MIX;
     return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 2 : 1;
 }
-// classify a set of data pointers: returns 1 host, 2 device, 0 all-null, RDB_ERR_POINTER_MIX on a mix
-int classify(std::initializer_list<const void*> ps) {
+// classify a set of data pointers: returns 1 host, 2 device, 0 all-null, RDB_ERR_POINTER_MIX on a mix (or on device memory that
+// does not belong to `device`, the context's GPU)
+int classify(std::initializer_list<const void*> ps, int device = -1) {
     int kind = 0;
     for (const void* p : ps) {
-        const int k = ptr_kind(p);
+        const int k = ptr_kind(p, device);
         if (k == 0) continue;
+        if (k < 0) return k;
         if (kind == 0) kind = k;
         else if (kind != k) return RDB_ERR_POINTER_MIX;
     }
@@ -143,8 +189,10 @@ int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long 
         const int rc = dispatch(M, dtype, &q);
         if (rc != RDB_ERR_NOT_IMPLEMENTED) return rc;
     }
-    SoaScratch* sc;
-    { std::lock_guard<std::mutex> lock(c->soa_mu); sc = &c->soa[r.stream]; }
+    // the scratch of a stream is shared by every host thread that submits on it (notably the NULL stream): the lock is held for the
+    // whole enqueue sequence, so two threads cannot interleave transpose / kernel / transpose on the same buffers
+    std::lock_guard<std::mutex> lock(c->soa_mu);
+    SoaScratch* sc = &c->soa[r.stream];
     long long SOA_CHUNK = (long long)(SOA_SCRATCH_BYTES / (size_t(E) * es));
     SOA_CHUNK = SOA_CHUNK < 1024 ? 1024 : (SOA_CHUNK / 1024) * 1024;
     const long long cap = r.N < SOA_CHUNK ? r.N : SOA_CHUNK;
@@ -163,6 +211,7 @@ int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long 
         KnotRequest q = r;
         q.Z = sc->buf[0]; q.J = r.J ? sc->buf[1] : nullptr; q.out = r.out ? sc->buf[2] : nullptr; q.N = cnt;
         q.dt = r.dt ? r.dt + k0 : nullptr;
+        q.t = r.t ? r.t + k0 : nullptr;
         if ((rc = dispatch(M, dtype, &q))) return rc;
         if (r.J && (rc = aos_to_soa(dtype, sc->buf[1], (char*)r.J + size_t(k0) * es, ld, E, cnt, r.stream))) return rc;
         if (r.out && (rc = aos_to_soa(dtype, sc->buf[2], (char*)r.out + size_t(k0) * es, ld, n, cnt, r.stream))) return rc;
@@ -171,16 +220,28 @@ int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long 
 }
 
 // The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
-int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* dt,
+// KnotPoint.t reaches only models whose dynamics can depend on it: user models (dynamics(model, x, u, t), src/dynamics.jl:81-83).
+// The shipped families are time-invariant, so their kernels never load it and the host path never copies it.
+bool model_uses_time(const rdb_model* M) { return M->kind == RDB_CUSTOM; }
+
+int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* t, const double* dt,
             double dt0, void* J, void* out, void* stream, int err = 0) {
     if (!M || N < 0 || (dtype != RDB_F32 && dtype != RDB_F64) || (layout != RDB_AOS && layout != RDB_SOA)) return RDB_ERR_ARG;
     if (N == 0) return 0;
     if (!Z || (with_j && !J) || (!with_j && !out)) return RDB_ERR_ARG;
     if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
     rdb_context* c = M->ctx;
-    RDB_CUDA(cudaSetDevice(c->device));
-    const int kind = classify({Z, dt, J, out});
-    if (kind < 0) return kind;
+    RDB_ON_DEVICE(c);
+    if (!model_uses_time(M)) t = nullptr;
+    // inputs and outputs are classified separately: device-resident inputs (a persistent device trajectory) may be combined with
+    // HOST outputs (the solver keeps its Jacobians on the host) — the kernel then reads Z in place and only J / x+ cross PCIe.
+    const int kind_in = classify({Z, t, dt}, c->device), kind_out = classify({J, out}, c->device);
+    if (kind_in < 0) return kind_in;
+    if (kind_out < 0) return kind_out;
+    const bool dev_in_host_out = (kind_in == 2 && kind_out == 1);
+    if (kind_in != kind_out && !dev_in_host_out) return RDB_ERR_POINTER_MIX;
+    if (dev_in_host_out && layout != RDB_AOS) return RDB_ERR_POINTER_MIX;
+    const int kind = kind_out;
 
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
@@ -188,7 +249,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.err = err; r.params = M->p;
     r.dt0 = dt0; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
-        r.Z = Z; r.dt = dt; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
+        r.Z = Z; r.dt = dt; r.t = t; r.J = J; r.out = out; r.N = N; r.stream = (cudaStream_t)stream;
         return layout == RDB_SOA ? dispatch_soa(M, dtype, r, N) : dispatch(M, dtype, &r);
     }
     // host pointers: H2D -> kernel -> D2H per chunk, chunks round-robin over NSLOT streams so the three overlap
@@ -199,16 +260,27 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     long long ci = 0;
     const long long HOST_CHUNK = c->host_chunk;
     const long long cap_knots = N < HOST_CHUNK ? N : HOST_CHUNK;
+    if (dev_in_host_out) {      // the inputs are produced on the caller's stream: the slot streams start after it
+        if (!c->ev_in) RDB_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+        RDB_CUDA(cudaEventRecord(c->ev_in, (cudaStream_t)stream));
+        for (auto& s : c->slot) RDB_CUDA(cudaStreamWaitEvent(s.st, c->ev_in, 0));
+    }
     for (long long k0 = 0; k0 < N && !rc; k0 += HOST_CHUNK, ++ci) {
         const long long cnt = (N - k0 < HOST_CHUNK) ? (N - k0) : HOST_CHUNK;
         Slot& s = c->slot[ci % NSLOT];
-        if ((rc = ensure(s, B_Z, size_t(cap_knots) * NZ * es))) break;
-        if (dt && (rc = ensure(s, B_DT, size_t(cap_knots) * 8))) break;
         if (J && (rc = ensure(s, B_J, size_t(cap_knots) * E * es))) break;
         if (out && (rc = ensure(s, B_OUT, size_t(cap_knots) * n * es))) break;
-        if ((rc = copy_chunk(s.buf[B_Z], Z, layout, es, NZ, N, k0, cnt, cudaMemcpyHostToDevice, s.st))) break;
-        if (dt && (rc = cuda_rc(cudaMemcpyAsync(s.buf[B_DT], dt + k0, size_t(cnt) * 8, cudaMemcpyHostToDevice, s.st)))) break;
-        r.Z = s.buf[B_Z]; r.dt = dt ? (const double*)s.buf[B_DT] : nullptr;
+        if (dev_in_host_out) {
+            r.Z = (const char*)Z + size_t(k0) * NZ * es; r.dt = dt ? dt + k0 : nullptr; r.t = t ? t + k0 : nullptr;
+        } else {
+            if ((rc = ensure(s, B_Z, size_t(cap_knots) * NZ * es))) break;
+            if (dt && (rc = ensure(s, B_DT, size_t(cap_knots) * 8))) break;
+            if (t && (rc = ensure(s, B_T, size_t(cap_knots) * 8))) break;
+            if ((rc = copy_chunk(s.buf[B_Z], Z, layout, es, NZ, N, k0, cnt, cudaMemcpyHostToDevice, s.st))) break;
+            if (dt && (rc = cuda_rc(cudaMemcpyAsync(s.buf[B_DT], dt + k0, size_t(cnt) * 8, cudaMemcpyHostToDevice, s.st)))) break;
+            if (t && (rc = cuda_rc(cudaMemcpyAsync(s.buf[B_T], t + k0, size_t(cnt) * 8, cudaMemcpyHostToDevice, s.st)))) break;
+            r.Z = s.buf[B_Z]; r.dt = dt ? (const double*)s.buf[B_DT] : nullptr; r.t = t ? (const double*)s.buf[B_T] : nullptr;
+        }
         r.J = J ? s.buf[B_J] : nullptr; r.out = out ? s.buf[B_OUT] : nullptr; r.N = cnt; r.stream = s.st;
         if ((rc = (layout == RDB_SOA ? dispatch_soa(M, dtype, r, cnt) : dispatch(M, dtype, &r)))) break;
         if (J && (rc = copy_chunk(J, s.buf[B_J], layout, es, E, N, k0, cnt, cudaMemcpyDeviceToHost, s.st))) break;
@@ -258,21 +330,24 @@ int rdb_create(int device, rdb_context** ctx) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return RDB_ERR_NO_DEVICE; }
     if (device < 0 || device >= count) return RDB_ERR_ARG;
-    RDB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return int(guard.err);
     rdb_context* c = new (std::nothrow) rdb_context();
     if (!c) return RDB_ERR_ARG;
     c->device = device;
-    RDB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (const char* e = std::getenv("RDB200_PDL")) c->pdl = (e[0] != '0');
-    if (const char* e = std::getenv("RDB200_HOST_CHUNK")) { const long long v = std::atoll(e); if (v >= 1024) c->host_chunk = v; }
-    for (auto& s : c->slot) RDB_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char* v = std::getenv("RDB200_PDL")) c->pdl = (v[0] != '0');
+    if (const char* v = std::getenv("RDB200_HOST_CHUNK")) { const long long n = std::atoll(v); if (n >= 1024) c->host_chunk = n; }
+    for (auto& s : c->slot) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { rdb_destroy(c); return int(e); }       // frees the streams created so far and the context
     *ctx = c;
     return 0;
 }
 
 int rdb_destroy(rdb_context* c) {
     if (!c) return 0;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
     for (auto& s : c->slot) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         for (auto& b : s.buf) if (b) cudaFree(b);
@@ -392,33 +467,33 @@ int rdb_model_dims(const rdb_model* M, int* n, int* m, int* nerr) {
     return 0;
 }
 
-int rdb_dynamics(const rdb_model* M, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/, void* xdot, void* stream) {
-    return knot_op(M, Q_CONTINUOUS, dtype, layout, 0, N, Z, nullptr, 0.0, nullptr, xdot, stream);
+int rdb_dynamics(const rdb_model* M, int dtype, int layout, int64_t N, const void* Z, const double* t, void* xdot, void* stream) {
+    return knot_op(M, Q_CONTINUOUS, dtype, layout, 0, N, Z, t, nullptr, 0.0, nullptr, xdot, stream);
 }
 
-int rdb_discrete_dynamics(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/,
+int rdb_discrete_dynamics(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
                           const double* dt, double dt0, void* xn, void* stream) {
     const int Q = map_q(integrator);
     if (Q < 0) return RDB_ERR_ARG;
-    return knot_op(M, Q, dtype, layout, 0, N, Z, dt, dt0, nullptr, xn, stream);
+    return knot_op(M, Q, dtype, layout, 0, N, Z, t, dt, dt0, nullptr, xn, stream);
 }
 
-int rdb_jacobian(const rdb_model* M, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/, void* J, void* xdot, void* stream) {
-    return knot_op(M, Q_CONTINUOUS, dtype, layout, 1, N, Z, nullptr, 0.0, J, xdot, stream);
+int rdb_jacobian(const rdb_model* M, int dtype, int layout, int64_t N, const void* Z, const double* t, void* J, void* xdot, void* stream) {
+    return knot_op(M, Q_CONTINUOUS, dtype, layout, 1, N, Z, t, nullptr, 0.0, J, xdot, stream);
 }
 
-int rdb_discrete_jacobian(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/,
+int rdb_discrete_jacobian(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
                           const double* dt, double dt0, void* J, void* xn, void* stream) {
     const int Q = map_q(integrator);
     if (Q < 0) return RDB_ERR_ARG;
-    return knot_op(M, Q, dtype, layout, 1, N, Z, dt, dt0, J, xn, stream);
+    return knot_op(M, Q, dtype, layout, 1, N, Z, t, dt, dt0, J, xn, stream);
 }
 
-int rdb_discrete_error_jacobian(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* /*t*/,
+int rdb_discrete_error_jacobian(const rdb_model* M, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
                                 const double* dt, double dt0, void* Jbar, void* xn, void* stream) {
     const int Q = map_q(integrator);
     if (Q < 0) return RDB_ERR_ARG;
-    return knot_op(M, Q, dtype, layout, 1, N, Z, dt, dt0, Jbar, xn, stream, 1);
+    return knot_op(M, Q, dtype, layout, 1, N, Z, t, dt, dt0, Jbar, xn, stream, 1);
 }
 
 int rdb_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const void* X, int ldx, void* G, void* stream) {
@@ -426,8 +501,8 @@ int rdb_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const void* 
     if (N == 0) return 0;
     if (!X || !G) return RDB_ERR_ARG;
     rdb_context* c = M->ctx;
-    RDB_CUDA(cudaSetDevice(c->device));
-    const int kind = classify({X, G});
+    RDB_ON_DEVICE(c);
+    const int kind = classify({X, G}, c->device);
     if (kind < 0) return kind;
     if (kind == 2) return lie_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, X, ldx, G, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
@@ -446,8 +521,8 @@ int rdb_grad_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const v
     if (N == 0) return 0;
     if (!X || !Xbar || !H) return RDB_ERR_ARG;
     rdb_context* c = M->ctx;
-    RDB_CUDA(cudaSetDevice(c->device));
-    const int kind = classify({X, Xbar, H});
+    RDB_ON_DEVICE(c);
+    const int kind = classify({X, Xbar, H}, c->device);
     if (kind < 0) return kind;
     if (kind == 2) return lie_grad_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, X, ldx, Xbar, ldb, H, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
@@ -466,8 +541,8 @@ int rdb_state_diff(const rdb_model* M, int dtype, int64_t N, const void* X, int 
     if (N == 0) return 0;
     if (!X || !X0 || !dXo) return RDB_ERR_ARG;
     rdb_context* c = M->ctx;
-    RDB_CUDA(cudaSetDevice(c->device));
-    const int kind = classify({X, X0, dXo});
+    RDB_ON_DEVICE(c);
+    const int kind = classify({X, X0, dXo}, c->device);
     if (kind < 0) return kind;
     if (kind == 2) return lie_state_diff(dtype, M->rot, M->n, M->nerr, N, X, ldx, X0, ldx0, dXo, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
@@ -481,7 +556,7 @@ int rdb_state_diff(const rdb_model* M, int dtype, int64_t N, const void* X, int 
     return st.finish();
 }
 
-int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, int K, const void* x0, const void* U, const double* /*t*/,
+int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, int K, const void* x0, const void* U, const double* t,
                 const double* dt, double dt0, void* X, void* stream) {
     const int Q = map_q(integrator);
     if (!M || Q < 0 || ntraj < 0 || K < 1 || (dtype != RDB_F32 && dtype != RDB_F64)) return RDB_ERR_ARG;
@@ -489,15 +564,16 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     if (!x0 || !X || (K > 1 && !U)) return RDB_ERR_ARG;
     if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
     rdb_context* c = M->ctx;
-    RDB_CUDA(cudaSetDevice(c->device));
-    const int kind = classify({x0, U, dt, X});
+    RDB_ON_DEVICE(c);
+    if (!model_uses_time(M)) t = nullptr;
+    const int kind = classify({x0, U, t, dt, X}, c->device);
     if (kind < 0) return kind;
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
     r.op = OP_ROLLOUT; r.Q = Q; r.dtype = dtype; r.params = M->p; r.dt0 = dt0; r.ntraj = ntraj; r.K = K;
     r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
-        r.x0 = x0; r.U = U; r.dt = dt; r.X = X; r.stream = (cudaStream_t)stream;
+        r.x0 = x0; r.U = U; r.dt = dt; r.t = t; r.X = X; r.stream = (cudaStream_t)stream;
         return dispatch(M, dtype, &r);
     }
     std::lock_guard<std::mutex> lock(c->mu);
@@ -506,6 +582,7 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     r.x0 = st.in(B_Z, x0, size_t(ntraj) * M->n * es);
     r.U = st.in(B_AUX, U, size_t(ntraj) * (K - 1) * M->m * es);
     r.dt = (const double*)st.in(B_DT, dt, size_t(ntraj) * K * 8);
+    r.t = (const double*)st.in(B_T, t, size_t(ntraj) * K * 8);
     r.X = st.outbuf(B_J, size_t(ntraj) * K * M->n * es);
     r.stream = st.s.st;
     if (!st.rc) st.rc = dispatch(M, dtype, &r);
@@ -513,4 +590,276 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     return st.finish();
 }
 
+
+// ---- pre-validated launches ("plans") ---------------------------------------------------------------------------------------------
+int rdb_plan_create(const rdb_model* M, int op, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
+                    const double* dt, double dt0, void* J, void* out, rdb_plan** plan) {
+    if (!plan) return RDB_ERR_ARG;
+    *plan = nullptr;
+    if (!M || N <= 0 || (dtype != RDB_F32 && dtype != RDB_F64) || (layout != RDB_AOS && layout != RDB_SOA) || !Z) return RDB_ERR_ARG;
+    int Q = Q_CONTINUOUS, with_j = 0, err = 0;
+    switch (op) {
+        case RDB_OP_DYNAMICS: break;
+        case RDB_OP_JACOBIAN: with_j = 1; break;
+        case RDB_OP_DISCRETE_DYNAMICS: Q = map_q(integrator); break;
+        case RDB_OP_DISCRETE_JACOBIAN: Q = map_q(integrator); with_j = 1; break;
+        case RDB_OP_DISCRETE_ERROR_JACOBIAN: Q = map_q(integrator); with_j = 1; err = (M->rot != RDB_ROT_NONE); break;
+        default: return RDB_ERR_ARG;
+    }
+    if (Q < 0 || (with_j && !J) || (!with_j && !out)) return RDB_ERR_ARG;
+    if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
+    rdb_context* c = M->ctx;
+    RDB_ON_DEVICE(c);
+    if (!model_uses_time(M)) t = nullptr;
+    if (Q == Q_CONTINUOUS) { dt = nullptr; dt0 = 0.0; }
+    const int kind = classify({Z, t, dt, J, out}, c->device);
+    if (kind < 0) return kind;
+    if (kind != 2) return RDB_ERR_POINTER_MIX;          // plans are for device-resident data
+    rdb_plan* p = new (std::nothrow) rdb_plan();
+    if (!p) return RDB_ERR_ARG;
+    p->M = M; p->dtype = dtype; p->layout = layout;
+    std::memset(&p->r, 0, sizeof(p->r));
+    KnotRequest& r = p->r;
+    r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.err = err; r.params = M->p; r.dt0 = dt0;
+    r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
+    r.Z = Z; r.dt = dt; r.t = t; r.J = J; r.out = out; r.N = N;
+    *plan = p;
+    return 0;
+}
+
+int rdb_plan_launch(const rdb_plan* p, void* stream) {
+    if (!p) return RDB_ERR_ARG;
+    RDB_ON_DEVICE(p->M->ctx);
+    KnotRequest r = p->r;
+    r.stream = (cudaStream_t)stream;
+    return p->layout == RDB_SOA ? dispatch_soa(p->M, p->dtype, r, r.N) : dispatch(p->M, p->dtype, &r);
+}
+
+int rdb_plan_destroy(rdb_plan* p) { delete p; return 0; }
+
+// ---- persistent device trajectory ------------------------------------------------------------------------------------------------------
+int rdb_trajectory_create(const rdb_model* M, int dtype, int64_t ntraj, int K, rdb_trajectory** traj) {
+    if (!traj) return RDB_ERR_ARG;
+    *traj = nullptr;
+    if (!M || ntraj < 1 || K < 1 || (dtype != RDB_F32 && dtype != RDB_F64)) return RDB_ERR_ARG;
+    if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
+    RDB_ON_DEVICE(M->ctx);
+    rdb_trajectory* T = new (std::nothrow) rdb_trajectory();
+    if (!T) return RDB_ERR_ARG;
+    T->M = M; T->dtype = dtype; T->ntraj = ntraj; T->K = K;
+    const size_t rows = size_t(ntraj) * K, zb = rows * (M->n + M->m) * esize(dtype);
+    cudaError_t e = cudaMalloc(&T->Z, zb);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&T->t, rows * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&T->dt, rows * 8);
+    if (e == cudaSuccess) e = cudaMemset(T->Z, 0, zb);
+    if (e == cudaSuccess) e = cudaMemset(T->t, 0, rows * 8);
+    if (e == cudaSuccess) e = cudaMemset(T->dt, 0, rows * 8);
+    for (auto& st : T->aux) if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&T->ev_fork, cudaEventDisableTiming);
+    for (auto& ev : T->ev_join) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { rdb_trajectory_destroy(T); return int(e); }
+    *traj = T;
+    return 0;
+}
+
+int rdb_trajectory_destroy(rdb_trajectory* T) {
+    if (!T) return 0;
+    DeviceGuard guard(T->M->ctx->device);
+    for (auto& st : T->aux) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (T->ev_fork) cudaEventDestroy(T->ev_fork);
+    for (auto& ev : T->ev_join) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : T->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (T->Z) cudaFree(T->Z);
+    if (T->t) cudaFree(T->t);
+    if (T->dt) cudaFree(T->dt);
+    if (T->stage) cudaFree(T->stage);
+    delete T;
+    return 0;
+}
+
+int rdb_trajectory_dims(const rdb_trajectory* T, int64_t* ntraj, int* K, int* n, int* m, int* dtype) {
+    if (!T) return RDB_ERR_ARG;
+    if (ntraj) *ntraj = T->ntraj;
+    if (K) *K = T->K;
+    if (n) *n = T->M->n;
+    if (m) *m = T->M->m;
+    if (dtype) *dtype = T->dtype;
+    return 0;
+}
+
+int rdb_trajectory_data(const rdb_trajectory* T, void** Z, double** t, double** dt) {
+    if (!T) return RDB_ERR_ARG;
+    if (Z) *Z = T->Z;
+    if (t) *t = T->t;
+    if (dt) *dt = T->dt;
+    return 0;
+}
+
 }  // extern "C"
+
+namespace {
+int traj_stage(rdb_trajectory* T, size_t bytes) {
+    if (bytes <= T->stage_cap) return 0;
+    if (T->stage) { RDB_CUDA(cudaFree(T->stage)); T->stage = nullptr; T->stage_cap = 0; }
+    RDB_CUDA(cudaMalloc(&T->stage, bytes));
+    T->stage_cap = bytes;
+    return 0;
+}
+// copy a dense (rows, width) block `src` (host or device) into columns [col, col + width) of rows [r0, r0 + rows) of Z
+int traj_put(rdb_trajectory* T, const void* src, long long r0, long long rows, int col, int width, cudaStream_t st) {
+    if (!T || !src || rows < 0) return RDB_ERR_ARG;
+    if (rows == 0) return 0;
+    rdb_context* c = T->M->ctx;
+    RDB_ON_DEVICE(c);
+    const int kind = ptr_kind(src, c->device);
+    if (kind < 0) return kind;
+    const size_t es = esize(T->dtype);
+    const int NZ = T->M->n + T->M->m;
+    char* dst = (char*)T->Z + size_t(r0) * NZ * es;
+    if (kind == 2) return copy_cols(T->dtype, src, width, 0, dst, NZ, col, width, rows, st);
+    std::lock_guard<std::mutex> lock(T->mu);
+    const size_t bytes = size_t(rows) * width * es;
+    if (int rc = traj_stage(T, bytes)) return rc;
+    RDB_CUDA(cudaMemcpyAsync(T->stage, src, bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = copy_cols(T->dtype, T->stage, width, 0, dst, NZ, col, width, rows, st)) return rc;
+    return cuda_rc(cudaStreamSynchronize(st));           // host source: consumed when the call returns
+}
+int traj_get(rdb_trajectory* T, void* dstp, int col, int width, cudaStream_t st) {
+    if (!T || !dstp) return RDB_ERR_ARG;
+    rdb_context* c = T->M->ctx;
+    RDB_ON_DEVICE(c);
+    const int kind = ptr_kind(dstp, c->device);
+    if (kind < 0) return kind;
+    const int NZ = T->M->n + T->M->m;
+    const long long rows = T->ntraj * T->K;
+    if (kind == 2) return copy_cols(T->dtype, T->Z, NZ, col, dstp, width, 0, width, rows, st);
+    std::lock_guard<std::mutex> lock(T->mu);
+    const size_t bytes = size_t(rows) * width * esize(T->dtype);
+    if (int rc = traj_stage(T, bytes)) return rc;
+    if (int rc = copy_cols(T->dtype, T->Z, NZ, col, T->stage, width, 0, width, rows, st)) return rc;
+    RDB_CUDA(cudaMemcpyAsync(dstp, T->stage, bytes, cudaMemcpyDeviceToHost, st));
+    return cuda_rc(cudaStreamSynchronize(st));
+}
+KnotRequest traj_request(const rdb_trajectory* T, int Q, int err) {
+    const rdb_model* M = T->M;
+    rdb_context* c = M->ctx;
+    KnotRequest r;
+    std::memset(&r, 0, sizeof(r));
+    r.Q = Q; r.dtype = T->dtype; r.params = M->p; r.dt0 = 0.0; r.dt = T->dt; r.t = model_uses_time(M) ? T->t : nullptr;
+    r.err = (M->rot == RDB_ROT_NONE) ? 0 : err;
+    r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
+    return r;
+}
+}  // namespace
+
+extern "C" {
+
+int rdb_trajectory_set_states(rdb_trajectory* T, const void* X, void* stream) {
+    return T ? traj_put(T, X, 0, T->ntraj * T->K, 0, T->M->n, (cudaStream_t)stream) : RDB_ERR_ARG;
+}
+int rdb_trajectory_set_initial_state(rdb_trajectory* T, const void* x0, void* stream) {
+    return T ? traj_put(T, x0, 0, T->ntraj, 0, T->M->n, (cudaStream_t)stream) : RDB_ERR_ARG;
+}
+int rdb_trajectory_set_controls(rdb_trajectory* T, const void* U, int knots, void* stream) {
+    if (!T || (knots != T->K && knots != T->K - 1)) return RDB_ERR_ARG;
+    if (int rc = traj_put(T, U, 0, T->ntraj * knots, T->M->n, T->M->m, (cudaStream_t)stream)) return rc;
+    if (knots == T->K - 1) {                             // no terminal control given: it is zero (src/knotpoint.jl:57-67)
+        RDB_ON_DEVICE(T->M->ctx);
+        return zero_cols(T->dtype, T->Z, T->M->n + T->M->m, T->M->n, T->M->m, T->ntraj * (T->K - 1), T->ntraj * T->K, (cudaStream_t)stream);
+    }
+    return 0;
+}
+int rdb_trajectory_set_timesteps(rdb_trajectory* T, const double* dt, double dt0, double t0, void* stream) {
+    if (!T) return RDB_ERR_ARG;
+    rdb_context* c = T->M->ctx;
+    RDB_ON_DEVICE(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = T->ntraj * T->K;
+    const int kind = ptr_kind(dt, c->device);
+    if (kind < 0) return kind;
+    if (kind != 1) return time_grid(dt, dt0, t0, T->dt, T->t, T->ntraj, T->K, st);
+    std::lock_guard<std::mutex> lock(T->mu);
+    if (int rc = traj_stage(T, size_t(rows) * 8)) return rc;
+    RDB_CUDA(cudaMemcpyAsync(T->stage, dt, size_t(rows) * 8, cudaMemcpyHostToDevice, st));
+    if (int rc = time_grid((const double*)T->stage, dt0, t0, T->dt, T->t, T->ntraj, T->K, st)) return rc;
+    return cuda_rc(cudaStreamSynchronize(st));
+}
+int rdb_trajectory_get_states(rdb_trajectory* T, void* X, void* stream) { return T ? traj_get(T, X, 0, T->M->n, (cudaStream_t)stream) : RDB_ERR_ARG; }
+int rdb_trajectory_get_controls(rdb_trajectory* T, void* U, void* stream) { return T ? traj_get(T, U, T->M->n, T->M->m, (cudaStream_t)stream) : RDB_ERR_ARG; }
+
+int rdb_trajectory_rollout(rdb_trajectory* T, int integrator, void* stream) {
+    const int Q = map_q(integrator);
+    if (!T || Q < 0) return RDB_ERR_ARG;
+    RDB_ON_DEVICE(T->M->ctx);
+    KnotRequest r = traj_request(T, Q, 0);
+    r.op = OP_ROLLOUT; r.zmode = 1; r.kb = 0; r.ke = T->K - 1; r.X = T->Z; r.ntraj = T->ntraj; r.K = T->K; r.stream = (cudaStream_t)stream;
+    return dispatch(T->M, T->dtype, &r);
+}
+
+int rdb_trajectory_linearize(rdb_trajectory* T, int integrator, int error_state, void* J, void* xn, void* stream) {
+    const int Q = map_q(integrator);
+    if (!T || Q < 0 || !J) return RDB_ERR_ARG;
+    return knot_op(T->M, Q, T->dtype, RDB_AOS, 1, T->ntraj * T->K, T->Z, T->t, T->dt, 0.0, J, xn, stream, error_state ? 1 : 0);
+}
+
+// Forward pass + linearisation as a two-stream pipeline: the rollout (latency-bound: one thread per trajectory, sequential in k) runs
+// in chunks of knots on one stream; as soon as a chunk's states exist, the Jacobians of that chunk — a contiguous range of rows in
+// the knot-major batch — are evaluated at full-GPU rate on the other stream while the next chunk is rolled out.  Fork / join by
+// events from the caller's stream, so the whole call is still one asynchronous unit of work on `stream` (and is graph-capturable).
+int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int error_state, int chunks, void* J, void* stream) {
+    const int Q = map_q(integrator);
+    if (!T || Q < 0 || !J || chunks < 0) return RDB_ERR_ARG;
+    const rdb_model* M = T->M;
+    rdb_context* c = M->ctx;
+    RDB_ON_DEVICE(c);
+    const int jkind = ptr_kind(J, c->device);
+    if (jkind < 0) return jkind;
+    if (jkind != 2) {                                    // host Jacobians: roll out, then the chunked device -> host pipeline of knot_op
+        if (int rc = rdb_trajectory_rollout(T, integrator, stream)) return rc;
+        return rdb_trajectory_linearize(T, integrator, error_state, J, nullptr, stream);
+    }
+    std::lock_guard<std::mutex> lock(T->mu);
+    const int steps = T->K - 1;
+    int nch = chunks > 0 ? chunks : 8;
+    if (nch > steps) nch = steps > 0 ? steps : 1;
+    while ((int)T->ev_chunk.size() < nch) {
+        cudaEvent_t ev;
+        RDB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        T->ev_chunk.push_back(ev);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int err = (M->rot == RDB_ROT_NONE) ? 0 : (error_state ? 1 : 0);
+    const size_t es = esize(T->dtype);
+    const int NZ = M->n + M->m, E = err ? M->nerr * (M->nerr + M->m) : M->n * NZ;
+    RDB_CUDA(cudaEventRecord(T->ev_fork, st));
+    for (auto& a : T->aux) RDB_CUDA(cudaStreamWaitEvent(a, T->ev_fork, 0));
+    long long row_lo = 0;                                // first knot whose Jacobian has not been enqueued yet
+    for (int ch = 0; ch < nch; ++ch) {
+        const int kb = int((long long)steps * ch / nch), ke = int((long long)steps * (ch + 1) / nch);
+        if (ke > kb) {
+            KnotRequest r = traj_request(T, Q, 0);
+            r.op = OP_ROLLOUT; r.zmode = 1; r.kb = kb; r.ke = ke; r.X = T->Z; r.ntraj = T->ntraj; r.K = T->K; r.stream = T->aux[0];
+            if (int rc = dispatch(M, T->dtype, &r)) return rc;
+        }
+        RDB_CUDA(cudaEventRecord(T->ev_chunk[ch], T->aux[0]));
+        RDB_CUDA(cudaStreamWaitEvent(T->aux[1], T->ev_chunk[ch], 0));
+        const long long row_hi = (ch == nch - 1) ? (long long)T->K : (long long)ke + 1;   // states of knots < row_hi are final
+        if (row_hi > row_lo) {
+            KnotRequest r = traj_request(T, Q, err);
+            r.op = OP_KNOT; r.with_j = 1; r.N = (row_hi - row_lo) * T->ntraj; r.stream = T->aux[1];
+            r.Z = (const char*)T->Z + size_t(row_lo) * T->ntraj * NZ * es;
+            r.dt = T->dt + row_lo * T->ntraj; if (r.t) r.t = T->t + row_lo * T->ntraj;
+            r.J = (char*)J + size_t(row_lo) * T->ntraj * E * es;
+            if (int rc = dispatch(M, T->dtype, &r)) return rc;
+            row_lo = row_hi;
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        RDB_CUDA(cudaEventRecord(T->ev_join[i], T->aux[i]));
+        RDB_CUDA(cudaStreamWaitEvent(st, T->ev_join[i], 0));
+    }
+    return 0;
+}
+
+}  // extern "C"
+

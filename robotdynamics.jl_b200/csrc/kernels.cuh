@@ -40,6 +40,7 @@ struct KnotArgs {
     const T* Z;          // [x;u] per knot, knot-major (N, n+m)
     const double* dt;    // per-knot step (N) or nullptr -> dt0      (KnotPoint.dt is Float64: src/knotpoint.jl:148-153)
     double dt0;
+    const double* t;     // per-knot time (N) or nullptr -> 0; read only by models that declare time_varying (KnotPoint.t)
     T* J;                // (N, n+m, n): per knot an n x (n+m) column-major matrix;  may be nullptr
                          // (error-state mode: nerr x (nerr+m) per knot instead)
     T* out;              // xdot or x+, (N, n);  may be nullptr
@@ -228,21 +229,21 @@ __device__ __forceinline__ void read_row(const T* zrow, T (&z)[NZ]) {
 
 // One role: evaluate the map for one knot with partials for the columns in CHUNK; write this role's share.
 template <class Model, int Q, class T, bool WITH_J, bool ERR, mask_t CHUNK, bool WRITE_OUT, int NTHR, int ROLL, int ISSUERS, bool VEC, int ES>
-__device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
+__device__ __forceinline__ void role_body(const Model& model, const T* zrow, T h, T t, T* jrow, T* orow, int tid) {
     constexpr int n = Model::n, m = Model::m, NZ = n + m;
     model.reset();                 // per-knot evaluation caches (e.g. Cartpole's stage-1 sincos) start empty
     T zreg[NZ];
     read_row<T, NZ, ES>(zrow, zreg);
     if constexpr (ERR) {
         auto zz = load_seeded_err<Model, T, CHUNK>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
-        auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h);
+        auto xn = integrate<Q, T, ROLL>(model, slice<0, n>(zz), slice<n, m>(zz), h, t);
         auto e = project_err<Model, T>(xn);
         images_free_barrier<NTHR, ISSUERS>(tid);
         put_cols<Model::nerr, CHUNK, VEC, ES>(e, jrow, rstd::make_index_sequence<size_t(Model::nerr + m)>{});
         if constexpr (WRITE_OUT) { if (orow) put_vals<ES>(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
     } else {
         auto zz = load_seeded<T, (WITH_J ? CHUNK : mask_t(0))>(zreg, rstd::make_index_sequence<size_t(NZ)>{});
-        auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h);
+        auto xn = integrate<Q, T, (WITH_J ? ROLL : 0)>(model, slice<0, n>(zz), slice<n, m>(zz), h, t);
         images_free_barrier<NTHR, ISSUERS>(tid);
         if constexpr (WITH_J) put_cols<n, CHUNK, VEC, ES>(xn, jrow, rstd::make_index_sequence<size_t(NZ)>{});
         if constexpr (WRITE_OUT) { if (orow) put_vals<ES>(xn, orow, rstd::make_index_sequence<size_t(n)>{}); }
@@ -254,12 +255,12 @@ template <int R, mask_t M0, mask_t... Ms> struct list_at<R, MaskList<M0, Ms...>>
 template <mask_t M0, mask_t... Ms> struct list_at<0, MaskList<M0, Ms...>> { static constexpr mask_t value = M0; };
 
 template <class Model, int Q, class T, bool WITH_J, bool ERR, class Chunks, int NTHR, int ROLL, int ISSUERS, bool VEC, int ES, int R = 0>
-__device__ __forceinline__ void dispatch_role(int role, const Model& model, const T* zrow, T h, T* jrow, T* orow, int tid) {
+__device__ __forceinline__ void dispatch_role(int role, const Model& model, const T* zrow, T h, T t, T* jrow, T* orow, int tid) {
     if constexpr (R + 1 == Chunks::count) {
-        role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, jrow, orow, tid);
+        role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, t, jrow, orow, tid);
     } else {
-        if (role == R) role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, jrow, orow, tid);
-        else dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, ISSUERS, VEC, ES, R + 1>(role, model, zrow, h, jrow, orow, tid);
+        if (role == R) role_body<Model, Q, T, WITH_J, ERR, list_at<R, Chunks>::value, R == 0, NTHR, ROLL, ISSUERS, VEC, ES>(model, zrow, h, t, jrow, orow, tid);
+        else dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, ISSUERS, VEC, ES, R + 1>(role, model, zrow, h, t, jrow, orow, tid);
     }
 }
 
@@ -401,11 +402,13 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         constexpr int ES = SOA ? TILE : 1;                     // element stride of the images
         T h = T(0);
         if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? (kt < cnt ? a.dt[k0 + kt] : 0.0) : a.dt0);
+        T tk = T(0);                                           // KnotPoint.t: only time-varying (user) models read it
+        if constexpr (uses_time<Model>::value) tk = T(a.t && kt < cnt ? a.t[k0 + kt] : 0.0);
         (void)cnt;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
         dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, S::ISSUERS, S::ROWSTORE && !SOA, ES>(
-            role, model, zrow, h, SOA ? j_img + kt : j_img + kt * S::PJ, want_o ? (SOA ? o_img + kt : o_img + kt * n) : nullptr, tid);
+            role, model, zrow, h, tk, SOA ? j_img + kt : j_img + kt * S::PJ, want_o ? (SOA ? o_img + kt : o_img + kt * n) : nullptr, tid);
         // (5) publish
         if (tma) {
             fence_proxy_async();
@@ -480,6 +483,10 @@ __global__ void __launch_bounds__(128) implicit_midpoint_kernel(const Model mode
     if (k >= a.N) return;
     const T* z = a.Z + k * NZ;
     const T h = T(a.dt ? a.dt[k] : a.dt0);
+    // the midpoint time t + h/2 of dynamics_error (src/integration.jl:652-653); the reference's Jacobian evaluates at t (:693), an
+    // inconsistency with its own residual that is not reproduced
+    T tm = T(0);
+    if constexpr (uses_time<Model>::value) tm = T(a.t ? a.t[k] : 0.0) + T(0.5) * h;
     const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
     T zm[NZ], x2[n], r[n], J1[n * NZ], A2[n * n], W[n * n];
 #pragma unroll
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(128) implicit_midpoint_kernel(const Model mode
         for (int i = 0; i < n; ++i) zm[i] = (z[i] + x2[i]) * T(0.5);
         model.reset();
         auto zz = load_seeded<T, ALL>(zm, rstd::make_index_sequence<size_t(NZ)>{});
-        auto f = model.f(slice<0, n>(zz), slice<n, m>(zz));
+        auto f = feval<T>(model, slice<0, n>(zz), slice<n, m>(zz), tm);
         put_vals(f, r, rstd::make_index_sequence<size_t(n)>{});
         put_cols<n, ALL, false>(f, J1, rstd::make_index_sequence<size_t(NZ)>{});
         T nrm = T(0);
@@ -603,6 +610,8 @@ __global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model
     const long long k = valid ? gtid / GS : a.N - 1;           // lanes past the end shadow the last knot (shuffles stay convergent)
     const T* zg = a.Z + k * NZ;
     const T h = T(a.dt ? a.dt[k] : a.dt0);
+    T tm = T(0);
+    if constexpr (uses_time<Model>::value) tm = T(a.t ? a.t[k] : 0.0) + T(0.5) * h;
     const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
     T z[NZ], zm[NZ], x2[n], Mf[n], Rf[n];
 #pragma unroll
@@ -616,7 +625,7 @@ __global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model
         for (int i = 0; i < n; ++i) zm[i] = (z[i] + x2[i]) * T(0.5);
         model.reset();
         auto zz = load_lane_seeded<T>(zm, col, rstd::make_index_sequence<size_t(NZ)>{});
-        auto f = model.f(slice<0, n>(zz), slice<n, m>(zz));
+        auto f = feval<T>(model, slice<0, n>(zz), slice<n, m>(zz), tm);
         T r[n], acol[n];
         put_vals(f, r, rstd::make_index_sequence<size_t(n)>{});
         put_cols<n, 1u, false>(f, acol, rstd::make_index_sequence<size_t(1)>{});     // column `col` of [A B]
@@ -654,25 +663,70 @@ __global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model
 
 // rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
 // (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
+//
+// Rows: knot k of trajectory j lives in row  j * sj + k * sk  of X (row width ldx), of dt and of t.
+//   trajectory-major (rdb_rollout):      sj = K, sk = 1, ldx = n, controls from U (rows j * uj + k * uk, width m)
+//   knot-major batch (rdb_trajectory_*): sj = 1, sk = ntraj, ldx = n + m, U == nullptr: the controls are read from the SAME rows
+//     (Z = [x; u] per knot, like the reference's rollout! that reads control(Z[k]) and writes state(Z[k+1])); adjacent threads own
+//     adjacent rows, so every step's stores and loads of a warp are one contiguous range.
+// Steps k in [kb, ke) are computed (x_{k+1} written for each); kb == 0 with x0 != nullptr also writes row 0.  Time: t[row] when
+// given, else accumulated from 0 (times of a SampledTrajectory built from dt, src/trajectories.jl:82-110).
+template <class T>
+struct RolloutArgs {
+    const T* x0;         // (ntraj, n) or nullptr: the states already in row 0 of X
+    const T* U;          // controls, or nullptr (Z mode)
+    const double* dt;    // per-row steps or nullptr -> dt0
+    const double* t;     // per-row times or nullptr
+    double dt0;
+    T* X;
+    long long ntraj;
+    int K, kb, ke;
+    long long sj, sk, uj, uk;
+    int ldx;
+};
 template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, rstd::index_sequence<Is...>) { return vec(p[Is]...); }
 template <class Model, int Q, class T>
-__global__ void __launch_bounds__(64) rollout_kernel(const Model model, const T* __restrict__ x0, const T* __restrict__ U,
-                                                     const double* __restrict__ dt, double dt0, T* __restrict__ X,
-                                                     long long ntraj, int K) {
+__global__ void __launch_bounds__(32) rollout_kernel(const Model model, const RolloutArgs<T> a) {
     constexpr int n = Model::n, m = Model::m;
     const long long tr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (tr >= ntraj) return;
-    auto x = load_plain(x0 + tr * n, rstd::make_index_sequence<size_t(n)>{});
-    T* Xt = X + tr * (long long)K * n;
-    put_vals(x, Xt, rstd::make_index_sequence<size_t(n)>{});
-    for (int k = 0; k + 1 < K; ++k) {
-        auto u = load_plain(U + (tr * (long long)(K - 1) + k) * m, rstd::make_index_sequence<size_t(m)>{});
-        const T h = T(dt ? dt[tr * K + k] : dt0);
+    if (tr >= a.ntraj) return;
+    const long long base = tr * a.sj;
+    T* X = a.X;
+    const T* Usrc = a.U ? a.U + tr * a.uj * m : X + base * a.ldx + n;          // controls of knot 0
+    const long long ustep = a.U ? a.uk * m : a.sk * (long long)a.ldx;
+    auto x = load_plain((a.kb == 0 && a.x0) ? a.x0 + tr * n : X + (base + a.kb * a.sk) * a.ldx, rstd::make_index_sequence<size_t(n)>{});
+    if (a.kb == 0 && a.x0) put_vals(x, X + base * a.ldx, rstd::make_index_sequence<size_t(n)>{});
+    T tacc = T(0);
+    if constexpr (uses_time<Model>::value) {
+        if (!a.t) { for (int k = 0; k < a.kb; ++k) tacc += T(a.dt ? a.dt[base + k * a.sk] : a.dt0); }
+    }
+    // software prefetch: the controls and step of knot k + 1 are requested before the arithmetic of knot k
+    T ucur[m];
+    double hcur = a.dt0;
+    if (a.kb < a.ke) {
+#pragma unroll
+        for (int i = 0; i < m; ++i) ucur[i] = Usrc[a.kb * ustep + i];
+        if (a.dt) hcur = a.dt[base + a.kb * a.sk];
+    }
+    for (int k = a.kb; k < a.ke; ++k) {
+        T unext[m];
+        double hnext = a.dt0;
+        const bool more = k + 1 < a.ke;
+#pragma unroll
+        for (int i = 0; i < m; ++i) unext[i] = more ? Usrc[(k + 1) * ustep + i] : T(0);
+        if (a.dt && more) hnext = a.dt[base + (k + 1) * a.sk];
+        auto u = load_plain(ucur, rstd::make_index_sequence<size_t(m)>{});
+        const T h = T(hcur);
+        T tk = tacc;
+        if constexpr (uses_time<Model>::value) { if (a.t) tk = T(a.t[base + k * a.sk]); }
         model.reset();
-        x = integrate<Q, T>(model, x, u, h);
-        put_vals(x, Xt + (long long)(k + 1) * n, rstd::make_index_sequence<size_t(n)>{});
+        x = integrate<Q, T>(model, x, u, h, tk);
+        put_vals(x, X + (base + (k + 1) * a.sk) * a.ldx, rstd::make_index_sequence<size_t(n)>{});
+        tacc += h;
+#pragma unroll
+        for (int i = 0; i < m; ++i) ucur[i] = unext[i];
+        hcur = hnext;
     }
 }
-
 
 }  // namespace rdb

@@ -1,5 +1,6 @@
 // launch.cuh — per-(model, dtype) tiling configuration and the host-side launcher of knot_kernel.
 #pragma once
+#include <atomic>
 #include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link dependency)
 #include "kernels.cuh"
 
@@ -23,7 +24,9 @@ template <class Model, class T, bool WITH_J, int Q, class Enable = void>
 struct KnotConfigDefault {   // small models (Cartpole, double integrators) and every value-only kernel: one role.
     // Jacobians of small models: single-warp CTAs (TILE 32), 12 per SM — warps drift apart instead of hitting the FP64-heavy and
     // FP64-free phases of a tile in lockstep (Cartpole RK4 fp64: 47.5 -> 45.1 us, profiles/tuning_r01.md).
-    static constexpr int TILE = WITH_J ? 32 : 128, MINB = WITH_J ? 12 : 4, ROLL = 0;
+    // Round 2 (elemental Cartpole, 112 registers): 64-knot tiles, 8 CTAs per SM measured best (38.3 us against 39.4 us for the
+    // single-warp form, 45 us with 18 CTAs of 96 registers + spills; profiles/tuning_r02.md).
+    static constexpr int TILE = WITH_J ? 64 : 128, MINB = WITH_J ? 8 : 4, ROLL = 0;
     using Chunks = MaskList<WITH_J ? range_mask(0, Model::n + Model::m) : mask_t(0)>;
 };
 // Rigid bodies with Jacobians.  Measured on B200 (profiles/tuning_r01.md): few wide roles beat many narrow ones (every role
@@ -184,19 +187,23 @@ struct KnotLaunch {
     // ld: knots per component row of the caller's arrays (component-major kernels only)
     static int run(const Model& model, const KnotArgs<T>& a, const DeviceInfo& dev, cudaStream_t st, long long ld = 0) {
         auto kern = knot_kernel<Model, Q, T, Cfg::TILE, WITH_J, typename Cfg::Chunks, Cfg::MINB, Cfg::ROLL, ERR, SOA>;
-        static int occ_cache[64];   // CTAs/SM per device id; 0 = not yet configured on that device
+        // CTAs/SM per device id; 0 = not yet configured on that device.  Atomic: two host threads may race on the first use of a
+        // kernel — both then set the same attribute and store the same value (idempotent), and nobody reads a torn entry.
+        static std::atomic<int> occ_cache[64];
         const int d = dev.device & 63;
-        if (occ_cache[d] == 0) {
+        int occ_d = occ_cache[d].load(std::memory_order_acquire);
+        if (occ_d == 0) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::total));
             if (e != cudaSuccess) return int(e);
             int occ = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHR, S::total);
             if (e != cudaSuccess) return int(e);
-            occ_cache[d] = occ > 0 ? occ : 1;
+            occ_d = occ > 0 ? occ : 1;
+            occ_cache[d].store(occ_d, std::memory_order_release);
         }
         if (a.N <= 0) return 0;
         const long long ntiles = (a.N + Cfg::TILE - 1) / Cfg::TILE;
-        const long long cap = (long long)dev.sm_count * occ_cache[d];
+        const long long cap = (long long)dev.sm_count * occ_d;
         const unsigned grid = unsigned(ntiles < cap ? ntiles : cap);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = S::total; cfg.stream = st;
@@ -231,9 +238,12 @@ struct KnotRequest {
     int err;             // error-state Jacobian  G(x+)' [A B] blkdiag(G(x), I)  (rigid bodies; needs with_j)
     ModelParams<double> params;
     const void* Z; const double* dt; double dt0; void* J; void* out; long long N;   // knot-major, or component-major when soa != 0
+    const double* t;         // per-knot times (N) or null; only time-varying (user) models read them
     int soa; long long ld;   // component-major arrays with ld knots per component row, served by the tensor-map kernels
-    // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)
+    // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)   [trajectory-major, zmode == 0]
+    //             zmode != 0: X is the knot-major batch Z (K, ntraj, n+m) holding the controls; steps [kb, ke)   (kernels.cuh)
     const void* x0; const void* U; void* X; long long ntraj; int K;
+    int zmode, kb, ke;
     DeviceInfo dev;
     cudaStream_t stream;
 };
@@ -254,7 +264,7 @@ template <template <class> class ModelT, class T, int Q, bool WITH_J, bool ERR =
 inline int run_one(const KnotRequest& r) {
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
-    a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
+    a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0; a.t = r.t;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.soa) {
         if constexpr (RDB_SOA_KERNELS) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, true>::run(model, a, r.dev, r.stream, r.ld);
@@ -270,7 +280,7 @@ inline int run_implicit(const KnotRequest& r) {
     if (r.op != OP_KNOT || r.err) return -2;
     ModelT<T> model; model.p = cast_params<T>(r.params);
     KnotArgs<T> a;
-    a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0;
+    a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0; a.t = r.t;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
     if constexpr (ModelT<T>::n >= RDB_IMPLICIT_WARP_MIN_N && ModelT<T>::n + ModelT<T>::m <= 32) {
@@ -286,15 +296,24 @@ inline int run_implicit(const KnotRequest& r) {
     }
     return int(cudaGetLastError());
 }
+template <class T>
+inline RolloutArgs<T> rollout_args(const KnotRequest& r, int n, int m) {
+    RolloutArgs<T> a;
+    a.x0 = static_cast<const T*>(r.x0); a.U = static_cast<const T*>(r.U); a.dt = r.dt; a.t = r.t; a.dt0 = r.dt0;
+    a.X = static_cast<T*>(r.X); a.ntraj = r.ntraj; a.K = r.K;
+    if (r.zmode) { a.kb = r.kb; a.ke = r.ke; a.sj = 1; a.sk = r.ntraj; a.uj = 0; a.uk = 0; a.ldx = n + m; a.U = nullptr; }
+    else { a.kb = 0; a.ke = r.K - 1; a.sj = r.K; a.sk = 1; a.uj = r.K - 1; a.uk = 1; a.ldx = n; }
+    return a;
+}
 template <template <class> class ModelT, class T, int Q>
 inline int run_rollout(const KnotRequest& r) {
     if constexpr (Q == Q_CONTINUOUS) return -2;
     else {
         ModelT<T> model; model.p = cast_params<T>(r.params);
         if (r.ntraj <= 0 || r.K <= 0) return 0;
-        const unsigned grid = unsigned((r.ntraj + 63) / 64);
-        rollout_kernel<ModelT<T>, Q, T><<<grid, 64, 0, r.stream>>>(model, static_cast<const T*>(r.x0), static_cast<const T*>(r.U),
-                                                                  r.dt, r.dt0, static_cast<T*>(r.X), r.ntraj, r.K);
+        // single-warp CTAs: 4096 trajectories = 128 warps, one per SM (the sweep is latency-bound: every warp gets a scheduler to itself)
+        const unsigned grid = unsigned((r.ntraj + 31) / 32);
+        rollout_kernel<ModelT<T>, Q, T><<<grid, 32, 0, r.stream>>>(model, rollout_args<T>(r, ModelT<T>::n, ModelT<T>::m));
         return int(cudaGetLastError());
     }
 }

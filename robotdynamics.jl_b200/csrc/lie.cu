@@ -7,6 +7,7 @@
 //   state_diff           reference: src/liestate.jl:210-260 (vector parts x - x0, rotations Cayley error of q0\q)
 //
 // Here the attitude IS normalised (default R(w,x,y,z) constructor), unlike inside dynamics.
+#include <atomic>
 #include "lie.h"
 #include "kernels.cuh"   // mbarrier / bulk-copy PTX helpers
 
@@ -77,13 +78,20 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
     constexpr int n = 9 + NP, ne = 12, PER = n * ne;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* img[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw) + TILE * PER};
-    for (int e = threadIdx.x; e < 2 * TILE * PER; e += TILE) {
-        const int r = e % PER, j = r / n, i = r - j * n;
-        img[0][e] = (i < 3) ? T(j == i) : (i < 3 + NP) ? T(0) : T(j == i - NP + 3);
+    const long long ntiles = (N + TILE - 1) / TILE;
+    // structural 0/1 pattern: every thread writes its own knot's row with compile-time indices (no div/mod; the round-1 form, a
+    // strided loop over both images with two integer divisions per element, cost ~30 us per launch whatever N was); the second
+    // image only if this CTA has a second tile
+    const int nimg = (blockIdx.x + (long long)gridDim.x < ntiles) ? 2 : 1;
+    for (int b = 0; b < nimg; ++b) {
+        T* row = img[b] + threadIdx.x * PER;
+#pragma unroll
+        for (int j = 0; j < ne; ++j)
+#pragma unroll
+            for (int i = 0; i < n; ++i) row[i + n * j] = (i < 3) ? T(j == i) : (i < 3 + NP) ? T(0) : T(j == i - NP + 3);
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const long long ntiles = (N + TILE - 1) / TILE;
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const long long k0 = tile * TILE;
@@ -221,8 +229,15 @@ int lie_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const 
         const long long ntiles = (N + TILE - 1) / TILE, cap = (long long)sm_count * 2;
         const unsigned g = unsigned(ntiles < cap ? ntiles : cap);
         auto go = [&](auto kern, auto* x, auto* out) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            if (e != cudaSuccess) return int(e);
+            static std::atomic<unsigned long long> configured{0};          // one bit per device: the attribute is set once, not per call
+            int dev = 0;
+            cudaGetDevice(&dev);
+            const unsigned long long bit = 1ull << (dev & 63);
+            if (!(configured.load(std::memory_order_acquire) & bit)) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                if (e != cudaSuccess) return int(e);
+                configured.fetch_or(bit, std::memory_order_release);
+            }
             kern<<<g, TILE, smem, st>>>(rot, N, x, ldx, out);
             return int(cudaGetLastError());
         };

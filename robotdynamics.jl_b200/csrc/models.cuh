@@ -45,26 +45,46 @@ struct Cartpole {
     mutable T th0, s0, c0;
     mutable bool cached;
     RDB_HD void reset() const { cached = false; }
+    // qdd(theta, w, u) is ONE elemental operation: values on plain scalars, its 2 x 3 local Jacobian by hand (the reference ships the
+    // same thing as its UserDefined analytic Jacobian, test/cartpole_model.jl:57-96), partials by chain() — 14 FMAs per stage for the
+    // three live columns {theta, w, u} where forward mode through every intermediate of the 2x2 solve spends ~70 (the C2 kernel is
+    // co-limited by the FP64 pipe).  Equal to ForwardDiff to rounding (parity tests: 1e-10 against a dense Dual-number restatement of the reference path).
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const {
+        const auto& th = get<1>(x);
         const auto& qd0 = get<2>(x);
         const auto& qd1 = get<3>(x);
-        auto th = get<1>(x);
-        T sv, cv;
-        if (!cached) { sincos_(val(th), sv, cv); th0 = val(th); s0 = sv; c0 = cv; cached = true; }
-        else sincos_near(val(th), th0, s0, c0, sv, cv);
-        auto s = th, c = th;
-        sincos_with(th, sv, cv, s, c);
-        // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s qd1^2 - u, mp g l s];  qdd = -H \\ r  (closed-form 2x2 solve,
-        // like StaticArrays).  Both sides are divided by mp*l first, so the off-diagonal of H is just c and no partial is ever
-        // multiplied by that constant:  H' = [(mc+mp)/(mp l)  c; c  l],  r' = [-s qd1^2 - u/(mp l), g s].
-        const T ia = p.cp_ia, H00 = p.cp_H00, H11 = p.l;
-        auto r0 = fmadd<T, -1>(ia, get<0>(u), -(s * sq_(qd1)));
-        auto r1 = p.g * s;
-        auto idet = T(1) / sqadd<T, -1>(c, H00 * H11);
-        auto qdd1 = fmadd<T, -1>(H00, r1, c * r0) * idet;
-        auto qdd0 = fmadd<T>(c, qdd1, r0) * p.cp_nH00i;          // first row of H' qdd = -r' (H00 is a constant)
-        return vec(qd0, qd1, qdd0, qdd1);
+        const auto& uu = get<0>(u);
+        const T thv = val(th), w = val(qd1), uv = val(uu);
+        T s, c;
+        if (!cached) { sincos_(thv, s, c); th0 = thv; s0 = s; c0 = c; cached = true; }
+        else sincos_near(thv, th0, s0, c0, s, c);
+        // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s w^2 - u, mp g l s];  qdd = -H \ r  (closed-form 2x2 solve, like
+        // StaticArrays).  Both sides divided by mp*l:  H' = [H00  c; c  l],  r' = [-s w^2 - u/(mp l), g s],  H00 = (mc+mp)/(mp l).
+        const T ia = p.cp_ia, H00 = p.cp_H00, k = p.cp_nH00i, g = p.g;
+        const T w2 = w * w;
+        const T r0 = -(s * w2) - ia * uv;
+        const T r1 = g * s;
+        const T iD = T(1) / (H00 * p.l - c * c);
+        const T q1 = (c * r0 - H00 * r1) * iD;                   // qdd1
+        const T q0 = k * (c * q1 + r0);                          // qdd0: first row of H' qdd = -r'
+        using In = decltype(vec(th, qd1, uu));
+        if constexpr (!has_partials<T, In>()) return vec(qd0, qd1, q0, q1);
+        else {
+            // d/dtheta: s' = c, c' = -s;  d/dw: r0' = -2 s w;  d/du: r0' = -1/(mp l)
+            const T r0t = -(c * w2);
+            const T q1t = ((c * r0t - s * r0 - (H00 * g) * c) - q1 * (T(2) * c * s)) * iD;
+            const T q0t = k * (c * q1t - s * q1 + r0t);
+            const T r0w = T(-2) * s * w;
+            const T ciD = c * iD;
+            const T q1w = ciD * r0w;
+            const T q0w = k * (c * q1w + r0w);
+            const T q1u = -(ia * ciD);
+            const T q0u = k * (c * q1u - ia);
+            const T d0[3] = {q0t, q0w, q0u}, d1[3] = {q1t, q1w, q1u};
+            const auto in = vec(th, qd1, uu);
+            return vec(qd0, qd1, chain<T>(q0, d0, in), chain<T>(q1, d1, in));
+        }
     }
 };
 

@@ -203,6 +203,10 @@ template <class T, class X> struct opnd {                        // plain scalar
     static constexpr mask_t mask = 0;
     RDB_HD static T v(const X& x) { return x; }
 };
+template <class T> struct opnd<T, Zero> {                        // structural zero operand
+    static constexpr mask_t mask = 0;
+    RDB_HD static T v(const Zero&) { return T(0); }
+};
 template <class T, mask_t M> struct opnd<T, SD<T, M>> {
     static constexpr mask_t mask = M;
     RDB_HD static T v(const SD<T, M>& x) { return x.v; }
@@ -339,13 +343,15 @@ template <class T, mask_t A>
 RDB_HD SD<T, A> rsqrt_(const SD<T, A>& a) {   // a^(-1/2);  d = -1/2 a^(-3/2) da
     const T r = rsqrt_(a.v); return scale_parts<T, A>(a, r, T(-0.5) * r / a.v);
 }
-// max(0, a): ForwardDiff compares values; derivative is 0 when the clamp is active or at exactly 0
-// (reference: test/quadrotor.jl:67-70).
-RDB_HD float relu_(float a) { return a > 0.0f ? a : 0.0f; }
-RDB_HD double relu_(double a) { return a > 0.0 ? a : 0.0; }
+// max(0, a) as the reference's Quadrotor writes it (test/quadrotor.jl:67-70).  Under ForwardDiff `max(0, d)` promotes the 0 to a
+// Dual and returns `ifelse(d < 0, 0, d)` (Base.max(x::T, y::T) = ifelse(isless(y, x), x, y); DiffRules' rule for max(x, y) gives the
+// same: d/dy = (x > y ? 0 : 1)): the clamp is active only for a < 0, and AT the tie a == 0 the result is `a` itself, partials kept.
+// A zero control (the common initial guess) therefore has d relu/da = 1, not 0.
+RDB_HD float relu_(float a) { return a < 0.0f ? 0.0f : a; }
+RDB_HD double relu_(double a) { return a < 0.0 ? 0.0 : a; }
 template <class T, mask_t A>
 RDB_HD SD<T, A> relu_(const SD<T, A>& a) {
-    SD<T, A> r; const bool on = a.v > T(0); r.v = on ? a.v : T(0); for (int i = 0; i < SD<T, A>::NS; ++i) r.d[i] = PK<T>::sel(on, a.d[i]); return r;
+    SD<T, A> r; const bool on = !(a.v < T(0)); r.v = on ? a.v : T(0); for (int i = 0; i < SD<T, A>::NS; ++i) r.d[i] = PK<T>::sel(on, a.d[i]); return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -404,6 +410,45 @@ template <class T, class A> RDB_HD auto mat3_mul(const T* M, const A& x) {
                fmadd<T>(M[5], get<2>(x), fmadd<T>(M[4], get<1>(x), M[3] * get<0>(x))),
                fmadd<T>(M[8], get<2>(x), fmadd<T>(M[7], get<1>(x), M[6] * get<0>(x))));
 }
+
+// ---------------------------------------------------------------------------------------------
+// Elemental operations with hand-written local derivatives.
+//   chain<T>(v, c, in):  the number with value v and partials  sum_i c[i] * d(in_i)   (in: a Vec of plain / SD / Zero elements).
+// A model can evaluate a block of its formulas on plain values, compute the block's local Jacobian by hand (like the reference's
+// UserDefined analytic Jacobians, test/cartpole_model.jl:57-96) and hand both to chain(): one FMA per (output, input, partial)
+// instead of forward mode through every intermediate.  With plain inputs chain() returns v and the local derivatives are dead code.
+// ---------------------------------------------------------------------------------------------
+template <class V, int I> using elem_t = rstd::remove_cv_t<rstd::remove_reference_t<decltype(get<I>(rstd::declval<const V&>()))>>;
+template <class T, class V, int I = 0> __host__ __device__ constexpr mask_t vec_mask() {
+    if constexpr (I == V::size) return 0; else return opnd<T, elem_t<V, I>>::mask | vec_mask<T, V, I + 1>();
+}
+template <class T, int J, int I, bool HAVE, class V>
+RDB_HD typename PK<T>::vec chain_acc(const T* c, const V& in, typename PK<T>::vec acc) {
+    if constexpr (I == V::size) return acc;
+    else {
+        using E = elem_t<V, I>;
+        if constexpr (chas(smask<T>(opnd<T, E>::mask), J)) {
+            const auto s = opnd<T, E>::template slot<J>(get<I>(in));
+            if constexpr (HAVE) return chain_acc<T, J, I + 1, true>(c, in, PK<T>::fma(s, PK<T>::splat(c[I]), acc));
+            else return chain_acc<T, J, I + 1, true>(c, in, PK<T>::mul(s, PK<T>::splat(c[I])));
+        } else return chain_acc<T, J, I + 1, HAVE>(c, in, acc);
+    }
+}
+template <class T, mask_t R, class V, int J = 0>
+RDB_HD void chain_parts(SD<T, R>& r, const T* c, const V& in) {
+    constexpr mask_t SR = smask<T>(R);
+    if constexpr ((SR >> J) != 0) {
+        if constexpr (chas(SR, J)) r.d[cslot(SR, J)] = chain_acc<T, J, 0, false>(c, in, PK<T>::zero());
+        chain_parts<T, R, V, J + 1>(r, c, in);
+    }
+}
+template <class T, class V>
+RDB_HD auto chain(T v, const T* c, const V& in) {
+    constexpr mask_t R = vec_mask<T, V>();
+    if constexpr (R == 0) return v;
+    else { SD<T, R> r; r.v = v; chain_parts<T, R, V>(r, c, in); return r; }
+}
+template <class T, class V> __host__ __device__ constexpr bool has_partials() { return vec_mask<T, V>() != 0; }
 
 // ---------------------------------------------------------------------------------------------
 // Seeding and extraction.

@@ -75,12 +75,12 @@ VARIANTS = {
     },
     "cartpole": {
         "base": {},
-        "dense": dict(RDB_TUNE_ROWSTORE=0),
         "t32_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16),
         "t32_minb14": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=14),
-        "t32_minb10": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=10),
-        "t64_minb6": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=6),
+        "t32_minb18": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=18),
         "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
+        "t64_minb7": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=7),
+        "roll1_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16, RDB_TUNE_ROLL=1),
     },
     "satellite": {
         "base": {},

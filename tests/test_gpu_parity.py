@@ -119,6 +119,26 @@ def test_empty_batch_and_argument_errors(rd, torch_):
         gm._h.discrete_jacobian(o.RK4, np.zeros((4, 5), dtype=np.float16), 0.01)
     with pytest.raises(rd.NotImplementedModelError):
         rd.DoubleIntegrator(4)
+    # caller-supplied buffers are validated before their bare pointers reach the C ABI (a float32 or short J would otherwise be
+    # an out-of-bounds write of N * 20 * sizeof(double) bytes)
+    Z = np.random.default_rng(0).random((8, 5))
+    with pytest.raises(TypeError):
+        gm._h.discrete_jacobian(o.RK4, Z, 0.01, J=np.empty((8, 5, 4), dtype=np.float32))
+    with pytest.raises(ValueError):
+        gm._h.discrete_jacobian(o.RK4, Z, 0.01, J=np.empty((7, 5, 4)))
+    with pytest.raises(ValueError):
+        gm._h.discrete_jacobian(o.RK4, Z, np.full(7, 0.01))              # dt vector shorter than the batch
+    with pytest.raises(ValueError):
+        gm._h.discrete_jacobian(o.RK4, Z, 0.01, xn=np.empty((8, 5)))
+    with pytest.raises(ValueError):
+        gm._h.discrete_jacobian(o.RK4, Z, 0.01, J=np.empty((8, 4, 5)).transpose(0, 2, 1))     # right shape, not contiguous
+    with pytest.raises(TypeError):
+        gm._h.rollout(o.RK4, Z[:, :4].copy(), np.zeros((8, 3, 1), dtype=np.float32), 0.01)    # U dtype differs from x0
+    with pytest.raises(ValueError):
+        gm._h.rollout(o.RK4, Z[:, :4].copy(), np.zeros((8, 3, 1)), np.full((8, 3), 0.01))     # dt must be (ntraj, K)
+    with pytest.raises(TypeError):                                       # one DynamicsJacobian cannot receive a trajectory's Jacobians
+        rd.jacobian_(rd.StaticReturn(), rd.ForwardAD(), rd.DiscretizedDynamics(gm, rd.RK4), rd.DynamicsJacobian(4, 1), None,
+                     rd.SampledTrajectory(Z[:, :4], Z[:, 4:], 0.01))
 
 
 def test_terminal_knots_and_per_knot_dt(rd, torch_):
@@ -136,14 +156,16 @@ def test_terminal_knots_and_per_knot_dt(rd, torch_):
 
 
 def test_quadrotor_clamp_kink(rd):
-    """max(0, kf w): zero derivative when clamped and at exactly 0; yaw moment unclamped (test/quadrotor.jl:67-70,86-95)."""
+    """max(0, kf w): zero derivative when clamped (w < 0), partials KEPT at the tie w == 0 (ForwardDiff / Base.max semantics);
+    yaw moment unclamped (test/quadrotor.jl:67-70,86-95)."""
     gm, om = rd.Quadrotor(), o.quadrotor()
     Z = rand_inputs(13, 4, 64, np.random.default_rng(6))
     Z[:, 13] = -0.3; Z[:, 14] = 0.0
     for dtype in (np.float64, np.float32):
         J = gm._h.jacobian(Z.astype(dtype))
         Jm = o.as_matrix(J)
-        assert np.all(Jm[:, 7:10, 13:15] == 0) and np.all(Jm[:, 10:12, 13:15] == 0)
+        assert np.all(Jm[:, 7:10, 13] == 0) and np.all(Jm[:, 10:12, 13] == 0)
+        assert np.any(Jm[:, 7:10, 14] != 0) and np.allclose(Jm[:, 7:10, 14], Jm[:, 7:10, 15], rtol=1e-5)     # tie == active
         assert np.abs(J - o.jacobian(om, Z.astype(dtype).astype(np.float64))).max() < TOL[dtype] * 100
 
 
@@ -411,7 +433,7 @@ def test_device_trajectory_and_rollout_linearize(rd, torch_):
     rng = np.random.default_rng(71)
     K = 65
     Zh = rd.SampledTrajectory(rand_inputs(13, 4, K, rng)[:, :13], 0.5 + rng.random((K - 1, 4)), dt=0.02)
-    Zd = rd.DeviceTrajectory(Zh)
+    Zd = rd.DeviceTrajectory(model, Zh)
     J = torch_.zeros((K, 17, 13), dtype=torch_.float64, device="cuda")
     y = torch_.zeros((K, 13), dtype=torch_.float64, device="cuda")
     rd.jacobian_(rd.StaticReturn(), rd.B200(), dmodel, J, y, Zd)
@@ -437,6 +459,107 @@ def test_device_trajectory_and_rollout_linearize(rd, torch_):
     assert np.abs(Jt.cpu().numpy().reshape(-1, 17, 13) - o.discrete_jacobian(om, o.RK4, Zo, 0.02)).max() < 1e-8
     Xh, Jh = rd.rollout_and_linearize(dmodel, x0, U, 0.02, error_state=True)        # host arrays, error-state form
     assert Jh.shape == (ntraj, K - 1, 16, 12) and np.abs(Xh - Xo).max() < 1e-10 * max(1.0, np.abs(Xo).max())
+
+
+@pytest.mark.parametrize("name,dtype", [("cartpole", np.float64), ("quad_quat_world", np.float32), ("body_mrp_body", np.float64)])
+def test_trajectory_batch_rollout_linearize(rd, torch_, name, dtype):
+    """rdb_trajectory_*: the device trajectory of the C ABI.  Rollout in place (knot-major batch), Jacobians of every knot, and the
+    chunk-pipelined rollout + linearisation on two streams — against the CPU checker, for host and device outputs, scalar and
+    per-knot steps, full-state and error-state Jacobians."""
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    n, m = om.n, om.m
+    dm = rd.DiscretizedDynamics(gm, rd.RK4)
+    rng = np.random.default_rng(150)
+    ntraj, K = 70, 37
+    x0 = rand_inputs(n, m, ntraj, rng)[:, :n].astype(dtype)
+    U = (0.4 * rng.random((K - 1, ntraj, m))).astype(dtype)
+    dts = rng.uniform(0.005, 0.03, (K, ntraj))
+    tol = TOL[dtype] * (1 if dtype == np.float64 else 3)
+    for dt in (0.02, dts):
+        tb = rd.TrajectoryBatch(dm, ntraj, K, dtype)
+        tb.set_initial_state(x0); tb.set_controls(U); tb.set_timesteps(dt)
+        Zv, tv, dv = tb.views()
+        dt_ref = dv.cpu().numpy()                                              # (K, ntraj): terminal step forced to 0
+        assert np.all(dt_ref[-1] == 0) and np.allclose(tv.cpu().numpy()[1:], np.cumsum(dt_ref[:-1], axis=0))
+        assert np.all(Zv.cpu().numpy()[-1, :, n:] == 0)                       # no terminal control
+        tb.rollout()
+        X = tb.states()
+        Xo = o.rollout(om, o.RK4, x0.astype(np.float64), np.transpose(U, (1, 0, 2)).astype(np.float64), np.ascontiguousarray(dt_ref.T))
+        assert np.abs(np.transpose(X, (1, 0, 2)) - Xo).max() < tol * max(1.0, np.abs(Xo).max())
+        Zall = Zv.cpu().numpy().reshape(K * ntraj, n + m)
+        ref = o.discrete_jacobian(om, o.RK4, Zall.astype(np.float64), dt_ref.reshape(-1)).reshape(K, ntraj, n + m, n)
+        Jd = tb.linearize()                                                   # device output
+        xn = np.empty((K, ntraj, n), dtype=dtype)
+        Jh = tb.linearize(J=np.empty((K, ntraj, n + m, n), dtype=dtype), xn=xn, device=False)     # device inputs, HOST outputs
+        assert np.abs(Jd.cpu().numpy() - ref).max() < tol and np.array_equal(Jh, Jd.cpu().numpy())
+        assert np.abs(xn[:-1] - X[1:]).max() < tol * max(1.0, np.abs(Xo).max())
+        eye = np.concatenate([np.eye(n), np.zeros((m, n))])                    # terminal knots: J = [I 0] (src/knotpoint.jl:57-67)
+        assert np.abs(Jh[-1] - eye).max() == 0
+        # the pipelined forward pass + linearisation from scratch, several chunkings: same states, same Jacobians
+        for chunks in (0, 1, 5, K + 3):
+            tb2 = rd.TrajectoryBatch(dm, ntraj, K, dtype)
+            tb2.set_initial_state(dev(torch_, x0)); tb2.set_controls(dev(torch_, U)); tb2.set_timesteps(dt if np.ndim(dt) == 0 else dev(torch_, dt))
+            J2 = tb2.rollout_linearize(chunks=chunks)
+            torch_.cuda.synchronize()
+            assert np.array_equal(tb2.states(), X) and np.array_equal(J2.cpu().numpy(), Jh), chunks
+        Jp = tb.rollout_linearize(device=False)                                # host Jacobians
+        assert np.array_equal(Jp, Jh)
+        if name != "cartpole":
+            Jb = tb.rollout_linearize(error_state=True)
+            refb = _error_jacobian_ref(om, o.RK4, Zall.astype(np.float64), dt_ref.reshape(-1))
+            assert np.abs(o.as_matrix(Jb.cpu().numpy().reshape(K * ntraj, 12 + m, 12)) - refb).max() < tol * 3
+    # setters: states / controls round trip, shape and dtype errors
+    Xs = rng.random((K, ntraj, n)).astype(dtype)
+    tb.set_states(Xs)
+    assert np.array_equal(tb.states(), Xs) and np.array_equal(tb.controls()[:-1], U)
+    with pytest.raises(ValueError):
+        tb.set_states(Xs[:-1])
+    with pytest.raises(rd.RDBError):
+        rd._abi.check(rd._abi.lib().rdb_trajectory_set_controls(tb._t._p, Xs.ctypes.data, K - 2, None), "bad knot count")
+
+
+def test_plans_and_time_varying_trajectory(rd, torch_):
+    """rdb_plan_*: a pre-validated launch equals the direct call bit for bit, replays under CUDA-graph capture and follows the buffer
+    contents; and a time-varying user model rolled out on a device trajectory sees the trajectory's own time grid."""
+    gm = rd.Quadrotor()
+    N = 777
+    Z = dev(torch_, rand_inputs(13, 4, N, np.random.default_rng(160)).astype(np.float32))
+    ref = gm._h.discrete_jacobian(rd.RK4.code, Z, 0.01)
+    plan = rd._abi.Plan(gm._h, rd._abi.OP_DISCRETE_JACOBIAN, rd.RK4.code, Z, 0.01)
+    assert torch_.equal(plan.launch(), ref)
+    eplan = rd._abi.Plan(gm._h, rd._abi.OP_DISCRETE_ERROR_JACOBIAN, rd.RK4.code, Z, 0.01)
+    assert torch_.equal(eplan.launch(), gm._h.discrete_error_jacobian(rd.RK4.code, Z, 0.01))
+    vplan = rd._abi.Plan(gm._h, rd._abi.OP_DISCRETE_DYNAMICS, rd.RK4.code, Z, 0.01)
+    assert torch_.equal(vplan.launch(), gm._h.discrete_dynamics(rd.RK4.code, Z, 0.01))
+    g = torch_.cuda.CUDAGraph()
+    st = torch_.cuda.Stream()
+    with torch_.cuda.stream(st):
+        plan.launch(); torch_.cuda.synchronize()
+        with torch_.cuda.graph(g, stream=st):
+            plan.launch()
+    Z.mul_(0.5); Z[:, 3:7] *= 2.0                                           # new contents, same buffers
+    plan.J.zero_(); g.replay(); torch_.cuda.synchronize()
+    assert torch_.equal(plan.J, gm._h.discrete_jacobian(rd.RK4.code, Z, 0.01))
+    with pytest.raises(rd.RDBError):
+        rd._abi.Plan(gm._h, rd._abi.OP_DISCRETE_JACOBIAN, rd.RK4.code, Z.cpu().numpy(), 0.01)      # plans are for device data
+    # time-varying user model on a device trajectory: stage times come from the trajectory's time grid (t0 + cumsum(dt))
+    p0, t0, h = 1.7, 0.25, 0.04
+    tv = rd.CustomModel(2, 1, TV_BODY, params=[p0])
+    dm = rd.DiscretizedDynamics(tv, rd.RK4)
+    rng = np.random.default_rng(161)
+    ntraj, K = 9, 11
+    x0, U = rng.random((ntraj, 2)), rng.random((K - 1, ntraj, 1))
+    tb = rd.TrajectoryBatch(dm, ntraj, K)
+    tb.set_initial_state(x0); tb.set_controls(U); tb.set_timesteps(h, t0=t0)
+    J = tb.rollout_linearize(chunks=3, device=False)
+    X = tb.states()
+    for j in range(ntraj):
+        x = x0[j].copy()
+        for k in range(K - 1):
+            z = np.r_[x, U[k, j]]
+            assert np.abs(J[k, j].T - _cs_jac(lambda zz: _tv_step(o.RK4, zz, t0 + h * k, h, p0), z)).max() < 1e-10
+            x = _tv_step(o.RK4, z, t0 + h * k, h, p0)
+            assert np.abs(X[k + 1, j] - x).max() < 1e-12
 
 
 # ---- user-defined models (SURVEY §8f row 4) -----------------------------------------------------------------------------------------
@@ -515,6 +638,85 @@ def test_user_defined_models(rd, torch_):
     with pytest.raises(rd.RDBError) as e:
         rd.CustomModel(2, 1, "return vec(get<1>(x), nope);")
     assert e.value.code == rd._abi.ERR_COMPILE and "nope" in str(e.value)
+
+
+# ---- time-varying user models: dynamics(model, x, u, t) with the reference's stage times ---------------------------------------------
+TV_BODY = """
+        auto drive = cos_(T(3) * t) * get<0>(u);
+        return vec(get<1>(x), drive - p[0] * sin_(get<0>(x)) + t * get<1>(x));
+"""
+
+
+def _tv_f(x, u, t, p0):
+    return np.array([x[1], np.cos(3 * t) * u[0] - p0 * np.sin(x[0]) + t * x[1]])
+
+
+def _tv_step(rule, z, t, h, p0):
+    """one step with the stage times of src/integration.jl:73-76 (Euler), :130-135 (RK3), :280-286 (RK4); RK2 = explicit midpoint"""
+    x, u = z[:2], z[2:]
+    f = lambda xx, tt: _tv_f(xx, u, tt, p0)
+    if rule == o.EULER:
+        return x + h * f(x, t)
+    if rule == o.RK2:
+        return x + h * f(x + h / 2 * f(x, t), t + h / 2)
+    if rule == o.RK3:
+        k1 = f(x, t) * h; k2 = f(x + k1 / 2, t + h / 2) * h; k3 = f(x - k1 + 2 * k2, t + h) * h
+        return x + (k1 + 4 * k2 + k3) / 6
+    k1 = f(x, t) * h; k2 = f(x + k1 / 2, t + h / 2) * h; k3 = f(x + k2 / 2, t + h / 2) * h; k4 = f(x + k3, t + h) * h
+    return x + (k1 + 2 * k2 + 2 * k3 + k4) / 6
+
+
+def _cs_jac(fun, z):
+    zc = z.astype(complex)
+    return np.stack([np.imag(fun(zc + 1e-30j * np.eye(len(z))[j])) / 1e-30 for j in range(len(z))], axis=1)
+
+
+def test_time_varying_user_model(rd, torch_):
+    """`t` reaches user models exactly as the reference feeds it: dynamics(model, x, u, t) (src/dynamics.jl:81-83), RK stages at
+    t, t+h/2, t+h/2, t+h (src/integration.jl:281-284), never differentiated.  Checked by complex step of an independent numpy
+    statement, for every explicit rule, host and device pointers, per-knot t and dt, and through rollout."""
+    p0 = 1.7
+    tv = rd.CustomModel(2, 1, TV_BODY, params=[p0])
+    rng = np.random.default_rng(140)
+    N = 333
+    Z, t, dt = rng.random((N, 3)), rng.uniform(0.0, 5.0, N), rng.uniform(0.01, 0.1, N)
+    # continuous dynamics and Jacobian at time t
+    xd = tv._h.dynamics(Z, t=t)
+    Jc = tv._h.jacobian(dev(torch_, Z), t=t).cpu().numpy()
+    for k in range(0, N, 29):
+        assert np.abs(xd[k] - _tv_f(Z[k, :2], Z[k, 2:], t[k], p0)).max() < 1e-13
+        assert np.abs(Jc[k].T - _cs_jac(lambda zz: _tv_f(zz[:2], zz[2:], t[k], p0), Z[k])).max() < 1e-12
+    assert np.abs(tv._h.dynamics(Z, t=None) - np.stack([_tv_f(Z[k, :2], Z[k, 2:], 0.0, p0) for k in range(N)])).max() < 1e-13   # no t == t = 0
+    for Q in QS:
+        xn = np.empty((N, 2))
+        J = tv._h.discrete_jacobian(Q, Z, dt, t=t, xn=xn)
+        Jd = tv._h.discrete_jacobian(Q, dev(torch_, Z), dt, t=t).cpu().numpy()
+        assert np.array_equal(J, Jd)
+        J32 = tv._h.discrete_jacobian(Q, Z.astype(np.float32), dt, t=t)
+        for k in range(0, N, 29):
+            ref = _cs_jac(lambda zz: _tv_step(Q, zz, t[k], dt[k], p0), Z[k])
+            assert np.abs(J[k].T - ref).max() < 1e-10 and np.abs(xn[k] - _tv_step(Q, Z[k], t[k], dt[k], p0)).max() < 1e-12
+            assert np.abs(J32[k].T - ref).max() < 1e-4
+    # the time really matters: the same knots at another time give another Jacobian
+    assert np.abs(tv._h.discrete_jacobian(o.RK4, Z, dt, t=t + 1.0) - tv._h.discrete_jacobian(o.RK4, Z, dt, t=t)).max() > 1e-3
+    # reference-facing spelling: the knot point's own time is used
+    dm = rd.DiscretizedDynamics(tv, rd.RK4)
+    Jm, y = np.zeros((2, 3)), np.zeros(2)
+    rd.jacobian_(rd.StaticReturn(), rd.ForwardAD(), dm, Jm, y, rd.KnotPoint(Z[0, :2], Z[0, 2:], float(t[0]), float(dt[0])))
+    assert np.abs(Jm - _cs_jac(lambda zz: _tv_step(o.RK4, zz, t[0], dt[0], p0), Z[0])).max() < 1e-10
+    assert np.abs(rd.discrete_dynamics(dm, Z[0, :2], Z[0, 2:], float(t[0]), float(dt[0])) - _tv_step(o.RK4, Z[0], t[0], dt[0], p0)).max() < 1e-12
+    # rollout: explicit per-knot times, and times accumulated from 0 when none are given
+    ntraj, K, h = 40, 12, 0.05
+    x0, U = rng.random((ntraj, 2)), rng.random((ntraj, K - 1, 1))
+    tt = np.broadcast_to(0.3 + h * np.arange(K), (ntraj, K)).copy()
+    X = tv._h.rollout(o.RK4, x0, U, h, t=tt)
+    X0 = tv._h.rollout(o.RK4, dev(torch_, x0), dev(torch_, U), h).cpu().numpy()
+    for j in range(0, ntraj, 7):
+        xa, xb = x0[j].copy(), x0[j].copy()
+        for k in range(K - 1):
+            xa = _tv_step(o.RK4, np.r_[xa, U[j, k]], tt[j, k], h, p0)
+            xb = _tv_step(o.RK4, np.r_[xb, U[j, k]], h * k, h, p0)
+            assert np.abs(X[j, k + 1] - xa).max() < 1e-12 and np.abs(X0[j, k + 1] - xb).max() < 1e-12
 
 
 def test_user_rigid_body_wrench(rd, torch_):
@@ -607,7 +809,7 @@ def test_implicit_midpoint(rd, torch_, name):
     assert np.array_equal(Jd.cpu().numpy(), J) and np.abs(xd.cpu().numpy() - ref_x).max() < 1e-10
     Z32 = Z.astype(np.float32)
     J32 = gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, Z32, dt)
-    assert np.abs(J32 - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z32.astype(np.float64), dt)).max() < 2e-4
+    assert np.abs(J32 - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z32.astype(np.float64), dt)).max() < 1e-4        # north_star: 1e-4 (fp32)
     # reference-facing spelling
     dm = rd.DiscretizedDynamics(gm, rd.ImplicitMidpoint)
     Jm, y = np.zeros((om.n, om.n + om.m)), np.zeros(om.n)

@@ -199,13 +199,14 @@ def test_oracle_vs_independent_complex_step(name):
 
 
 def test_quadrotor_thrust_clamp_derivative():
-    """max(0, kf w): zero derivative when clamped or exactly 0 (SURVEY Appendix A.8, test/quadrotor.jl:67-70);
-    the yaw moment km*w is NOT clamped."""
+    """max(0, kf w) (test/quadrotor.jl:67-70): zero derivative when clamped (w < 0); AT the tie w == 0 ForwardDiff keeps the
+    partials (Base.max(x, y) = ifelse(isless(y, x), x, y) on the promoted Duals returns y); the yaw moment km*w is NOT clamped."""
     m = o.quadrotor()
     z = rand_inputs(13, 4, 1, np.random.default_rng(13))
     z[0, 13:] = [-0.5, 0.0, 0.7, 0.9]
     J = o.as_matrix(o.jacobian(m, z))[0]
-    assert np.all(J[7:10, 13] == 0) and np.all(J[7:10, 14] == 0) and np.any(J[7:10, 15] != 0)
+    assert np.all(J[7:10, 13] == 0) and np.any(J[7:10, 14] != 0) and np.any(J[7:10, 15] != 0)
+    assert np.allclose(J[7:10, 14], J[7:10, 15])                      # tie: same derivative as an active motor
     assert np.allclose(J[12, 13:], np.array([1, -1, 1, -1]) * 0.0245 / 0.004)
 
 
