@@ -48,8 +48,8 @@ typedef enum { RDB_F32 = 0, RDB_F64 = 1 } rdb_dtype;
 typedef enum { RDB_AOS = 0, RDB_SOA = 1 } rdb_layout;
 /* QuadratureRule subtypes: src/integration.jl:69 (Euler), :109 (RK3), :258 (RK4); RK2 = explicit midpoint
  * (v0.3 name kept by BASELINE; semantics pinned by test/old_tests/linear_tests.jl:135-141).  ImplicitMidpoint: src/integration.jl:620
- * (Newton solve :422-463, implicit-function-theorem Jacobian :524-543); accepted by rdb_discrete_dynamics / rdb_discrete_jacobian
- * for the built-in models. */
+ * (Newton solve :422-463, implicit-function-theorem Jacobian :524-543); accepted by rdb_discrete_dynamics / rdb_discrete_jacobian /
+ * rdb_dynamics_error* for built-in and user models (not by rollout or the error-state form). */
 typedef enum { RDB_EULER = 0, RDB_RK2 = 1, RDB_RK3 = 2, RDB_RK4 = 3, RDB_IMPLICIT_MIDPOINT = 4 } rdb_integrator;
 /* model families: test/cartpole_model.jl, test/quadrotor.jl, test/rigidbody_test.jl:23-56 (= the Satellite of
  * examples/single_satellite.jl:7-35 with other parameters), test/double_integrator.jl:97-127 */
@@ -105,6 +105,14 @@ int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, 
  * J: 3x3 inertia, row-major.  n = 13 (quaternion) or 12 (MRP, Rodrigues). */
 int rdb_model_create_custom_rigid(rdb_context* ctx, int rot, int frame, int m, const char* wrench_body, double mass, const double* J,
                                   const double* params, int nparams, rdb_model** model);
+/* User-defined model whose state is a general LieState{R,P} (src/liestate.jl:75-132): `nparts` vector blocks of lengths parts[0..nparts)
+ * with ONE rotation of type `rot` between consecutive blocks, e.g. parts = (3, 2, 3) with RDB_ROT_QUAT is the [v3, q, v2, q, v3] state of
+ * the reference's QuatState(16, (4, 10)) example (src/liestate.jl:93-100); n = sum(parts) + (nparts-1) params(R), errstate_dim =
+ * sum(parts) + 3 (nparts-1).  f_body as for rdb_model_create_custom (it sees the full state x, rotations NOT renormalised).
+ * rdb_errstate_jacobian / rdb_grad_errstate_jacobian / rdb_state_diff use the partition (block-diagonal I / ∇differential per
+ * rotation, src/liestate.jl:210-320) and rdb_discrete_error_jacobian returns G(x+)' [A B] blkdiag(G(x), I) in errstate coordinates. */
+int rdb_model_create_custom_lie(rdb_context* ctx, int rot, int nparts, const int* parts, int m, const char* f_body, const double* params,
+                                int nparams, rdb_model** model);
 /* compile-only check of a user model body (needs no GPU); on failure rdb_last_log() returns the compiler log */
 int rdb_custom_check(int n, int m, const char* f_body, int nparams, int dtype);
 int rdb_custom_rigid_check(int rot, int frame, int m, const char* wrench_body, int nparams, int dtype);
@@ -148,6 +156,16 @@ int rdb_state_diff(const rdb_model* model, int dtype, int64_t N, const void* X, 
  * x0 (n, ntraj); U (m, K-1, ntraj); t, dt (K, ntraj) or NULL; X (n, K, ntraj) out.  Parallel over trajectories. */
 int rdb_rollout(const rdb_model* model, int integrator, int dtype, int64_t ntraj, int K, const void* x0, const void* U,
                 const double* t, const double* dt, double dt0, void* X, void* stream);
+
+/* dynamics_error(dmodel, z2, z1) and dynamics_error_jacobian!(sig, diff, dmodel, J2, J1, y2, y1, z2, z1) for N pairs of knot points
+ * (src/discrete_dynamics.jl:116-200): Z1 (n+m, N) holds z1 = [x1; u1], Z2 (ld2, N) holds x2 in its first n rows (pass the next knots'
+ * z rows with ld2 = n+m).  Explicit rules: e = discrete_dynamics(z1) - x2, J1 = the discrete Jacobian, J2 = [-I 0]
+ * (src/discrete_dynamics.jl:137-138,181-182).  RDB_IMPLICIT_MIDPOINT: e = x1 + h f((x1+x2)/2, u1, t + h/2) - x2, J1 = [I + h/2 A, h B],
+ * J2 = [h/2 A - I, 0] (src/integration.jl:640-700).  e (n, N); J1, J2 (n, n+m, N); any of J2 / J1 / e may be NULL. */
+int rdb_dynamics_error(const rdb_model* model, int integrator, int dtype, int64_t N, const void* Z1, const void* Z2, int ld2,
+                       const double* t, const double* dt, double dt0, void* e, void* stream);
+int rdb_dynamics_error_jacobian(const rdb_model* model, int integrator, int dtype, int64_t N, const void* Z1, const void* Z2, int ld2,
+                                const double* t, const double* dt, double dt0, void* J2, void* J1, void* e, void* stream);
 
 /* ---- pre-validated launches --------------------------------------------------------------------------------------------------
  * A solver evaluates the SAME batch (same buffers, 10^2..10^3 knot points) every iteration; there the per-call host work (pointer

@@ -30,9 +30,10 @@ ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE, ERR_COMPILE = -1, 
 # every symbol include/rdb200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free",
-    "rdb_model_create", "rdb_model_create_custom", "rdb_model_create_custom_rigid", "rdb_custom_check", "rdb_custom_rigid_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
+    "rdb_model_create", "rdb_model_create_custom", "rdb_model_create_custom_rigid", "rdb_model_create_custom_lie", "rdb_custom_check", "rdb_custom_rigid_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
+    "rdb_dynamics_error", "rdb_dynamics_error_jacobian",
     "rdb_plan_create", "rdb_plan_launch", "rdb_plan_destroy",
     "rdb_trajectory_create", "rdb_trajectory_destroy", "rdb_trajectory_dims", "rdb_trajectory_data", "rdb_trajectory_set_states",
     "rdb_trajectory_set_initial_state", "rdb_trajectory_set_controls", "rdb_trajectory_set_timesteps", "rdb_trajectory_get_states",
@@ -74,6 +75,7 @@ def lib():
         L.rdb_model_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_model_create_custom.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_model_create_custom_rigid.argtypes = [vp, i32, i32, i32, ctypes.c_char_p, dbl, ctypes.POINTER(dbl), ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
+        L.rdb_model_create_custom_lie.argtypes = [vp, i32, i32, ctypes.POINTER(i32), i32, ctypes.c_char_p, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_custom_check.argtypes = [i32, i32, ctypes.c_char_p, i32, i32]
         L.rdb_custom_rigid_check.argtypes = [i32, i32, i32, ctypes.c_char_p, i32, i32]
         L.rdb_last_log.restype = ctypes.c_char_p
@@ -88,6 +90,8 @@ def lib():
         L.rdb_grad_errstate_jacobian.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
         L.rdb_state_diff.argtypes = [vp, i32, i64, vp, i32, vp, i32, vp, vp]
         L.rdb_rollout.argtypes = [vp, i32, i32, i64, i32, vp, vp, vp, vp, dbl, vp, vp]
+        L.rdb_dynamics_error.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, vp, dbl, vp, vp]
+        L.rdb_dynamics_error_jacobian.argtypes = [vp, i32, i32, i64, vp, vp, i32, vp, vp, dbl, vp, vp, vp, vp]
         L.rdb_plan_create.argtypes = [vp, i32, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp, ctypes.POINTER(vp)]
         L.rdb_plan_launch.argtypes = [vp, vp]
         L.rdb_plan_destroy.argtypes = [vp]
@@ -282,7 +286,14 @@ class ModelHandle:
         self.time_varying = custom is not None          # user models may define dynamics(model, x, u, t)
         self._h = ctypes.c_void_p()
         pp = self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-        if custom is not None and len(custom) == 3:    # (n, m, body of f): NVRTC-compiled user model
+        if custom is not None and len(custom) == 2:      # (parts, m, body): user model over a general LieState{R,P}
+            raise TypeError("custom LieState models take (parts, m, body, 'lie')")
+        if custom is not None and len(custom) == 4 and custom[3] == "lie":
+            parts, m, body, _ = custom
+            arr = (ctypes.c_int * len(parts))(*[int(v) for v in parts])
+            check(lib().rdb_model_create_custom_lie(self.ctx._h, self.rot, len(parts), arr, int(m), body.encode(), pp, len(self.params),
+                                                    ctypes.byref(self._h)), "rdb_model_create_custom_lie")
+        elif custom is not None and len(custom) == 3:    # (n, m, body of f): NVRTC-compiled user model
             n, m, body = custom
             check(lib().rdb_model_create_custom(self.ctx._h, int(n), int(m), body.encode(), pp, len(self.params),
                                                 ctypes.byref(self._h)), "rdb_model_create_custom")
@@ -443,6 +454,26 @@ class ModelHandle:
         check(lib().rdb_state_diff(self._h, dtype_code(X), N, px, ld, p0, ld0, pd,
                                    current_stream(X)), "rdb_state_diff")
         return dX
+
+    def dynamics_error(self, Q, Z1, Z2, dt, t=None, e=None, J1=None, J2=None, jacobian=False):
+        """dynamics_error (and, jacobian=True, dynamics_error_jacobian!) of the knot pairs (Z1[k], Z2[k]): Z1 (N, n+m), Z2 (N, ld2 >= n).
+        Returns e, or (J2, J1, e)."""
+        self._zcheck(Z1)
+        N = self._count(Z1, AOS)
+        _, ld2 = self._xcheck("Z2", Z2)
+        check_buffer("Z2", Z2, (N, ld2), Z1)
+        e = empty_like_kind(Z1, (N, self.n)) if e is None else check_buffer("e", e, (N, self.n), Z1)
+        dtv, dt0 = self._dt(dt, Z1, N)
+        tv = self._t(t, Z1, N)
+        p1, _ = ptr(Z1); p2, _ = ptr(Z2); pe, _ = ptr(e); pd, _ = ptr(dtv); pt, _ = ptr(tv)
+        if not jacobian:
+            check(lib().rdb_dynamics_error(self._h, int(Q), dtype_code(Z1), N, p1, p2, ld2, pt, pd, dt0, pe, current_stream(Z1)), "rdb_dynamics_error")
+            return e
+        J1 = empty_like_kind(Z1, self._jshape(N, AOS)) if J1 is None else check_buffer("J1", J1, self._jshape(N, AOS), Z1)
+        J2 = empty_like_kind(Z1, self._jshape(N, AOS)) if J2 is None else check_buffer("J2", J2, self._jshape(N, AOS), Z1)
+        check(lib().rdb_dynamics_error_jacobian(self._h, int(Q), dtype_code(Z1), N, p1, p2, ld2, pt, pd, dt0, ptr(J2)[0], ptr(J1)[0], pe,
+                                                current_stream(Z1)), "rdb_dynamics_error_jacobian")
+        return J2, J1, e
 
     def rollout(self, Q, x0, U, dt, X=None, t=None):
         """x0 (ntraj, n); U (ntraj, K-1, m); dt scalar or (ntraj, K); t None or (ntraj, K).  Returns X (ntraj, K, n)."""

@@ -135,6 +135,32 @@ class CustomRigidBody(RigidBody):
         self._h = _abi.ModelHandle(_abi.CUSTOM, R.code, int(bool(bodyframe)), params, device, custom=(m, wrench_body, mass, _inertia(J)))
 
 
+class LieState:
+    """LieState{R,P} (src/liestate.jl:75-132): vector blocks of lengths P with one rotation of type R between consecutive blocks."""
+    def __init__(self, R, *P):
+        self.R, self.P = R, tuple(int(p) for p in (P[0] if len(P) == 1 and not isinstance(P[0], int) else P))
+
+    def __len__(self):
+        return sum(self.P) + (len(self.P) - 1) * (4 if self.R.code == _abi.ROT_QUAT else 3)
+
+
+def QuatState(n, Q):
+    """QuatState(n, Q): LieState of QuatRotations whose first (1-based) indices are Q (src/liestate.jl:84-111)."""
+    Q = list(Q)
+    P = [Q[0] - 1] + [Q[i] - Q[i - 1] - 4 for i in range(1, len(Q))] + [n - (Q[-1] + 4) + 1]
+    return LieState(QuatRotation, *P)
+
+
+class CustomLieModel(ContinuousDynamics):
+    """A user model (body of `f(x, u[, t])`, like CustomModel) whose state vector is a general LieState{R,P}: several rotations, any
+    partition.  errstate_jacobian_, grad_errstate_jacobian_, state_diff and discrete_error_jacobian_ follow the partition."""
+    statevectortype = RotationState
+
+    def __init__(self, liestate, m, body, params=(), device=None):
+        self.liestate = liestate
+        self._h = _abi.ModelHandle(_abi.CUSTOM, liestate.R.code, 0, params, device, custom=(liestate.P, m, body, "lie"))
+
+
 class DiscreteDynamics(AbstractModel): pass
 
 
@@ -396,6 +422,28 @@ def discrete_error_jacobian_(dmodel, Jbar, y, z):
         Jbar[...] = Jb[0].T
         if y is not None:
             y[...] = yb[0]
+    return None
+
+
+def dynamics_error(dmodel, z2, z1):
+    """dynamics_error(dmodel, z2, z1)  (src/discrete_dynamics.jl:116-138; ImplicitMidpoint: src/integration.jl:640-654): for explicit
+    rules discrete_dynamics(z1) - state(z2), for ImplicitMidpoint x1 + h f((x1+x2)/2, u1, t + h/2) - x2.  One knot pair, or two
+    trajectories / arrays of equal length (pair k = (z1[k], z2[k]))."""
+    Z1, t, dt, single = _batch(z1)
+    Z2, _, _, _ = _batch(z2)
+    e = dmodel._h.dynamics_error(_qcode(dmodel.integrator), Z1, Z2, dt, t=t)
+    return e[0] if single else e
+
+
+def dynamics_error_jacobian_(sig, diff, dmodel, J2, J1, y2, y1, z2, z1):
+    """dynamics_error_jacobian!(sig, diff, dmodel, J2, J1, y2, y1, z2, z1)  (src/discrete_dynamics.jl:160-200): J1 <- d e / d z1,
+    J2 <- d e / d z2 (n x (n+m) each, J2 = [-I 0] for explicit rules), y2 <- e."""
+    Z1, t, dt, single = _batch(z1)
+    Z2, _, _, _ = _batch(z2)
+    j2, j1, e = dmodel._h.dynamics_error(_qcode(dmodel.integrator), Z1, Z2, dt, t=t, jacobian=True)
+    _write(J2, j2, single); _write(J1, j1, single)
+    if y2 is not None:
+        y2[...] = e[0] if single else e
     return None
 
 

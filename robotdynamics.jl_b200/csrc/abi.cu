@@ -50,6 +50,9 @@ struct rdb_model {
     int n, m, nerr;
     ModelParams<double> p;
     CustomModel* custom;   // kind == RDB_CUSTOM: NVRTC-compiled user model (custom.cu)
+    LieParts lie;          // LieState{R,P} partition of the state (Euclidean: one vector block; RigidBody{R}: (3, 6))
+    int general_lie;       // user model with an arbitrary LieState{R,P} (rdb_model_create_custom_lie): kernels see a Euclidean model,
+                           // the LieState maps and the error-state projection use `lie`
 };
 
 // Persistent device mirror of a batch of SampledTrajectories (reference: src/trajectories.jl:40-50), knot-major across the batch:
@@ -219,13 +222,51 @@ int dispatch_soa(const rdb_model* M, int dtype, const KnotRequest& r, long long 
     return 0;
 }
 
-// The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
 // KnotPoint.t reaches only models whose dynamics can depend on it: user models (dynamics(model, x, u, t), src/dynamics.jl:81-83).
 // The shipped families are time-invariant, so their kernels never load it and the host path never copies it.
 bool model_uses_time(const rdb_model* M) { return M->kind == RDB_CUSTOM; }
 
 int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* t, const double* dt,
-            double dt0, void* J, void* out, void* stream, int err = 0) {
+            double dt0, void* J, void* out, void* stream, int err = 0);
+
+// Error-state Jacobian of a user model with an arbitrary LieState{R,P}: the full-state Jacobian and x+ go to stream-ordered scratch,
+// then one projection kernel forms G(x+)' [A B] blkdiag(G(x), I) (lie.cu).  Two passes: the G-seeded one-pass form of the rigid bodies is
+// specialised to LieState(R, (3, 6)).
+int general_error_jacobian(const rdb_model* M, int Q, int dtype, int layout, long long N, const void* Z, const double* t, const double* dt,
+                           double dt0, void* Jbar, void* xn, void* stream) {
+    if (layout != RDB_AOS) return RDB_ERR_NOT_IMPLEMENTED;
+    rdb_context* c = M->ctx;
+    const int kind = classify({Z, t, dt, Jbar, xn}, c->device);
+    if (kind < 0) return kind;
+    const size_t es = esize(dtype);
+    const int n = M->n, NZ = M->n + M->m, ne = M->nerr;
+    cudaStream_t st = kind == 2 ? (cudaStream_t)stream : c->slot[0].st;
+    void *dJ = nullptr, *dX = nullptr, *dZ = nullptr, *dB = nullptr;
+    double *dT = nullptr, *dDt = nullptr;
+    int rc = 0;
+    auto alloc = [&](void** p, size_t bytes) { if (!rc) rc = cuda_rc(cudaMallocAsync(p, bytes, st)); };
+    alloc(&dJ, size_t(N) * n * NZ * es);
+    alloc(&dX, size_t(N) * n * es);
+    const void* Zd = Z; const double* td = t; const double* dtd = dt; void* Bd = Jbar;
+    if (kind == 1) {
+        alloc(&dZ, size_t(N) * NZ * es); alloc(&dB, size_t(N) * ne * (ne + M->m) * es);
+        if (!rc) rc = cuda_rc(cudaMemcpyAsync(dZ, Z, size_t(N) * NZ * es, cudaMemcpyHostToDevice, st));
+        if (t && model_uses_time(M)) { alloc((void**)&dT, size_t(N) * 8); if (!rc) rc = cuda_rc(cudaMemcpyAsync(dT, t, size_t(N) * 8, cudaMemcpyHostToDevice, st)); }
+        if (dt) { alloc((void**)&dDt, size_t(N) * 8); if (!rc) rc = cuda_rc(cudaMemcpyAsync(dDt, dt, size_t(N) * 8, cudaMemcpyHostToDevice, st)); }
+        Zd = dZ; td = dT; dtd = dDt; Bd = dB;
+    }
+    if (!rc) rc = knot_op(M, Q, dtype, RDB_AOS, 1, N, Zd, td, dtd, dt0, dJ, dX, st, 0);
+    if (!rc) rc = lie_project_error_jacobian(dtype, M->rot, M->lie, n, M->m, ne, N, Zd, NZ, dX, dJ, Bd, c->sm_count, st);
+    if (!rc && kind == 1) rc = cuda_rc(cudaMemcpyAsync(Jbar, dB, size_t(N) * ne * (ne + M->m) * es, cudaMemcpyDeviceToHost, st));
+    if (!rc && xn) rc = cuda_rc(cudaMemcpyAsync(xn, dX, size_t(N) * n * es, kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    for (void* p : {dJ, dX, dZ, dB, (void*)dT, (void*)dDt}) if (p) cudaFreeAsync(p, st);
+    if (kind == 1) { const int r2 = cuda_rc(cudaStreamSynchronize(st)); if (!rc) rc = r2; }
+    return rc;
+}
+
+// The one knot-point operation behind rdb_dynamics / rdb_discrete_dynamics / rdb_jacobian / rdb_discrete_jacobian.
+int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long long N, const void* Z, const double* t, const double* dt,
+            double dt0, void* J, void* out, void* stream, int err) {
     if (!M || N < 0 || (dtype != RDB_F32 && dtype != RDB_F64) || (layout != RDB_AOS && layout != RDB_SOA)) return RDB_ERR_ARG;
     if (N == 0) return 0;
     if (!Z || (with_j && !J) || (!with_j && !out)) return RDB_ERR_ARG;
@@ -246,6 +287,7 @@ int knot_op(const rdb_model* M, int Q, int dtype, int layout, int with_j, long l
     KnotRequest r;
     std::memset(&r, 0, sizeof(r));
     if (M->rot == RDB_ROT_NONE) err = 0;     // EuclideanState: G = I (src/statevectortype.jl:149-155)
+    if (err && M->general_lie) return general_error_jacobian(M, Q, dtype, layout, N, Z, t, dt, dt0, J, out, stream);
     r.op = OP_KNOT; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.err = err; r.params = M->p;
     r.dt0 = dt0; r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
     if (kind == 2) {
@@ -402,6 +444,7 @@ int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const doubl
             break;
         default: return RDB_ERR_ARG;
     }
+    M.lie = (M.rot == RDB_ROT_NONE) ? lie_parts_euclidean(M.n) : lie_parts_rigid();
     rdb_model* out = new (std::nothrow) rdb_model(M);
     if (!out) return RDB_ERR_ARG;
     *model = out;
@@ -416,7 +459,30 @@ int rdb_model_create_custom(rdb_context* ctx, int n, int m, const char* f_body, 
     rdb_model M;
     std::memset(&M, 0, sizeof(M));
     M.ctx = ctx; M.kind = RDB_CUSTOM; M.rot = RDB_ROT_NONE; M.n = n; M.m = m; M.nerr = n;
+    M.lie = lie_parts_euclidean(n);
     M.custom = custom_create(n, m, f_body, params, np);
+    if (!M.custom) return RDB_ERR_ARG;
+    *model = new (std::nothrow) rdb_model(M);
+    return *model ? 0 : RDB_ERR_ARG;
+}
+
+int rdb_model_create_custom_lie(rdb_context* ctx, int rot, int nparts, const int* parts, int m, const char* f_body, const double* params, int np,
+                                rdb_model** model) {
+    if (!ctx || !model || !f_body || !parts || nparts < 1 || nparts > 8 || m < 1 || np < 0 || (np > 0 && !params) || rot < RDB_ROT_QUAT || rot > RDB_ROT_RP)
+        return RDB_ERR_ARG;
+    *model = nullptr;
+    LieParts lp{};
+    lp.nv = nparts;
+    int nvec = 0;
+    for (int i = 0; i < nparts; ++i) { if (parts[i] < 0) return RDB_ERR_ARG; lp.P[i] = parts[i]; nvec += parts[i]; }
+    const int nrot = nparts - 1, w = (rot == RDB_ROT_QUAT) ? 4 : 3;
+    const int n = nvec + nrot * w, ne = nvec + 3 * nrot;                 // length(LieState), errstate_dim (src/liestate.jl:118-124)
+    if (n < 1 || n + m > 32) return RDB_ERR_ARG;
+    if (custom_check(n, m, f_body, np, RDB_F64) != 0) return RDB_ERR_COMPILE;
+    rdb_model M;
+    std::memset(&M, 0, sizeof(M));
+    M.ctx = ctx; M.kind = RDB_CUSTOM; M.rot = rot; M.n = n; M.m = m; M.nerr = ne; M.lie = lp; M.general_lie = 1;
+    M.custom = custom_create(n, m, f_body, params, np);                  // the kernels see a plain (Euclidean) user model
     if (!M.custom) return RDB_ERR_ARG;
     *model = new (std::nothrow) rdb_model(M);
     return *model ? 0 : RDB_ERR_ARG;
@@ -436,6 +502,7 @@ int rdb_model_create_custom_rigid(rdb_context* ctx, int rot, int frame, int m, c
     M.p.mass = mass; M.p.inv_mass = 1.0 / mass;
     for (int i = 0; i < 9; ++i) M.p.J[i] = J[i];
     inv3(M.p.J, M.p.Jinv);
+    M.lie = lie_parts_rigid();
     M.custom = custom_create(n, m, wrench_body, params, np, rot, frame, &M.p);
     if (!M.custom) return RDB_ERR_ARG;
     *model = new (std::nothrow) rdb_model(M);
@@ -504,13 +571,13 @@ int rdb_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const void* 
     RDB_ON_DEVICE(c);
     const int kind = classify({X, G}, c->device);
     if (kind < 0) return kind;
-    if (kind == 2) return lie_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, X, ldx, G, c->sm_count, (cudaStream_t)stream);
+    if (kind == 2) return lie_errstate_jacobian(dtype, M->rot, M->lie, M->n, M->nerr, N, X, ldx, G, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t es = esize(dtype);
     Staged st(c->slot[0]);
     const void* dX = st.in(B_Z, X, size_t(N) * ldx * es);
     void* dG = st.outbuf(B_J, size_t(N) * M->n * M->nerr * es);
-    if (!st.rc) st.rc = lie_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, dX, ldx, dG, c->sm_count, st.s.st);
+    if (!st.rc) st.rc = lie_errstate_jacobian(dtype, M->rot, M->lie, M->n, M->nerr, N, dX, ldx, dG, c->sm_count, st.s.st);
     st.back(G, B_J, size_t(N) * M->n * M->nerr * es);
     return st.finish();
 }
@@ -524,14 +591,14 @@ int rdb_grad_errstate_jacobian(const rdb_model* M, int dtype, int64_t N, const v
     RDB_ON_DEVICE(c);
     const int kind = classify({X, Xbar, H}, c->device);
     if (kind < 0) return kind;
-    if (kind == 2) return lie_grad_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, X, ldx, Xbar, ldb, H, c->sm_count, (cudaStream_t)stream);
+    if (kind == 2) return lie_grad_errstate_jacobian(dtype, M->rot, M->lie, M->n, M->nerr, N, X, ldx, Xbar, ldb, H, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t es = esize(dtype);
     Staged st(c->slot[0]);
     const void* dX = st.in(B_Z, X, size_t(N) * ldx * es);
     const void* dB = st.in(B_AUX, Xbar, size_t(N) * ldb * es);
     void* dH = st.outbuf(B_J, size_t(N) * M->nerr * M->nerr * es);
-    if (!st.rc) st.rc = lie_grad_errstate_jacobian(dtype, M->rot, M->n, M->nerr, N, dX, ldx, dB, ldb, dH, c->sm_count, st.s.st);
+    if (!st.rc) st.rc = lie_grad_errstate_jacobian(dtype, M->rot, M->lie, M->n, M->nerr, N, dX, ldx, dB, ldb, dH, c->sm_count, st.s.st);
     st.back(H, B_J, size_t(N) * M->nerr * M->nerr * es);
     return st.finish();
 }
@@ -544,14 +611,14 @@ int rdb_state_diff(const rdb_model* M, int dtype, int64_t N, const void* X, int 
     RDB_ON_DEVICE(c);
     const int kind = classify({X, X0, dXo}, c->device);
     if (kind < 0) return kind;
-    if (kind == 2) return lie_state_diff(dtype, M->rot, M->n, M->nerr, N, X, ldx, X0, ldx0, dXo, c->sm_count, (cudaStream_t)stream);
+    if (kind == 2) return lie_state_diff(dtype, M->rot, M->lie, M->n, M->nerr, N, X, ldx, X0, ldx0, dXo, c->sm_count, (cudaStream_t)stream);
     std::lock_guard<std::mutex> lock(c->mu);
     const size_t es = esize(dtype);
     Staged st(c->slot[0]);
     const void* dX = st.in(B_Z, X, size_t(N) * ldx * es);
     const void* dX0 = st.in(B_AUX, X0, size_t(N) * ldx0 * es);
     void* dD = st.outbuf(B_OUT, size_t(N) * M->nerr * es);
-    if (!st.rc) st.rc = lie_state_diff(dtype, M->rot, M->n, M->nerr, N, dX, ldx, dX0, ldx0, dD, c->sm_count, st.s.st);
+    if (!st.rc) st.rc = lie_state_diff(dtype, M->rot, M->lie, M->n, M->nerr, N, dX, ldx, dX0, ldx0, dD, c->sm_count, st.s.st);
     st.back(dXo, B_OUT, size_t(N) * M->nerr * es);
     return st.finish();
 }
@@ -590,6 +657,69 @@ int rdb_rollout(const rdb_model* M, int integrator, int dtype, int64_t ntraj, in
     return st.finish();
 }
 
+
+// dynamics_error(dmodel, z2, z1) / dynamics_error_jacobian!(sig, diff, dmodel, J2, J1, y2, y1, z2, z1) for N pairs of knot points
+static int dynamics_error_op(const rdb_model* M, int integrator, int dtype, int64_t N, const void* Z1, const void* Z2, int ld2, const double* t,
+                             const double* dt, double dt0, void* J2, void* J1, void* e, void* stream, int with_j) {
+    const int Q = map_q(integrator);
+    if (!M || Q < 0 || N < 0 || (dtype != RDB_F32 && dtype != RDB_F64) || ld2 < M->n) return RDB_ERR_ARG;
+    if (N == 0) return 0;
+    if (!Z1 || !Z2 || (with_j && !J1 && !J2) || (!with_j && !e)) return RDB_ERR_ARG;
+    if (M->kind != RDB_CUSTOM && !find_unit(M->kind, M->rot, M->frame, M->D, dtype)) return RDB_ERR_NOT_IMPLEMENTED;
+    rdb_context* c = M->ctx;
+    RDB_ON_DEVICE(c);
+    if (!model_uses_time(M)) t = nullptr;
+    const int kind = classify({Z1, Z2, t, dt, J2, J1, e}, c->device);
+    if (kind < 0) return kind;
+    const size_t es = esize(dtype);
+    const int n = M->n, NZ = M->n + M->m;
+    auto run = [&](const void* dZ1, const void* dZ2, const double* dtt, const double* ddt, void* dJ2, void* dJ1, void* de, cudaStream_t st) -> int {
+        if (Q == Q_IMPLICIT_MIDPOINT) {
+            KnotRequest r;
+            std::memset(&r, 0, sizeof(r));
+            r.op = OP_DYNERR; r.Q = Q; r.dtype = dtype; r.with_j = with_j; r.params = M->p; r.dt0 = dt0; r.dt = ddt; r.t = dtt;
+            r.dev = DeviceInfo{c->device, c->sm_count, c->pdl};
+            r.Z = dZ1; r.Z2 = dZ2; r.ld2 = ld2; r.J2 = dJ2; r.J = dJ1; r.out = de; r.N = N; r.stream = st;
+            return dispatch(M, dtype, &r);
+        }
+        // explicit rules: e = discrete_dynamics(z1) - x2, J1 = the discrete Jacobian, J2 = [-I 0]   (src/discrete_dynamics.jl:137-138,181-182)
+        if (with_j && dJ1) { if (int rc = knot_op(M, Q, dtype, RDB_AOS, 1, N, dZ1, dtt, ddt, dt0, dJ1, de, st)) return rc; }
+        else if (de) { if (int rc = knot_op(M, Q, dtype, RDB_AOS, 0, N, dZ1, dtt, ddt, dt0, nullptr, de, st)) return rc; }
+        if (!de && !dJ2) return 0;
+        const long long total = N * (long long)(dJ2 ? n * NZ : n);
+        const unsigned g = unsigned(total + 255 < (1ll << 28) ? (total + 255) / 256 : (1ll << 20));
+        if (dtype == RDB_F32) explicit_error_fixup_kernel<float><<<g, 256, 0, st>>>(n, M->m, N, (const float*)dZ2, ld2, (float*)de, (float*)dJ2);
+        else explicit_error_fixup_kernel<double><<<g, 256, 0, st>>>(n, M->m, N, (const double*)dZ2, ld2, (double*)de, (double*)dJ2);
+        return int(cudaGetLastError());
+    };
+    if (kind == 2) return run(Z1, Z2, t, dt, J2, J1, e, (cudaStream_t)stream);
+    std::lock_guard<std::mutex> lock(c->mu);
+    Staged st(c->slot[0]);
+    Slot& s2 = c->slot[1];                               // second set of staging buffers for Z2 and J2
+    const void* dZ1 = st.in(B_Z, Z1, size_t(N) * NZ * es);
+    const double* ddt = (const double*)st.in(B_DT, dt, size_t(N) * 8);
+    const double* dtt = (const double*)st.in(B_T, t, size_t(N) * 8);
+    void* dJ1 = J1 ? st.outbuf(B_J, size_t(N) * n * NZ * es) : nullptr;
+    void* de = e ? st.outbuf(B_OUT, size_t(N) * n * es) : nullptr;
+    void* dZ2 = nullptr; void* dJ2 = nullptr;
+    if (!st.rc) st.rc = ensure(s2, B_Z, size_t(N) * ld2 * es);
+    if (!st.rc) { dZ2 = s2.buf[B_Z]; st.rc = cuda_rc(cudaMemcpyAsync(dZ2, Z2, size_t(N) * ld2 * es, cudaMemcpyHostToDevice, st.s.st)); }
+    if (!st.rc && J2) { st.rc = ensure(s2, B_J, size_t(N) * n * NZ * es); dJ2 = s2.buf[B_J]; }
+    if (!st.rc) st.rc = run(dZ1, dZ2, dtt, ddt, dJ2, dJ1, de, st.s.st);
+    if (J1) st.back(J1, B_J, size_t(N) * n * NZ * es);
+    if (e) st.back(e, B_OUT, size_t(N) * n * es);
+    if (!st.rc && J2) st.rc = cuda_rc(cudaMemcpyAsync(J2, dJ2, size_t(N) * n * NZ * es, cudaMemcpyDeviceToHost, st.s.st));
+    return st.finish();
+}
+
+int rdb_dynamics_error(const rdb_model* M, int integrator, int dtype, int64_t N, const void* Z1, const void* Z2, int ld2, const double* t,
+                       const double* dt, double dt0, void* e, void* stream) {
+    return dynamics_error_op(M, integrator, dtype, N, Z1, Z2, ld2, t, dt, dt0, nullptr, nullptr, e, stream, 0);
+}
+int rdb_dynamics_error_jacobian(const rdb_model* M, int integrator, int dtype, int64_t N, const void* Z1, const void* Z2, int ld2, const double* t,
+                                const double* dt, double dt0, void* J2, void* J1, void* e, void* stream) {
+    return dynamics_error_op(M, integrator, dtype, N, Z1, Z2, ld2, t, dt, dt0, J2, J1, e, stream, 1);
+}
 
 // ---- pre-validated launches ("plans") ---------------------------------------------------------------------------------------------
 int rdb_plan_create(const rdb_model* M, int op, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,

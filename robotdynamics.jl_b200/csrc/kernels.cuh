@@ -661,6 +661,85 @@ __global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model
     }
 }
 
+// ---- dynamics_error / dynamics_error_jacobian! for ImplicitMidpoint ---------------------------------------------------------------
+// e = x1 + h f((x1 + x2)/2, u1, t + h/2) - x2   (reference: src/integration.jl:640-654);  J1 = de/dz1 = [I + h/2 A, h B],
+// J2 = de/dz2 = [h/2 A - I, 0]  (src/integration.jl:674-700), A, B the continuous Jacobian at the midpoint (evaluated at t + h/2 like
+// the residual; the reference's Jacobian passes t there, an inconsistency with its own residual that is not reproduced).
+// One thread per knot pair, ONE forward-mode evaluation of f with every column seeded (sparse: it fits registers).
+template <class T>
+struct DynErrArgs {
+    const T* Z1;         // (N, n+m): z1 = [x1; u1]
+    const T* Z2;         // (N, ld2): x2 in the first n entries of every row
+    int ld2;
+    const double* t; const double* dt; double dt0;
+    T* J2; T* J1;        // (N, n+m, n) each: column-major n x (n+m) per knot; may be nullptr
+    T* e;                // (N, n); may be nullptr
+    long long N;
+};
+template <class Model, class T, bool WITH_J>
+__global__ void __launch_bounds__(128) midpoint_error_kernel(const Model model, const DynErrArgs<T> a) {
+    constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    constexpr mask_t ALL = (NZ >= 32) ? ~mask_t(0) : ((mask_t(1) << NZ) - 1u);
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= a.N) return;
+    const T* z1 = a.Z1 + k * NZ;
+    const T* x2 = a.Z2 + k * (long long)a.ld2;
+    const T h = T(a.dt ? a.dt[k] : a.dt0);
+    T tm = T(0);
+    if constexpr (uses_time<Model>::value) tm = T(a.t ? a.t[k] : 0.0) + T(0.5) * h;
+    T zm[NZ], f[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) zm[i] = (z1[i] + x2[i]) * T(0.5);
+#pragma unroll
+    for (int i = 0; i < m; ++i) zm[n + i] = z1[n + i];
+    model.reset();
+    if constexpr (WITH_J) {
+        T AB[n * NZ];
+        auto zz = load_seeded<T, ALL>(zm, rstd::make_index_sequence<size_t(NZ)>{});
+        auto fd = feval<T>(model, slice<0, n>(zz), slice<n, m>(zz), tm);
+        put_vals(fd, f, rstd::make_index_sequence<size_t(n)>{});
+        put_cols<n, ALL, false>(fd, AB, rstd::make_index_sequence<size_t(NZ)>{});
+        T* J1 = a.J1 ? a.J1 + k * (long long)(n * NZ) : nullptr;
+        T* J2 = a.J2 ? a.J2 + k * (long long)(n * NZ) : nullptr;
+#pragma unroll
+        for (int j = 0; j < NZ; ++j)
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const T ha = h * AB[i + n * j], hha = T(0.5) * ha, d = (i == j) ? T(1) : T(0);
+                if (J1) J1[i + n * j] = j < n ? hha + d : ha;
+                if (J2) J2[i + n * j] = j < n ? hha - d : T(0);
+            }
+    } else {
+        auto zz = load_seeded<T, mask_t(0)>(zm, rstd::make_index_sequence<size_t(NZ)>{});
+        auto fd = feval<T>(model, slice<0, n>(zz), slice<n, m>(zz), tm);
+        put_vals(fd, f, rstd::make_index_sequence<size_t(n)>{});
+    }
+    if (a.e) {
+        T* e = a.e + k * n;
+#pragma unroll
+        for (int i = 0; i < n; ++i) e[i] = z1[i] + h * f[i] - x2[i];
+    }
+}
+// explicit rules: e = discrete_dynamics(z1) - x2 and J2 = [-I 0] (reference: src/discrete_dynamics.jl:137-138,181-182); the knot kernel
+// has already written discrete_dynamics(z1) into e and its Jacobian into J1
+template <class T>
+__global__ void __launch_bounds__(256) explicit_error_fixup_kernel(int n, int m, long long N, const T* __restrict__ Z2, int ld2, T* __restrict__ e,
+                                                                   T* __restrict__ J2) {
+    const int per = n * (n + m);
+    const long long total = N * (long long)(J2 ? per : n);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        if (J2) {
+            const long long k = idx / per;
+            const int r = int(idx - k * per), j = r / n, i = r - j * n;
+            J2[idx] = (i == j) ? T(-1) : T(0);
+            if (e && j == 0) e[k * n + i] -= Z2[k * (long long)ld2 + i];
+        } else {
+            const long long k = idx / n;
+            e[idx] -= Z2[k * (long long)ld2 + int(idx - k * n)];
+        }
+    }
+}
+
 // rollout!: x_{k+1} = discrete_dynamics(x_k, u_k, t_k, dt_k), sequential in k, one thread per trajectory
 // (reference: src/trajectories.jl:436-441, src/discrete_dynamics.jl:217-235).
 //

@@ -229,7 +229,7 @@ struct KnotLaunch {
 };
 
 // ---- request passed from the C ABI to a per-model compilation unit ------------------------------------------------
-enum UnitOp { OP_KNOT = 0, OP_ROLLOUT = 1 };
+enum UnitOp { OP_KNOT = 0, OP_ROLLOUT = 1, OP_DYNERR = 2 };
 struct KnotRequest {
     int op;              // UnitOp
     int Q;               // QuadRule (Q_CONTINUOUS for dynamics / continuous Jacobian)
@@ -244,6 +244,9 @@ struct KnotRequest {
     //             zmode != 0: X is the knot-major batch Z (K, ntraj, n+m) holding the controls; steps [kb, ke)   (kernels.cuh)
     const void* x0; const void* U; void* X; long long ntraj; int K;
     int zmode, kb, ke;
+    // OP_DYNERR (ImplicitMidpoint): dynamics_error / dynamics_error_jacobian! of the pairs (Z[k], Z2[k]): Z2 (N, ld2) holds x2, J2 -> de/dz2,
+    // J -> de/dz1, out -> e
+    const void* Z2; int ld2; void* J2;
     DeviceInfo dev;
     cudaStream_t stream;
 };
@@ -326,8 +329,26 @@ inline int run_q(const KnotRequest& r) {
     }
     return r.with_j ? run_one<ModelT, T, Q, true>(r) : run_one<ModelT, T, Q, false>(r);
 }
+template <class T>
+inline DynErrArgs<T> dynerr_args(const KnotRequest& r) {
+    DynErrArgs<T> a;
+    a.Z1 = static_cast<const T*>(r.Z); a.Z2 = static_cast<const T*>(r.Z2); a.ld2 = r.ld2; a.t = r.t; a.dt = r.dt; a.dt0 = r.dt0;
+    a.J2 = static_cast<T*>(r.J2); a.J1 = static_cast<T*>(r.J); a.e = static_cast<T*>(r.out); a.N = r.N;
+    return a;
+}
+template <template <class> class ModelT, class T>
+inline int run_dynerr(const KnotRequest& r) {
+    if (r.Q != Q_IMPLICIT_MIDPOINT) return -2;          // explicit rules are composed from the knot kernel by the caller (abi.cu)
+    if (r.N <= 0) return 0;
+    ModelT<T> model; model.p = cast_params<T>(r.params);
+    const unsigned grid = unsigned((r.N + 127) / 128);
+    if (r.with_j) midpoint_error_kernel<ModelT<T>, T, true><<<grid, 128, 0, r.stream>>>(model, dynerr_args<T>(r));
+    else midpoint_error_kernel<ModelT<T>, T, false><<<grid, 128, 0, r.stream>>>(model, dynerr_args<T>(r));
+    return int(cudaGetLastError());
+}
 template <template <class> class ModelT, class T>
 inline int run_t(const KnotRequest& r) {
+    if (r.op == OP_DYNERR) return run_dynerr<ModelT, T>(r);
     switch (r.Q) {
         case Q_EULER: return run_q<ModelT, T, Q_EULER>(r);
         case Q_RK2: return run_q<ModelT, T, Q_RK2>(r);

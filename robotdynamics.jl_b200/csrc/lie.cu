@@ -51,19 +51,46 @@ __device__ __forceinline__ T grad_differential(int rot, const T* p, int i, int j
     return I + sk[i][j] + p[i] * p[j];
 }
 
+// ---- index algebra of LieState{R,P} (reference: src/liestate.jl:127-131: rot_inds / vec_inds) -------------------------------------------
+// where state index i (or error-state index, ERR = true) falls: block b, offset o within it, and whether the block is a rotation
+struct LiePos { int rot; int b; int o; int start; };
+template <bool ERR>
+__device__ __forceinline__ LiePos lie_locate(const LieParts& parts, int np, int i) {
+    const int w = ERR ? 3 : np;
+    int s = 0;
+    for (int k = 0; k < parts.nv; ++k) {
+        if (i < s + parts.P[k]) return {0, k, i - s, s};
+        s += parts.P[k];
+        if (k + 1 < parts.nv) {
+            if (i < s + w) return {1, k, i - s, s};
+            s += w;
+        }
+    }
+    return {0, parts.nv, 0, s};
+}
+__device__ __forceinline__ int lie_rot_start(const LieParts& parts, int w, int b) {      // first index of rotation b (width w per rotation)
+    int s = 0;
+    for (int k = 0; k <= b; ++k) s += parts.P[k];
+    return s + b * w;
+}
+
+// errstate_jacobian! for ANY LieState (and Euclidean states, nv = 1): block diagonal, I on the vector blocks, Rotations.∇differential on
+// every rotation (reference: src/liestate.jl:262-298).  One thread per output element, coalesced stores.
 template <class T>
-__global__ void __launch_bounds__(256) errstate_jacobian_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx, T* __restrict__ G) {
+__global__ void __launch_bounds__(256) errstate_jacobian_kernel(int rot, LieParts parts, int n, int ne, long long N, const T* __restrict__ X, int ldx,
+                                                                T* __restrict__ G) {
     const long long total = N * (long long)n * ne;
     const int per = n * ne;
     const int np = (rot == ROT_QUAT) ? 4 : 3;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long k = idx / per;
         const int e = int(idx - k * per), j = e / n, i = e - j * n;
-        T v;
-        if (rot == ROT_NONE) v = (i == j) ? T(1) : T(0);
-        else if (i < 3) v = (j == i) ? T(1) : T(0);
-        else if (i < 3 + np) v = (j >= 3 && j < 6) ? grad_differential(rot, X + k * ldx + 3, i - 3, j - 3) : T(0);
-        else v = (j == i - np + 3) ? T(1) : T(0);
+        const LiePos pi = lie_locate<false>(parts, np, i), pj = lie_locate<true>(parts, np, j);
+        T v = T(0);
+        if (pi.rot == pj.rot && pi.b == pj.b) {
+            if (!pi.rot) v = (pi.o == pj.o) ? T(1) : T(0);
+            else v = grad_differential(rot, X + k * ldx + pi.start, pi.o, pj.o);
+        }
         G[idx] = v;
     }
 }
@@ -115,20 +142,24 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
     if (threadIdx.x == 0) bulk_wait0();
 }
 
-// ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p)
+// ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p); one 3x3 block per rotation on
+// the diagonal, zeros elsewhere (reference: src/liestate.jl:300-320)
 template <class T>
-__global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx,
+__global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, LieParts parts, int n, int ne, long long N, const T* __restrict__ X, int ldx,
                                                                      const T* __restrict__ B, int ldb, T* __restrict__ H) {
     const long long total = N * (long long)ne * ne;
     const int per = ne * ne;
+    const int np = (rot == ROT_QUAT) ? 4 : 3;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long k = idx / per;
         const int e = int(idx - k * per), j = e / ne, i = e - j * ne;
+        const LiePos pi = lie_locate<true>(parts, np, i), pj = lie_locate<true>(parts, np, j);
         T v = T(0);
-        if (rot != ROT_NONE && i >= 3 && i < 6 && j >= 3 && j < 6) {
-            const T* p = X + k * ldx + 3;
-            const T* b = B + k * ldb + 3;
-            const int a = i - 3, c = j - 3;
+        if (pi.rot && pj.rot && pi.b == pj.b) {
+            const int xs = lie_rot_start(parts, np, pi.b);
+            const T* p = X + k * ldx + xs;
+            const T* b = B + k * ldb + xs;
+            const int a = pi.o, c = pj.o;
             if (rot == ROT_QUAT) {
                 if (a == c) { T q[4]; unit_quat(rot, p, q); v = -(q[0] * b[0] + q[1] * b[1] + q[2] * b[2] + q[3] * b[3]); }
             } else {
@@ -148,8 +179,9 @@ __global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, in
     }
 }
 
+// state_diff for ANY LieState: vector blocks x - x0, every rotation the Cayley error of q0 \ q (reference: src/liestate.jl:210-260)
 template <class T>
-__global__ void __launch_bounds__(256) state_diff_kernel(int rot, int n, int ne, long long N, const T* __restrict__ X, int ldx,
+__global__ void __launch_bounds__(256) state_diff_kernel(int rot, LieParts parts, int n, int ne, long long N, const T* __restrict__ X, int ldx,
                                                          const T* __restrict__ X0, int ldx0, T* __restrict__ dX) {
     const long long total = N * (long long)ne;
     const int np = (rot == ROT_QUAT) ? 4 : 3;
@@ -158,23 +190,69 @@ __global__ void __launch_bounds__(256) state_diff_kernel(int rot, int n, int ne,
         const int i = int(idx - k * ne);
         const T* x = X + k * ldx;
         const T* x0 = X0 + k * ldx0;
+        const LiePos pe = lie_locate<true>(parts, np, i);
         T v;
-        if (rot == ROT_NONE || i < 3) v = x[i] - x0[i];
-        else if (i >= 6) v = x[i + np - 3] - x0[i + np - 3];
-        else {
+        if (!pe.rot) {
+            const int xi = pe.start + pe.b * (np - 3) + pe.o;          // every rotation before this block is np wide in x, 3 wide in dx
+            v = x[xi] - x0[xi];
+        } else {
+            const int xs = lie_rot_start(parts, np, pe.b);
             T q[4], q0[4];
-            unit_quat(rot, x + 3, q);
-            unit_quat(rot, x0 + 3, q0);
+            unit_quat(rot, x + xs, q);
+            unit_quat(rot, x0 + xs, q0);
             // e = conj(q0) (x) q ;  Cayley map: vec(e) / scalar(e)
             const T c0 = q0[0], c1 = -q0[1], c2 = -q0[2], c3 = -q0[3];
             const T e0 = c0 * q[0] - c1 * q[1] - c2 * q[2] - c3 * q[3];
             T ev;
-            if (i == 3) ev = c0 * q[1] + c1 * q[0] + c2 * q[3] - c3 * q[2];
-            else if (i == 4) ev = c0 * q[2] - c1 * q[3] + c2 * q[0] + c3 * q[1];
+            if (pe.o == 0) ev = c0 * q[1] + c1 * q[0] + c2 * q[3] - c3 * q[2];
+            else if (pe.o == 1) ev = c0 * q[2] - c1 * q[3] + c2 * q[0] + c3 * q[1];
             else ev = c0 * q[3] + c1 * q[2] - c2 * q[1] + c3 * q[0];
             v = ev / e0;
         }
         dX[idx] = v;
+    }
+}
+
+// Error-state projection for ANY LieState:  Jbar = G(x+)' [A B] blkdiag(G(x), I)  (what Altro / TrajectoryOptimization build from
+// jacobian! and errstate_jacobian!, src/liestate.jl:262-298, src/functionbase.jl:135).  G is block diagonal, so entry (a, c) of Jbar only
+// sums over the rows of a's block and the columns of c's block (1 term for vector blocks, np x np for two rotations).
+template <class T>
+__global__ void __launch_bounds__(256) project_error_jacobian_kernel(int rot, LieParts parts, int n, int m, int ne, long long N, const T* __restrict__ Z, int ldz,
+                                                                     const T* __restrict__ Xn, const T* __restrict__ J, T* __restrict__ Jbar) {
+    const int per = ne * (ne + m);
+    const long long total = N * (long long)per;
+    const int np = (rot == ROT_QUAT) ? 4 : 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long k = idx / per;
+        const int e = int(idx - k * per), c = e / ne, a = e - c * ne;
+        const T* Jk = J + k * (long long)(n * (n + m));
+        const LiePos pa = lie_locate<true>(parts, np, a);
+        // rows of J that meet error row a, with weights G(x+)[i][a]
+        int i0, ni; T wr[4];
+        if (!pa.rot) { i0 = pa.start + pa.b * (np - 3) + pa.o; ni = 1; wr[0] = T(1); }
+        else {
+            i0 = lie_rot_start(parts, np, pa.b); ni = np;
+            for (int i = 0; i < np; ++i) wr[i] = grad_differential(rot, Xn + k * n + i0, i, pa.o);
+        }
+        T v = T(0);
+        if (c >= ne) {                                                   // control column: Bbar = G(x+)' B
+            for (int i = 0; i < ni; ++i) v += wr[i] * Jk[(i0 + i) + n * (n + (c - ne))];
+        } else {
+            const LiePos pc = lie_locate<true>(parts, np, c);
+            if (!pc.rot) {
+                const int j = pc.start + pc.b * (np - 3) + pc.o;
+                for (int i = 0; i < ni; ++i) v += wr[i] * Jk[(i0 + i) + n * j];
+            } else {
+                const int j0 = lie_rot_start(parts, np, pc.b);
+                for (int jj = 0; jj < np; ++jj) {
+                    const T g = grad_differential(rot, Z + k * ldz + j0, jj, pc.o);
+                    T col = T(0);
+                    for (int i = 0; i < ni; ++i) col += wr[i] * Jk[(i0 + i) + n * (j0 + jj)];
+                    v += col * g;
+                }
+            }
+        }
+        Jbar[idx] = v;
     }
 }
 
@@ -220,49 +298,51 @@ static unsigned grid_for(long long total, int sm_count) {
     return unsigned(g < 1 ? 1 : g);
 }
 
-int lie_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, void* G, int sm_count, cudaStream_t st) {
+int lie_errstate_jacobian(int dtype, int rot, const LieParts& parts, int n, int ne, long long N, const void* X, int ldx, void* G, int sm_count, cudaStream_t st) {
     if (N <= 0) return 0;
-    if (rot != ROT_NONE && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {      // rigid bodies, 16-byte aligned output: TMA image kernel
+    if (rot != ROT_NONE && lie_is_rigid(parts) && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {      // rigid bodies, 16-byte aligned output: TMA image kernel
         const int np = rot == ROT_QUAT ? 4 : 3;
         const int TILE = dtype == 0 ? 64 : 32;
         const size_t smem = size_t(2) * TILE * (9 + np) * 12 * (dtype == 0 ? 4 : 8);
         const long long ntiles = (N + TILE - 1) / TILE, cap = (long long)sm_count * 2;
         const unsigned g = unsigned(ntiles < cap ? ntiles : cap);
-        auto go = [&](auto kern, auto* x, auto* out) {
-            static std::atomic<unsigned long long> configured{0};          // one bit per device: the attribute is set once, not per call
+        // the dynamic-smem attribute is set once per (kernel, device), not per call.  `kid` tells the four instantiations apart: two of
+        // them share one function-pointer TYPE, so a static inside this generic lambda alone would be shared between them.
+        static std::atomic<unsigned long long> configured[4];              // one bit per device
+        auto go = [&](int kid, auto kern, auto* x, auto* out) {
             int dev = 0;
             cudaGetDevice(&dev);
             const unsigned long long bit = 1ull << (dev & 63);
-            if (!(configured.load(std::memory_order_acquire) & bit)) {
+            if (!(configured[kid].load(std::memory_order_acquire) & bit)) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
                 if (e != cudaSuccess) return int(e);
-                configured.fetch_or(bit, std::memory_order_release);
+                configured[kid].fetch_or(bit, std::memory_order_release);
             }
             kern<<<g, TILE, smem, st>>>(rot, N, x, ldx, out);
             return int(cudaGetLastError());
         };
-        if (dtype == 0) return np == 4 ? go(errstate_jacobian_tma_kernel<float, 4, 64>, (const float*)X, (float*)G)
-                                       : go(errstate_jacobian_tma_kernel<float, 3, 64>, (const float*)X, (float*)G);
-        return np == 4 ? go(errstate_jacobian_tma_kernel<double, 4, 32>, (const double*)X, (double*)G)
-                       : go(errstate_jacobian_tma_kernel<double, 3, 32>, (const double*)X, (double*)G);
+        if (dtype == 0) return np == 4 ? go(0, errstate_jacobian_tma_kernel<float, 4, 64>, (const float*)X, (float*)G)
+                                       : go(1, errstate_jacobian_tma_kernel<float, 3, 64>, (const float*)X, (float*)G);
+        return np == 4 ? go(2, errstate_jacobian_tma_kernel<double, 4, 32>, (const double*)X, (double*)G)
+                       : go(3, errstate_jacobian_tma_kernel<double, 3, 32>, (const double*)X, (double*)G);
     }
     const unsigned g = grid_for(N * (long long)n * ne, sm_count);
-    if (dtype == 0) errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (float*)G);
-    else errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (double*)G);
+    if (dtype == 0) errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const float*)X, ldx, (float*)G);
+    else errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const double*)X, ldx, (double*)G);
     return int(cudaGetLastError());
 }
-int lie_grad_errstate_jacobian(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, const void* B, int ldb, void* H,
+int lie_grad_errstate_jacobian(int dtype, int rot, const LieParts& parts, int n, int ne, long long N, const void* X, int ldx, const void* B, int ldb, void* H,
                                int sm_count, cudaStream_t st) {
     if (N <= 0) return 0;
     const unsigned g = grid_for(N * (long long)ne * ne, sm_count);
-    if (dtype == 0) grad_errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (const float*)B, ldb, (float*)H);
-    else grad_errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (const double*)B, ldb, (double*)H);
+    if (dtype == 0) grad_errstate_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const float*)X, ldx, (const float*)B, ldb, (float*)H);
+    else grad_errstate_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const double*)X, ldx, (const double*)B, ldb, (double*)H);
     return int(cudaGetLastError());
 }
-int lie_state_diff(int dtype, int rot, int n, int ne, long long N, const void* X, int ldx, const void* X0, int ldx0, void* dX,
+int lie_state_diff(int dtype, int rot, const LieParts& parts, int n, int ne, long long N, const void* X, int ldx, const void* X0, int ldx0, void* dX,
                    int sm_count, cudaStream_t st) {
     if (N <= 0) return 0;
-    if (rot != ROT_NONE) {
+    if (rot != ROT_NONE && lie_is_rigid(parts)) {
         constexpr int TILE = 128;
         const long long ntiles = (N + TILE - 1) / TILE, cap = (long long)sm_count * 12;
         const unsigned g = unsigned(ntiles < cap ? ntiles : cap);
@@ -276,8 +356,16 @@ int lie_state_diff(int dtype, int rot, int n, int ne, long long N, const void* X
         return int(cudaGetLastError());
     }
     const unsigned g = grid_for(N * (long long)ne, sm_count);
-    if (dtype == 0) state_diff_kernel<float><<<g, 256, 0, st>>>(rot, n, ne, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
-    else state_diff_kernel<double><<<g, 256, 0, st>>>(rot, n, ne, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);
+    if (dtype == 0) state_diff_kernel<float><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const float*)X, ldx, (const float*)X0, ldx0, (float*)dX);
+    else state_diff_kernel<double><<<g, 256, 0, st>>>(rot, parts, n, ne, N, (const double*)X, ldx, (const double*)X0, ldx0, (double*)dX);
+    return int(cudaGetLastError());
+}
+int lie_project_error_jacobian(int dtype, int rot, const LieParts& parts, int n, int m, int ne, long long N, const void* Z, int ldz, const void* Xn,
+                               const void* J, void* Jbar, int sm_count, cudaStream_t st) {
+    if (N <= 0) return 0;
+    const unsigned g = grid_for(N * (long long)ne * (ne + m), sm_count);
+    if (dtype == 0) project_error_jacobian_kernel<float><<<g, 256, 0, st>>>(rot, parts, n, m, ne, N, (const float*)Z, ldz, (const float*)Xn, (const float*)J, (float*)Jbar);
+    else project_error_jacobian_kernel<double><<<g, 256, 0, st>>>(rot, parts, n, m, ne, N, (const double*)Z, ldz, (const double*)Xn, (const double*)J, (double*)Jbar);
     return int(cudaGetLastError());
 }
 

@@ -62,25 +62,26 @@ struct Cartpole {
         // H = [mc+mp  mp l c; mp l c  mp l^2];  C qd + G - B u = [-mp l s w^2 - u, mp g l s];  qdd = -H \ r  (closed-form 2x2 solve, like
         // StaticArrays).  Both sides divided by mp*l:  H' = [H00  c; c  l],  r' = [-s w^2 - u/(mp l), g s],  H00 = (mc+mp)/(mp l).
         const T ia = p.cp_ia, H00 = p.cp_H00, k = p.cp_nH00i, g = p.g;
+        // (every multiply-add is an explicit fma_: see sdual.cuh)
         const T w2 = w * w;
-        const T r0 = -(s * w2) - ia * uv;
+        const T r0 = fma_(-ia, uv, -(s * w2));
         const T r1 = g * s;
-        const T iD = T(1) / (H00 * p.l - c * c);
-        const T q1 = (c * r0 - H00 * r1) * iD;                   // qdd1
-        const T q0 = k * (c * q1 + r0);                          // qdd0: first row of H' qdd = -r'
+        const T iD = T(1) / fma_(-c, c, H00 * p.l);
+        const T q1 = fma_(c, r0, -(H00 * r1)) * iD;              // qdd1
+        const T q0 = k * fma_(c, q1, r0);                        // qdd0: first row of H' qdd = -r'
         using In = decltype(vec(th, qd1, uu));
         if constexpr (!has_partials<T, In>()) return vec(qd0, qd1, q0, q1);
         else {
             // d/dtheta: s' = c, c' = -s;  d/dw: r0' = -2 s w;  d/du: r0' = -1/(mp l)
             const T r0t = -(c * w2);
-            const T q1t = ((c * r0t - s * r0 - (H00 * g) * c) - q1 * (T(2) * c * s)) * iD;
-            const T q0t = k * (c * q1t - s * q1 + r0t);
-            const T r0w = T(-2) * s * w;
+            const T q1t = fma_(-q1, (T(2) * c) * s, fma_(c, r0t, fma_(-s, r0, -((H00 * g) * c)))) * iD;
+            const T q0t = k * fma_(c, q1t, fma_(-s, q1, r0t));
+            const T r0w = (T(-2) * s) * w;
             const T ciD = c * iD;
             const T q1w = ciD * r0w;
-            const T q0w = k * (c * q1w + r0w);
+            const T q0w = k * fma_(c, q1w, r0w);
             const T q1u = -(ia * ciD);
-            const T q0u = k * (c * q1u - ia);
+            const T q0u = k * fma_(c, q1u, -ia);
             const T d0[3] = {q0t, q0w, q0u}, d1[3] = {q1t, q1w, q1u};
             const auto in = vec(th, qd1, uu);
             return vec(qd0, qd1, chain<T>(q0, d0, in), chain<T>(q1, d1, in));
@@ -175,6 +176,132 @@ RDB_HD auto rot_kinematics(const P& p, const W& w, T c = T(1)) {
     }
 }
 
+// ---- rotations as elemental operations ---------------------------------------------------------------------------------------------
+// AttRot holds the VALUES of the quaternion an attitude stands for (the state quaternion itself, un-normalised, for QuatRotation;
+// the unit quaternion Rotations.jl builds for an MRP / Rodrigues vector) and, for the 3-parameter attitudes, dq/dp.  rot<INV>(r)
+// evaluates  y = R(q) r  (INV: R(q)' r = q \ r)  on plain scalars, writes the 3 x (np + 3) local Jacobian by hand and lets chain()
+// build the partials: 7 (6) FMAs per output and partial, where forward mode through the polynomial  (w^2 - v.v) r + 2 v (v.r) +
+// 2 w (v x r)  spends ~14 — and ~18 more through to_quat for the 3-parameter attitudes.  The rigid-body kernels are bound by FP32 /
+// FP64 instruction issue, so this is where the body-frame and MRP / Rodrigues models lost their time in round 1
+// (0.31 - 0.52 of the HBM roofline).  Same map as quat_rotate / to_quat, hence the same derivatives (up to rounding).
+template <class T, class X> RDB_HD T pval(const X& x) { return opnd<T, X>::v(x); }
+template <class T, int ROT, class Att>
+struct AttRot {
+    static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
+    const Att& att;
+    T w, x, y, z;
+    T dq[4][3];                      // d(w, x, y, z) / dp   (3-parameter attitudes only)
+    RDB_HD explicit AttRot(const Att& a) : att(a) {
+        if constexpr (ROT == ROT_QUAT) {
+            w = pval<T>(get<0>(a)); x = pval<T>(get<1>(a)); y = pval<T>(get<2>(a)); z = pval<T>(get<3>(a));
+        } else {
+            const T p[3] = {pval<T>(get<0>(a)), pval<T>(get<1>(a)), pval<T>(get<2>(a))};
+            const T n2 = fma_(p[2], p[2], fma_(p[1], p[1], p[0] * p[0]));
+            if constexpr (ROT == ROT_MRP) {          // q = ((1 - |p|^2), 2 p) / (1 + |p|^2)
+                const T i1 = T(1) / (T(1) + n2), M = T(2) * i1;
+                w = (T(1) - n2) * i1; x = M * p[0]; y = M * p[1]; z = M * p[2];
+                const T qv[3] = {x, y, z};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const T g = -(M * p[j]);             // -2 p_j / (1 + |p|^2)
+                    dq[0][j] = g * (T(1) + w);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) dq[1 + i][j] = (i == j) ? fma_(g, qv[i], M) : g * qv[i];
+                }
+            } else {                                  // q = (1, g) / sqrt(1 + |g|^2)
+                const T M = rsqrt_(T(1) + n2), M3 = M * M * M;
+                w = M; x = M * p[0]; y = M * p[1]; z = M * p[2];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const T g = -(p[j] * M3);
+                    dq[0][j] = g;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) dq[1 + i][j] = (i == j) ? fma_(g, p[i], M) : g * p[i];
+                }
+            }
+        }
+    }
+    template <bool INV, class R3>
+    RDB_HD auto rot(const R3& r) const {
+        const T v[3] = {x, y, z};
+        const T rr[3] = {pval<T>(get<0>(r)), pval<T>(get<1>(r)), pval<T>(get<2>(r))};
+        const T sw = INV ? -w : w;                    // conj(q) = (w, -v): only the cross-product term changes sign
+        const T a = fma_(w, w, -fma_(z, z, fma_(y, y, x * x)));
+        const T d = fma_(z, rr[2], fma_(y, rr[1], x * rr[0]));
+        const T c[3] = {fma_(y, rr[2], -(z * rr[1])), fma_(z, rr[0], -(x * rr[2])), fma_(x, rr[1], -(y * rr[0]))};
+        const T sw2 = T(2) * sw, d2 = T(2) * d;
+        T yv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) yv[i] = fma_(sw2, c[i], fma_(d2, v[i], a * rr[i]));
+        using In = decltype(cat(att, r));
+        if constexpr (!has_partials<T, In>()) return vec(yv[0], yv[1], yv[2]);
+        else {
+            // (e_j x r)_i and (v x e_j)_i
+            const T exr[3][3] = {{T(0), rr[2], -rr[1]}, {-rr[2], T(0), rr[0]}, {rr[1], -rr[0], T(0)}};      // [i][j] = (e_j x r)_i
+            const T vxe[3][3] = {{T(0), -v[2], v[1]}, {v[2], T(0), -v[0]}, {-v[1], v[0], T(0)}};            // [i][j] = (v x e_j)_i
+            T cf[3][np + 3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const T cw = T(2) * fma_(w, rr[i], INV ? -c[i] : c[i]);
+                T cv[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const T sym = fma_(rr[j], v[i], fma_(-v[j], rr[i], i == j ? d : T(0)));
+                    cv[j] = (i == j) ? T(2) * sym : fma_(sw2, exr[i][j], T(2) * sym);         // (e_i x r)_i = 0
+                }
+                if constexpr (ROT == ROT_QUAT) {
+                    cf[i][0] = cw; cf[i][1] = cv[0]; cf[i][2] = cv[1]; cf[i][3] = cv[2];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) cf[i][j] = fma_(cv[2], dq[3][j], fma_(cv[1], dq[2][j], fma_(cv[0], dq[1][j], cw * dq[0][j])));
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) cf[i][np + j] = (i == j) ? fma_(T(2) * v[j], v[i], a) : fma_(sw2, vxe[i][j], (T(2) * v[j]) * v[i]);
+            }
+            const auto in = cat(att, r);
+            return vec(chain<T>(yv[0], cf[0], in), chain<T>(yv[1], cf[1], in), chain<T>(yv[2], cf[2], in));
+        }
+    }
+};
+
+// c * Rotations.kinematics for the 3-parameter attitudes as ONE elemental operation (3 x 6 local Jacobian; the quaternion form is
+// bilinear and already costs what its local Jacobian would).
+template <class T, int ROT, class P, class W>
+RDB_HD auto rot_kinematics_el(const P& pp, const W& ww, T c) {
+    static_assert(ROT == ROT_MRP || ROT == ROT_RP, "3-parameter attitudes");
+    const T p[3] = {pval<T>(get<0>(pp)), pval<T>(get<1>(pp)), pval<T>(get<2>(pp))};
+    const T w[3] = {pval<T>(get<0>(ww)), pval<T>(get<1>(ww)), pval<T>(get<2>(ww))};
+    const T pw = fma_(p[2], w[2], fma_(p[1], w[1], p[0] * w[0]));
+    const T cr[3] = {fma_(p[1], w[2], -(p[2] * w[1])), fma_(p[2], w[0], -(p[0] * w[2])), fma_(p[0], w[1], -(p[1] * w[0]))};
+    const T n2 = fma_(p[2], p[2], fma_(p[1], p[1], p[0] * p[0]));
+    // MRP: 1/4 [(1-|p|^2) w + 2 p x w + 2 p (p.w)];  RP: 1/2 [w + g x w + g (g.w)]  ==  k [a w + b (p x w + p (p.w))]
+    const T k = (ROT == ROT_MRP ? T(0.25) : T(0.5)) * c, a = ROT == ROT_MRP ? T(1) - n2 : T(1), b = ROT == ROT_MRP ? T(2) : T(1);
+    const T kb = k * b, ka = k * a;
+    T yv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) yv[i] = fma_(kb, fma_(p[i], pw, cr[i]), ka * w[i]);
+    using In = decltype(cat(pp, ww));
+    if constexpr (!has_partials<T, In>()) return vec(yv[0], yv[1], yv[2]);
+    else {
+        const T exw[3][3] = {{T(0), w[2], -w[1]}, {-w[2], T(0), w[0]}, {w[1], -w[0], T(0)}};      // [i][j] = (e_j x w)_i
+        const T pxe[3][3] = {{T(0), -p[2], p[1]}, {p[2], T(0), -p[0]}, {-p[1], p[0], T(0)}};      // [i][j] = (p x e_j)_i
+        T cf[3][6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                // d/dp_j: k [da/dp_j w_i + b ((e_j x w)_i + delta_ij (p.w) + p_i w_j)],  da/dp_j = -2 p_j (MRP) / 0 (RP)
+                const T inner = fma_(p[i], w[j], i == j ? pw : exw[i][j]);                   // (e_i x w)_i = 0
+                cf[i][j] = (ROT == ROT_MRP) ? fma_((-(T(2) * k)) * p[j], w[i], kb * inner) : kb * inner;
+                // d/dw_j: k [a delta_ij + b ((p x e_j)_i + p_i p_j)]
+                const T sym = (i == j) ? p[i] * p[j] : fma_(p[i], p[j], pxe[i][j]);
+                cf[i][3 + j] = (i == j) ? fma_(kb, sym, ka) : kb * sym;
+            }
+        const auto in = cat(pp, ww);
+        return vec(chain<T>(yv[0], cf[0], in), chain<T>(yv[1], cf[1], in), chain<T>(yv[2], cf[2], in));
+    }
+}
+
 // y = diag(d) x
 template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) { return vec(d0 * get<0>(x), d1 * get<1>(x), d2 * get<2>(x)); }
 
@@ -182,7 +309,8 @@ template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) 
 // RigidBody{R} with the Quadrotor or Body/Satellite wrench
 // ------------------------------------------------------------------------------------------------
 // The part every RigidBody{R} shares (reference: src/rigidbody.jl:213-236): kinematics, Newton and Euler equations around a
-// wrench supplied by the concrete model — `wrench(q, r, v, w, u)` returns vec(F/m in the world frame (3), tau in the body frame (3))
+// wrench supplied by the concrete model — `wrench(R, q, r, v, w, u)` (R: AttRot, the attitude as an elemental rotation; q: the same
+// attitude as a quaternion of duals, for user code) returns vec(F/m in the world frame (3), tau in the body frame (3))
 // (reference: forces / moments / wrenches, src/rigidbody.jl:244-257).
 //
 // SCALED: return c * f(x,u) instead of f(x,u) (the integrators ask for the stage increment h a_s f(X_s) directly, integrators.cuh).
@@ -195,11 +323,15 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
     auto att = slice<3, np>(x);
     auto v = slice<3 + np, 3>(x);
     auto w = slice<6 + np, 3>(x);
-    auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised)
-    auto xi = wrench(q, r, v, w, u);
+    auto q = to_quat<T, ROT>(att);          // identity for quaternions (never renormalised); dead code unless the wrench reads it
+    const AttRot<T, ROT, decltype(att)> R(att);
+    auto xi = wrench(R, q, r, v, w, u);
     auto Fm = slice<0, 3>(xi);
     auto tau = slice<3, 3>(xi);
-    auto qdot = [&]() { if constexpr (SCALED) return rot_kinematics<T, ROT>(att, w, c); else return rot_kinematics<T, ROT>(att, w); }();
+    auto qdot = [&]() {
+        if constexpr (ROT == ROT_QUAT) { if constexpr (SCALED) return rot_kinematics<T, ROT>(att, w, c); else return rot_kinematics<T, ROT>(att, w); }
+        else return rot_kinematics_el<T, ROT>(att, w, SCALED ? c : T(1));
+    }();
     // omega_dot = Jinv (tau - w x (J w))
     auto wdot = [&]() {
         if constexpr (DIAG_INERTIA) {      // w x (J w) = ((J3-J2) wy wz, (J1-J3) wz wx, (J2-J1) wx wy): three products instead of six
@@ -226,10 +358,10 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
     } else {
         if constexpr (SCALED) {            // c (q*v) = q*(c v),  c (q\F/m - w x v) = q\(c F/m) - w x (c v)
             auto cv = vscale(c, v);
-            return cat(quat_rotate<T>(q, cv), qdot, vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, cv)), wdot);
+            return cat(R.template rot<false>(cv), qdot, vsub(R.template rot<true>(Fm), cross3<T>(w, cv)), wdot);
         } else {
-            auto rdot = quat_rotate<T>(q, v);
-            auto vdot = vsub(quat_rotate<T>(quat_conj(q), Fm), cross3<T>(w, v));
+            auto rdot = R.template rot<false>(v);
+            auto vdot = vsub(R.template rot<true>(Fm), cross3<T>(w, v));
             return cat(rdot, qdot, vdot, wdot);
         }
     }
@@ -255,20 +387,25 @@ struct RigidBody {
         // wrench: F/m in the world frame (the 1/m of vdot = F/m — and the stage factor c — are folded into the few scalars that
         // build F, instead of scaling every partial of the rotated vector), tau in the body frame
         const T im = SCALED ? c * p.inv_mass : p.inv_mass;
-        return rigid_body_f<T, ROT, FRAME, diag_inertia, SCALED>(p, x, u, [&](const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
+        return rigid_body_f<T, ROT, FRAME, diag_inertia, SCALED>(p, x, u, [&](const auto& R, const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
             if constexpr (KIND == KIND_QUADROTOR) {
                 auto F1 = relu_(p.kf * get<0>(uu));
                 auto F2 = relu_(p.kf * get<1>(uu));
                 auto F3 = relu_(p.kf * get<2>(uu));
                 auto F4 = relu_(p.kf * get<3>(uu));
-                auto qF = quat_rotate_z<T>(q, im * (F1 + F2 + F3 + F4));
+                // thrust along the body z axis: the third column of R(q) for the state quaternion (quat_rotate_z: 18 products per partial),
+                // the elemental rotation of [0, 0, s] for the 3-parameter attitudes (12 FMAs per partial instead of to_quat + rotate)
+                auto qF = [&]() {
+                    if constexpr (ROT == ROT_QUAT) return quat_rotate_z<T>(q, im * (F1 + F2 + F3 + F4));
+                    else return R.template rot<false>(vec(Zero{}, Zero{}, im * (F1 + F2 + F3 + F4)));
+                }();
                 const T g0 = p.mg[0] * im, g1 = p.mg[1] * im, g2 = p.mg[2] * im;
                 auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
                                p.km * (get<0>(uu) - get<1>(uu) + get<2>(uu) - get<3>(uu)));
                 return cat(Fm, tau);
             } else {
-                return cat(quat_rotate<T>(q, vscale(im, slice<0, 3>(uu))), slice<3, 3>(uu));
+                return cat(R.template rot<false>(vscale(im, slice<0, 3>(uu))), slice<3, 3>(uu));
             }
         }, c);
     }

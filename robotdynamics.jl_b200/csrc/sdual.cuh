@@ -52,6 +52,12 @@ struct Zero {};
 #ifndef RDB_PACK_F32
 #define RDB_PACK_F32 0   // measured slower on the quadrotor RK4 kernel (59.3 vs 51.1 us): padded lanes + pair alignment, see profiles/tuning_r01.md
 #endif
+// a * b + c as ONE rounding, spelled out: the compiler may contract `p*q + r*s` into an FMA around either product, and it need not
+// choose the same one in two instantiations of a kernel — results are promised to be bit-identical across layouts and pointer kinds
+// (tests: test_layouts_and_pointer_kinds_agree_bitwise), so every multiply-add of the partial arithmetic and of the hand-written
+// elemental operations is an explicit fma
+RDB_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+RDB_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
 template <class T> struct PK {
     using vec = T;
     static constexpr int W = 1;
@@ -60,7 +66,7 @@ template <class T> struct PK {
     RDB_HD static vec add(vec a, vec b) { return a + b; }
     RDB_HD static vec sub(vec a, vec b) { return a - b; }
     RDB_HD static vec mul(vec a, vec b) { return a * b; }
-    RDB_HD static vec fma(vec a, vec b, vec c) { return a * b + c; }      // contracted to one FMA by nvcc
+    RDB_HD static vec fma(vec a, vec b, vec c) { return fma_(a, b, c); }
     RDB_HD static vec neg(vec a) { return -a; }
     RDB_HD static vec sel(bool on, vec a) { return on ? a : T(0); }
     template <int L> RDB_HD static T lane(vec a) { return a; }

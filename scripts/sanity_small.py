@@ -29,3 +29,32 @@ for name, gm, om, Z, dt, tol in cases:
     Jh = gm._h.discrete_jacobian(o.RK4, Z.astype(dt), 0.01)            # host path
     print("ok", name, flush=True)
 print("SANITY DONE")
+
+# ---- round 2 additions: component-major (tensor-map) kernels, ImplicitMidpoint (both kernels), dynamics_error, the device trajectory
+#      (rollout in place, linearize, pipelined rollout + linearize on two streams), plans, a time-varying user model
+cp, qd = rd.Cartpole(), rd.Quadrotor()
+Zs = torch.from_numpy(np.ascontiguousarray(rng.random((640, 5)).T)).cuda()
+cp._h.discrete_jacobian(o.RK4, Zs, 0.01, layout=rd.SOA)
+for gm, Z in ((cp, rng.random((300, 5))), (qd, rigid(13, 4, 200))):
+    Zd = torch.from_numpy(Z).cuda()
+    gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, Zd, 0.03)
+    x2 = gm._h.discrete_dynamics(rd._abi.IMPLICIT_MIDPOINT, Zd, 0.03)
+    gm._h.dynamics_error(rd._abi.IMPLICIT_MIDPOINT, Zd, x2, 0.03, jacobian=True)
+    gm._h.dynamics_error(o.RK4, Zd, x2, 0.03, jacobian=True)
+torch.cuda.synchronize()
+for gm, dtn in ((cp, np.float64), (qd, np.float32)):
+    dm = rd.DiscretizedDynamics(gm, rd.RK4)
+    h = gm._h
+    tb = rd.TrajectoryBatch(dm, 70, 19, dtn)
+    tb.set_initial_state(rigid(13, 4, 70)[:, :13].astype(dtn) if h.n == 13 else rng.random((70, 4)))
+    tb.set_controls((0.5 * rng.random((18, 70, h.m))).astype(dtn)); tb.set_timesteps(0.02)
+    tb.rollout(); tb.linearize(); tb.rollout_linearize(chunks=4); tb.rollout_linearize(error_state=True, device=False); tb.states()
+    torch.cuda.synchronize()
+Zq = torch.from_numpy(rigid(13, 4, 500).astype(np.float32)).cuda()
+plan = rd._abi.Plan(qd._h, rd._abi.OP_DISCRETE_ERROR_JACOBIAN, rd.RK4.code, Zq, 0.01)
+plan.launch(); plan.launch()
+tv = rd.CustomModel(2, 1, "return vec(get<1>(x), cos_(T(3) * t) * get<0>(u) - p[0] * sin_(get<0>(x)) + t * get<1>(x));", params=[1.7])
+tv._h.discrete_jacobian(o.RK4, rng.random((333, 3)), 0.05, t=rng.random(333))
+tv._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, torch.from_numpy(rng.random((333, 3))).cuda(), 0.05, t=rng.random(333))
+torch.cuda.synchronize()
+print("SANITY ROUND-2 DONE")

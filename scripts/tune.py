@@ -26,6 +26,8 @@ UNIT = {   # workload -> (unit name, -D flags, bench.py workload)
     "quadrotor64": ("quad_quat_world_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite": ("body_mrp_world_f64", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
     "satellite32": ("body_mrp_world_f32", dict(RDB_KIND=2, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=0)),
+    "quadbody64": ("quad_quat_body_f64", dict(RDB_KIND=1, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=1)),
+    "quadmrp64": ("quad_mrp_world_f64", dict(RDB_KIND=1, RDB_ROT=2, RDB_FRAME=0, RDB_DTYPE=1)),
 }
 
 VARIANTS = {
@@ -92,6 +94,25 @@ VARIANTS = {
         "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2),
     },
 }
+# round 2: packed fp32x2 partial arithmetic on top of the elemental rotations (dense chains), and role splits for the fp64 kernels
+for _w in ("quadrotor", "quadbody", "quadmrp", "bodyquat"):
+    VARIANTS[_w] = {"base": {}, "pack": dict(RDB_PACK_F32=1)}
+VARIANTS["quadbody"].update({"3r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+                             "pack_3r": dict(RDB_PACK_F32=1, RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u")})
+VARIANTS["quadbody64"] = {
+    "base": {},
+    "6r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7u", RDB_TUNE_C1="0x78u", RDB_TUNE_C2="0x380u", RDB_TUNE_C3="0x1C00u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
+    "6r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7u", RDB_TUNE_C1="0x78u", RDB_TUNE_C2="0x380u", RDB_TUNE_C3="0x1C00u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+    "4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
+    "unroll_4r": dict(RDB_TUNE_ROLL=0),
+}
+VARIANTS["quadmrp64"] = {
+    "base": {},
+    "6r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7u", RDB_TUNE_C1="0x38u", RDB_TUNE_C2="0x1C0u", RDB_TUNE_C3="0xE00u", RDB_TUNE_C4="0x3000u", RDB_TUNE_C5="0xC000u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
+    "4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
+}
 VARIANTS["satellite32"] = {"base": {}, "pad8": dict(RDB_ROWSTORE_MINWAY=8), "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=3),
                            "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2)}
 
@@ -144,14 +165,15 @@ import rdb200 as rd
 import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
-wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor", "bodyquat": "quadrotor"}.get(name, name)
+wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor", "bodyquat": "quadrotor",
+      "quadbody64": "quadrotor", "quadmrp64": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
-if name == "quadrotor64": dtn = "float64"
+if name in ("quadrotor64", "quadbody64", "quadmrp64"): dtn = "float64"
 if len(sys.argv) > 3: N = int(sys.argv[3])
 mk, Q = bench.gpu_model(wl, rd)
-if name == 'quadbody': mk = lambda: rd.Quadrotor(bodyframe=True)
-if name == 'quadmrp': mk = lambda: rd.Quadrotor(rd.MRP)
+if name in ('quadbody', 'quadbody64'): mk = lambda: rd.Quadrotor(bodyframe=True)
+if name in ('quadmrp', 'quadmrp64'): mk = lambda: rd.Quadrotor(rd.MRP)
 if name == 'bodyquat': mk = lambda: rd.Body()
 model = mk(); h = model._h
 n, m = h.n, h.m
@@ -169,8 +191,8 @@ for i in range(steps): call(Q.code, Zs[i % nsets], dt, J=Js[i % nsets])
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / steps * 1e3
 omk, oQ = bench.oracle_model(wl)
-if name == 'quadbody': omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
-if name == 'quadmrp': omk = lambda: o.quadrotor(o.ROT_MRP)
+if name in ('quadbody', 'quadbody64'): omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
+if name in ('quadmrp', 'quadmrp64'): omk = lambda: o.quadrotor(o.ROT_MRP)
 if name == 'bodyquat': omk = lambda: o.body()
 idx = np.arange(0, N, 4099)
 if ERR:

@@ -815,3 +815,206 @@ def test_implicit_midpoint(rd, torch_, name):
     Jm, y = np.zeros((om.n, om.n + om.m)), np.zeros(om.n)
     rd.jacobian_(rd.InPlace(), rd.ForwardAD(), dm, Jm, y, rd.KnotPoint(Z[0, :om.n], Z[0, om.n:], 0.0, float(dt[0])))
     assert np.abs(Jm - o.as_matrix(ref_J)[0]).max() < 1e-10 and np.abs(y - ref_x[0]).max() < 1e-10
+
+
+# ---- dynamics_error / dynamics_error_jacobian! and ImplicitMidpoint for user models ---------------------------------------------------
+def _cs_cols(fun, z):
+    zc = z.astype(complex)
+    return np.stack([np.imag(fun(zc + 1e-30j * np.eye(len(z))[j])) / 1e-30 for j in range(len(z))], axis=1)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "quad_quat_world", "body_mrp_body"])
+def test_dynamics_error_and_its_jacobian(rd, torch_, name):
+    """dynamics_error(dmodel, z2, z1) / dynamics_error_jacobian! (src/discrete_dynamics.jl:116-200): explicit rules give
+    discrete_dynamics(z1) - x2 with J1 = the discrete Jacobian and J2 = [-I 0]; ImplicitMidpoint gives the midpoint residual with
+    J1 = [I + h/2 A, h B], J2 = [h/2 A - I, 0] (src/integration.jl:640-700), A, B the continuous Jacobian at the midpoint."""
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    n, m = om.n, om.m
+    N = 500
+    rng = np.random.default_rng(170)
+    Z1 = rand_inputs(n, m, N, rng)
+    Z2 = Z1 + 0.05 * rng.standard_normal((N, n + m))                     # "next knots": only their states are read (ld2 = n + m)
+    dt = rng.uniform(0.01, 0.1, N)
+    # explicit
+    e = gm._h.dynamics_error(o.RK4, Z1, Z2, dt)
+    assert np.abs(e - (o.discrete_dynamics(om, o.RK4, Z1, dt) - Z2[:, :n])).max() < 1e-10
+    J2, J1, e2 = gm._h.dynamics_error(o.RK4, dev(torch_, Z1), dev(torch_, Z2), dt, jacobian=True)
+    assert np.abs(J1.cpu().numpy() - o.discrete_jacobian(om, o.RK4, Z1, dt)).max() < 1e-10 and np.abs(e2.cpu().numpy() - e).max() < 1e-12
+    eye = np.concatenate([-np.eye(n), np.zeros((m, n))])
+    assert np.array_equal(J2.cpu().numpy(), np.broadcast_to(eye, (N, n + m, n)))
+    # ImplicitMidpoint
+    IM = rd._abi.IMPLICIT_MIDPOINT
+    Zm = np.concatenate([0.5 * (Z1[:, :n] + Z2[:, :n]), Z1[:, n:]], axis=1)
+    f, AB = o.dynamics(om, Zm), o.as_matrix(o.jacobian(om, Zm))
+    h = dt[:, None]
+    ei = gm._h.dynamics_error(IM, Z1, Z2, dt)
+    assert np.abs(ei - (Z1[:, :n] + h * f - Z2[:, :n])).max() < 1e-10
+    J2, J1, e3 = gm._h.dynamics_error(IM, Z1, Z2, dt, jacobian=True)
+    A, Bm = AB[:, :, :n], AB[:, :, n:]
+    I = np.eye(n)[None]
+    assert np.abs(o.as_matrix(J1) - np.concatenate([I + 0.5 * h[:, :, None] * A, h[:, :, None] * Bm], axis=2)).max() < 1e-10
+    assert np.abs(o.as_matrix(J2) - np.concatenate([0.5 * h[:, :, None] * A - I, np.zeros((N, n, m))], axis=2)).max() < 1e-10
+    assert np.array_equal(e3, ei)
+    # the residual vanishes at the implicit step, and the two Jacobians give the step's Jacobian by the implicit function theorem
+    xn = gm._h.discrete_dynamics(IM, Z1, dt)
+    assert np.abs(gm._h.dynamics_error(IM, Z1, np.ascontiguousarray(xn), dt)).max() < 1e-10
+    J2s, J1s, _ = gm._h.dynamics_error(IM, Z1, np.ascontiguousarray(xn), dt, jacobian=True)
+    Jstep = o.as_matrix(gm._h.discrete_jacobian(IM, Z1, dt))
+    sol = -np.linalg.solve(o.as_matrix(J2s)[:, :, :n], o.as_matrix(J1s))
+    assert np.abs(sol - Jstep).max() < 1e-8
+    # reference-facing spelling, one knot pair
+    dm = rd.DiscretizedDynamics(gm, rd.ImplicitMidpoint)
+    z1, z2 = rd.KnotPoint(Z1[0, :n], Z1[0, n:], 0.0, float(dt[0])), rd.KnotPoint(Z2[0, :n], Z2[0, n:], float(dt[0]), float(dt[0]))
+    assert np.abs(rd.dynamics_error(dm, z2, z1) - ei[0]).max() < 1e-12
+    Ja, Jb, y2 = np.zeros((n, n + m)), np.zeros((n, n + m)), np.zeros(n)
+    rd.dynamics_error_jacobian_(rd.StaticReturn(), rd.ForwardAD(), dm, Ja, Jb, y2, None, z2, z1)
+    assert np.abs(Ja - o.as_matrix(J2)[0]).max() < 1e-12 and np.abs(Jb - o.as_matrix(J1)[0]).max() < 1e-12 and np.abs(y2 - ei[0]).max() < 1e-12
+
+
+def test_implicit_midpoint_for_user_models(rd, torch_):
+    """DiscretizedDynamics{L, ImplicitMidpoint} for NVRTC-compiled user models: the Cartpole written as a user model equals the built-in
+    one; a time-varying model solves x1 + h f((x1+x2)/2, u, t + h/2) - x2 = 0 with the midpoint TIME; an 8-state model takes the
+    warp-cooperative kernel (one column of [A B] per lane)."""
+    IM = rd._abi.IMPLICIT_MIDPOINT
+    um, om = rd.CustomModel(4, 1, CARTPOLE_BODY, params=[1.0, 0.2, 0.5, 9.81]), o.cartpole()
+    N = 700
+    rng = np.random.default_rng(180)
+    Z, dt = rng.random((N, 5)), rng.uniform(0.01, 0.1, N)
+    xn = np.empty((N, 4))
+    J = um._h.discrete_jacobian(IM, Z, dt, xn=xn)
+    assert np.abs(J - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z, dt)).max() < 1e-10
+    assert np.abs(xn - o.discrete_dynamics(om, o.IMPLICIT_MIDPOINT, Z, dt)).max() < 1e-10
+    J32 = um._h.discrete_jacobian(IM, dev(torch_, Z.astype(np.float32)), dt).cpu().numpy()
+    assert np.abs(J32 - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z.astype(np.float32).astype(np.float64), dt)).max() < 1e-4
+    # time-varying: residual at the returned x2 with the midpoint time, and the IFT Jacobian by complex step of a Newton solve
+    p0 = 1.7
+    tv = rd.CustomModel(2, 1, TV_BODY, params=[p0])
+    Zt, tt, ht = rng.random((64, 3)), rng.uniform(0, 3, 64), rng.uniform(0.01, 0.1, 64)
+    x2 = tv._h.discrete_dynamics(IM, Zt, ht, t=tt)
+    Jt = tv._h.discrete_jacobian(IM, Zt, ht, t=tt)
+    for k in range(0, 64, 5):
+        xm = 0.5 * (Zt[k, :2] + x2[k])
+        assert np.abs(Zt[k, :2] + ht[k] * _tv_f(xm, Zt[k, 2:], tt[k] + 0.5 * ht[k], p0) - x2[k]).max() < 1e-11
+
+        def solve(zz):                                    # Newton on the complexified residual (analytic in z)
+            x1, u = zz[:2], zz[2:]
+            x = x1.copy()
+            for _ in range(30):
+                r = lambda xx: x1 + ht[k] * _tv_f(0.5 * (x1 + xx), u, tt[k] + 0.5 * ht[k], p0) - xx
+                Jr = np.stack([(r(x + 1e-7 * np.eye(2)[j]) - r(x - 1e-7 * np.eye(2)[j])) / 2e-7 for j in range(2)], axis=1)
+                x = x - np.linalg.solve(Jr, r(x))
+            return x
+        assert np.abs(Jt[k].T - _cs_cols(solve, Zt[k])).max() < 1e-7
+    assert np.abs(tv._h.dynamics_error(IM, Zt, np.ascontiguousarray(x2), ht, t=tt)).max() < 1e-11
+    # 8 states, 2 controls: chain of four coupled pendula-like oscillators -> warp-cooperative kernel (16 lanes per knot)
+    body = """
+        return vec(get<4>(x), get<5>(x), get<6>(x), get<7>(x),
+                   -sin_(get<0>(x)) + p[0] * (get<1>(x) - get<0>(x)) + get<0>(u),
+                   -sin_(get<1>(x)) + p[0] * (get<0>(x) - T(2) * get<1>(x) + get<2>(x)),
+                   -sin_(get<2>(x)) + p[0] * (get<1>(x) - T(2) * get<2>(x) + get<3>(x)),
+                   -sin_(get<3>(x)) + p[0] * (get<2>(x) - get<3>(x)) + get<1>(u) * cos_(get<3>(x)));
+    """
+    ch = rd.CustomModel(8, 2, body, params=[0.8])
+    Zc, hc = rng.random((300, 10)), rng.uniform(0.01, 0.1, 300)
+    x2 = ch._h.discrete_dynamics(IM, Zc, hc)
+    J2, J1, e = ch._h.dynamics_error(IM, Zc, np.ascontiguousarray(x2), hc, jacobian=True)
+    assert np.abs(e).max() < 1e-11                           # the step solves the midpoint equation
+    Jc = ch._h.discrete_jacobian(IM, Zc, hc)
+    sol = -np.linalg.solve(o.as_matrix(J2)[:, :, :8], o.as_matrix(J1))
+    assert np.abs(o.as_matrix(Jc) - sol).max() < 1e-9        # and its Jacobian is the implicit-function-theorem one
+
+
+# ---- general LieState{R,P}: several rotations, any partition (src/liestate.jl:75-132, 210-320) ---------------------------------------
+TWO_BODY = """
+        // state [w1 (3), q1 (4), s (2), q2 (4), w2 (3)]: two attitudes driven by their body rates, a planar slider driven by u
+        auto kin = [&](const auto& q0, const auto& q1, const auto& q2, const auto& q3, const auto& wx, const auto& wy, const auto& wz) {
+            return vec(T(-0.5) * (q1 * wx + q2 * wy + q3 * wz), T(0.5) * (q0 * wx + q2 * wz - q3 * wy),
+                       T(0.5) * (q0 * wy - q1 * wz + q3 * wx), T(0.5) * (q0 * wz + q1 * wy - q2 * wx));
+        };
+        auto qa = kin(get<3>(x), get<4>(x), get<5>(x), get<6>(x), get<0>(x), get<1>(x), get<2>(x));
+        auto qb = kin(get<9>(x), get<10>(x), get<11>(x), get<12>(x), get<13>(x), get<14>(x), get<15>(x));
+        return vec(-p[0] * get<0>(x), get<0>(u) - get<1>(x), -get<2>(x) * get<1>(x),
+                   get<0>(qa), get<1>(qa), get<2>(qa), get<3>(qa),
+                   get<0>(u) * get<8>(x), get<1>(u) - get<7>(x),
+                   get<0>(qb), get<1>(qb), get<2>(qb), get<3>(qb),
+                   get<1>(u) * get<3>(x), -get<14>(x), p[1] * get<13>(x) * get<15>(x));
+"""
+
+
+def _two_body_f(z, p):
+    x, u = z[:16], z[16:]
+
+    def kin(q, w):
+        return 0.5 * np.array([-(q[1] * w[0] + q[2] * w[1] + q[3] * w[2]), q[0] * w[0] + q[2] * w[2] - q[3] * w[1],
+                               q[0] * w[1] - q[1] * w[2] + q[3] * w[0], q[0] * w[2] + q[1] * w[1] - q[2] * w[0]])
+    return np.concatenate([[-p[0] * x[0], u[0] - x[1], -x[2] * x[1]], kin(x[3:7], x[0:3]), [u[0] * x[8], u[1] - x[7]], kin(x[9:13], x[13:16]),
+                           [u[1] * x[3], -x[14], p[1] * x[13] * x[15]]])
+
+
+def _LH(q):
+    w, x, y, z = q / np.linalg.norm(q)
+    return np.array([[-x, -y, -z], [w, -z, y], [z, w, -x], [-y, x, w]])
+
+
+def test_general_liestate_two_rotations(rd, torch_):
+    """LieState(QuatRotation, (3, 2, 3)) == the reference's QuatState(16, (4, 10)) example (src/liestate.jl:93-100): errstate_dim 14,
+    G = blkdiag(I3, L(q1)H, I2, L(q2)H, I3), state_diff with one Cayley error per rotation, ∇G with one -(q.b) I3 block per rotation, and
+    the error-state Jacobian G(x+)' [A B] blkdiag(G(x), I) of a user model living on that state."""
+    ls = rd.QuatState(16, (4, 10))
+    assert ls.P == (3, 2, 3) and len(ls) == 16
+    p = [0.7, 0.3]
+    model = rd.CustomLieModel(ls, 2, TWO_BODY, params=p)
+    assert rd.dims(model) == (16, 2, 16) and rd.errstate_dim(model) == 14 and rd.jacobian_width(model) == 16
+    rng = np.random.default_rng(190)
+    N = 150
+
+    def rand_states(M):
+        X = rng.random((M, 16))
+        for s0 in (3, 9):
+            q = rng.standard_normal((M, 4)); X[:, s0:s0 + 4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        return X
+    X, X0 = rand_states(N), rand_states(N)
+    G = model._h.errstate_jacobian(X)                                      # (N, 14, 16): column-major 16 x 14 per knot
+    Gm = o.as_matrix(G)
+    for k in range(0, N, 13):
+        ref = np.zeros((16, 14))
+        ref[0:3, 0:3] = np.eye(3); ref[3:7, 3:6] = _LH(X[k, 3:7]); ref[7:9, 6:8] = np.eye(2); ref[9:13, 8:11] = _LH(X[k, 9:13]); ref[13:16, 11:14] = np.eye(3)
+        assert np.abs(Gm[k] - ref).max() < 1e-14
+    d = model._h.state_diff(dev(torch_, X), dev(torch_, X0)).cpu().numpy()
+    for k in range(0, N, 13):
+        ref = np.zeros(14)
+        ref[0:3] = X[k, 0:3] - X0[k, 0:3]; ref[6:8] = X[k, 7:9] - X0[k, 7:9]; ref[11:14] = X[k, 13:16] - X0[k, 13:16]
+        for s0, e0 in ((3, 3), (9, 8)):
+            q, q0 = X[k, s0:s0 + 4], X0[k, s0:s0 + 4]
+            Lq0c = np.array([[q0[0], q0[1], q0[2], q0[3]], [-q0[1], q0[0], q0[3], -q0[2]], [-q0[2], -q0[3], q0[0], q0[1]], [-q0[3], q0[2], -q0[1], q0[0]]])
+            e = Lq0c @ q                                                   # conj(q0) (x) q
+            ref[e0:e0 + 3] = e[1:] / e[0]
+        assert np.abs(d[k] - ref).max() < 1e-13
+    H = o.as_matrix(model._h.grad_errstate_jacobian(X, X0))
+    for k in range(0, N, 13):
+        ref = np.zeros((14, 14))
+        ref[3:6, 3:6] = -np.dot(X[k, 3:7], X0[k, 3:7]) * np.eye(3); ref[8:11, 8:11] = -np.dot(X[k, 9:13], X0[k, 9:13]) * np.eye(3)
+        assert np.abs(H[k] - ref).max() < 1e-14
+    # discrete Jacobian (plain forward mode: the kernels see a Euclidean user model) and its error-state projection
+    Z = np.concatenate([X, rng.random((N, 2))], axis=1)
+    h = 0.05
+    xn = np.empty((N, 16))
+    J = o.as_matrix(model._h.discrete_jacobian(o.RK4, Z, h, xn=xn))
+    Jb = o.as_matrix(model._h.discrete_error_jacobian(o.RK4, dev(torch_, Z), h).cpu().numpy())
+    Jbh = o.as_matrix(model._h.discrete_error_jacobian(o.RK4, Z, h))        # host pointers
+    assert Jb.shape == (N, 14, 16) and np.abs(Jb - Jbh).max() < 1e-15
+    for k in range(0, N, 13):
+        Jr, xr = _rk4_cs(lambda zz: _two_body_f(zz, p), Z[k], 16, h)
+        assert np.abs(J[k] - Jr).max() < 1e-10 and np.abs(xn[k] - xr).max() < 1e-12
+        Gx, Gn = o.as_matrix(model._h.errstate_jacobian(Z[k:k + 1, :16].copy()))[0], o.as_matrix(model._h.errstate_jacobian(xn[k:k + 1].copy()))[0]
+        ref = np.concatenate([Gn.T @ Jr[:, :16] @ Gx, Gn.T @ Jr[:, 16:]], axis=1)
+        assert np.abs(Jb[k] - ref).max() < 1e-10
+    # MRP partition with an empty leading block: LieState(MRP, (0, 4)) -> [p (3), v (4)], errstate_dim 7 == n (G is not the identity)
+    m2 = rd.CustomLieModel(rd.LieState(rd.MRP, 0, 4), 1, "return vec(get<3>(x), get<4>(x), get<5>(x), -get<0>(x), -get<1>(x), -get<2>(x), get<0>(u));")
+    Xm = rng.random((20, 7)) * 0.5
+    Gm2 = o.as_matrix(m2._h.errstate_jacobian(Xm))
+    for k in range(20):
+        pp = Xm[k, :3]
+        sk = np.array([[0, -pp[2], pp[1]], [pp[2], 0, -pp[0]], [-pp[1], pp[0], 0]])
+        ref = np.eye(7); ref[:3, :3] = (1 - pp @ pp) * np.eye(3) + 2 * (sk + np.outer(pp, pp))
+        assert np.abs(Gm2[k] - ref).max() < 1e-14
