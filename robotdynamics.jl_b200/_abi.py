@@ -286,9 +286,7 @@ class ModelHandle:
         self.time_varying = custom is not None          # user models may define dynamics(model, x, u, t)
         self._h = ctypes.c_void_p()
         pp = self.params.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-        if custom is not None and len(custom) == 2:      # (parts, m, body): user model over a general LieState{R,P}
-            raise TypeError("custom LieState models take (parts, m, body, 'lie')")
-        if custom is not None and len(custom) == 4 and custom[3] == "lie":
+        if custom is not None and len(custom) == 4 and isinstance(custom[3], str) and custom[3] == "lie":      # (parts, m, body, "lie")
             parts, m, body, _ = custom
             arr = (ctypes.c_int * len(parts))(*[int(v) for v in parts])
             check(lib().rdb_model_create_custom_lie(self.ctx._h, self.rot, len(parts), arr, int(m), body.encode(), pp, len(self.params),

@@ -963,12 +963,20 @@ int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int erro
     const int NZ = M->n + M->m, E = err ? M->nerr * (M->nerr + M->m) : M->n * NZ;
     RDB_CUDA(cudaEventRecord(T->ev_fork, st));
     for (auto& a : T->aux) RDB_CUDA(cudaStreamWaitEvent(a, T->ev_fork, 0));
+    // Spatial split of the GPU between the two stages.  A Jacobian CTA fills the register file of its SM, so a rollout warp can only run
+    // on an SM that holds none: with one-warp rollout CTAs spread over all SMs the two kernels would exclude each other and the pipeline
+    // would serialise (measured: slower than running the stages back to back).  Packed 8 warps per CTA the rollout needs R = ntraj / 256
+    // SMs — two latency-bound warps per scheduler cost it little — and the Jacobian kernel is launched for the other sm_count - R.
+    int R = nch > 1 ? int((T->ntraj + 255) / 256) : 0;
+    if (R > c->sm_count / 4) R = c->sm_count / 4;
+    const int rollout_block = (nch > 1 && T->ntraj >= 256) ? 256 : 0;
     long long row_lo = 0;                                // first knot whose Jacobian has not been enqueued yet
     for (int ch = 0; ch < nch; ++ch) {
         const int kb = int((long long)steps * ch / nch), ke = int((long long)steps * (ch + 1) / nch);
         if (ke > kb) {
             KnotRequest r = traj_request(T, Q, 0);
             r.op = OP_ROLLOUT; r.zmode = 1; r.kb = kb; r.ke = ke; r.X = T->Z; r.ntraj = T->ntraj; r.K = T->K; r.stream = T->aux[0];
+            r.rollout_block = rollout_block;
             if (int rc = dispatch(M, T->dtype, &r)) return rc;
         }
         RDB_CUDA(cudaEventRecord(T->ev_chunk[ch], T->aux[0]));
@@ -977,6 +985,8 @@ int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int erro
         if (row_hi > row_lo) {
             KnotRequest r = traj_request(T, Q, err);
             r.op = OP_KNOT; r.with_j = 1; r.N = (row_hi - row_lo) * T->ntraj; r.stream = T->aux[1];
+            if (rollout_block) r.dev.sm_count = c->sm_count - R;        // leave R SMs to the rollout (not after its last chunk)
+            if (ch == nch - 1) r.dev.sm_count = c->sm_count;
             r.Z = (const char*)T->Z + size_t(row_lo) * T->ntraj * NZ * es;
             r.dt = T->dt + row_lo * T->ntraj; if (r.t) r.t = T->t + row_lo * T->ntraj;
             r.J = (char*)J + size_t(row_lo) * T->ntraj * E * es;

@@ -204,8 +204,11 @@ __device__ __forceinline__ auto project_err(const XN& xn) {
 template <int NTHR, int ISSUERS>
 __device__ __forceinline__ void images_free_barrier(int tid) {
     if (tid < ISSUERS) bulk_wait_read0();      // bulk groups are per thread: every thread that issued stores waits for its own
-    __syncwarp();                              // bar.sync is an aligned barrier: the warp must be converged when it executes it
-    asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
+    __syncwarp();
+    // The roles (warp-uniform code paths) reach this barrier from role-specific program counters, so it is the NON-aligned form:
+    // `barrier.sync` lets the threads of a CTA arrive from different instructions (bar.sync == barrier.sync.aligned promises that every
+    // thread executes the same one, which compute-sanitizer's synccheck rightly reported for the round-1 form).
+    asm volatile("barrier.sync 1, %0;" ::"n"(NTHR) : "memory");
 }
 
 // this thread's [x;u] row from the smem image into registers.  Rows that are whole 16-byte units (n + m = 16, 18, ...) are read with
@@ -765,7 +768,7 @@ struct RolloutArgs {
 };
 template <class T, size_t... Is> __device__ __forceinline__ auto load_plain(const T* p, rstd::index_sequence<Is...>) { return vec(p[Is]...); }
 template <class Model, int Q, class T>
-__global__ void __launch_bounds__(32) rollout_kernel(const Model model, const RolloutArgs<T> a) {
+__global__ void __launch_bounds__(256) rollout_kernel(const Model model, const RolloutArgs<T> a) {
     constexpr int n = Model::n, m = Model::m;
     const long long tr = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (tr >= a.ntraj) return;

@@ -67,6 +67,24 @@ struct KnotConfigDefault<Model, double, true, Q, std::enable_if_t<(Model::n >= 1
 
 template <class Model, class T, bool WITH_J, int Q>
 struct KnotConfig : KnotConfigDefault<Model, T, WITH_J, Q> {};
+#if defined(RDB_TUNE_V_TILE) || defined(RDB_TUNE_V_MINB)      // tuning experiments on the value-only kernels (scripts/tune.py)
+template <class Model, class T, int Q>
+struct KnotConfig<Model, T, false, Q> {
+    using D = KnotConfigDefault<Model, T, false, Q>;
+#ifdef RDB_TUNE_V_TILE
+    static constexpr int TILE = RDB_TUNE_V_TILE;
+#else
+    static constexpr int TILE = D::TILE;
+#endif
+#ifdef RDB_TUNE_V_MINB
+    static constexpr int MINB = RDB_TUNE_V_MINB;
+#else
+    static constexpr int MINB = D::MINB;
+#endif
+    static constexpr int ROLL = 0;
+    using Chunks = typename D::Chunks;
+};
+#endif
 
 template <mask_t... Acc> struct nz_build {
     template <mask_t M> using add = std::conditional_t<M != 0, nz_build<Acc..., M>, nz_build<Acc...>>;
@@ -244,6 +262,7 @@ struct KnotRequest {
     //             zmode != 0: X is the knot-major batch Z (K, ntraj, n+m) holding the controls; steps [kb, ke)   (kernels.cuh)
     const void* x0; const void* U; void* X; long long ntraj; int K;
     int zmode, kb, ke;
+    int rollout_block;   // threads per CTA of the rollout kernel (0 -> 32: one warp per CTA, spread over the SMs)
     // OP_DYNERR (ImplicitMidpoint): dynamics_error / dynamics_error_jacobian! of the pairs (Z[k], Z2[k]): Z2 (N, ld2) holds x2, J2 -> de/dz2,
     // J -> de/dz1, out -> e
     const void* Z2; int ld2; void* J2;
@@ -314,9 +333,12 @@ inline int run_rollout(const KnotRequest& r) {
     else {
         ModelT<T> model; model.p = cast_params<T>(r.params);
         if (r.ntraj <= 0 || r.K <= 0) return 0;
-        // single-warp CTAs: 4096 trajectories = 128 warps, one per SM (the sweep is latency-bound: every warp gets a scheduler to itself)
-        const unsigned grid = unsigned((r.ntraj + 31) / 32);
-        rollout_kernel<ModelT<T>, Q, T><<<grid, 32, 0, r.stream>>>(model, rollout_args<T>(r, ModelT<T>::n, ModelT<T>::m));
+        // single-warp CTAs by default: 4096 trajectories = 128 warps, one per SM (the sweep is latency-bound: every warp gets a scheduler
+        // to itself).  The pipelined rollout + linearisation packs 8 warps per CTA instead, so that the rollout occupies FEW SMs and the
+        // Jacobian kernel — whose CTAs fill an SM's register file — keeps the rest (abi.cu: rdb_trajectory_rollout_linearize).
+        const int block = r.rollout_block > 0 ? r.rollout_block : 32;
+        const unsigned grid = unsigned((r.ntraj + block - 1) / block);
+        rollout_kernel<ModelT<T>, Q, T><<<grid, block, 0, r.stream>>>(model, rollout_args<T>(r, ModelT<T>::n, ModelT<T>::m));
         return int(cudaGetLastError());
     }
 }

@@ -113,6 +113,11 @@ VARIANTS["quadmrp64"] = {
     "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
     "4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
 }
+VARIANTS["cartpole_value"] = {"base": {}, "t128_minb8": dict(RDB_TUNE_V_TILE=128, RDB_TUNE_V_MINB=8), "t64_minb16": dict(RDB_TUNE_V_TILE=64, RDB_TUNE_V_MINB=16),
+                              "t64_minb12": dict(RDB_TUNE_V_TILE=64, RDB_TUNE_V_MINB=12), "t32_minb24": dict(RDB_TUNE_V_TILE=32, RDB_TUNE_V_MINB=24), "t256_minb4": dict(RDB_TUNE_V_TILE=256, RDB_TUNE_V_MINB=4)}
+UNIT["cartpole_value"] = UNIT["cartpole"]
+VARIANTS["quadrotor_value"] = {"base": {}, "t128_minb8": dict(RDB_TUNE_V_TILE=128, RDB_TUNE_V_MINB=8), "t64_minb12": dict(RDB_TUNE_V_TILE=64, RDB_TUNE_V_MINB=12)}
+UNIT["quadrotor_value"] = UNIT["quadrotor"]
 VARIANTS["satellite32"] = {"base": {}, "pad8": dict(RDB_ROWSTORE_MINWAY=8), "c9": dict(RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x3FE00u", RDB_TUNE_TILE=64, RDB_TUNE_MINB=3),
                            "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2)}
 
@@ -206,11 +211,42 @@ print(json.dumps({"us": us, "evals_per_s": N / (us * 1e-6), "GBs": gbs, "frac": 
 """
 
 
+_RUN_VALUE = r"""
+import sys, os, json
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+import rdb200 as rd
+import bench
+name = sys.argv[2]
+wl = "cartpole" if name.startswith("cartpole") else "quadrotor"
+desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
+N = 1 << 22 if wl == "cartpole" else 1 << 21
+mk, Q = bench.gpu_model(wl, rd)
+h = mk()._h
+nsets = 4
+Zs = [torch.from_numpy(bench.make_inputs(n, m, N, dtn, i)).cuda() for i in range(nsets)]
+Os = [torch.empty((N, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
+out = {}
+for label, op in (("discrete_dynamics", rd._abi.OP_DISCRETE_DYNAMICS), ("dynamics", rd._abi.OP_DYNAMICS)):
+    plans = [rd._abi.Plan(h, op, Q.code, Z, dt, out=O) for Z, O in zip(Zs, Os)]
+    for i in range(5): plans[i % nsets].launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(2000000); e0.record()
+    for i in range(50): plans[i % nsets].launch()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 50 * 1e3
+    es = Zs[0].element_size()
+    out[label] = {"us": round(us, 1), "frac": round(N * es * (2 * n + m) / (us * 1e-6) / 1e9 / 6551.4, 3)}
+print(json.dumps(out))
+"""
+
+
 def run_variants(workload, extra):
     libs = sorted(f for f in os.listdir(OUT) if f.startswith(workload + "_") and f.endswith(".so"))
     for lib in libs:
         env = dict(os.environ, RDB200_LIB=os.path.join(OUT, lib))
-        p = subprocess.run([sys.executable, "-c", _RUN_ONE, ROOT, workload] + extra, capture_output=True, text=True, env=env, timeout=600)
+        p = subprocess.run([sys.executable, "-c", _RUN_VALUE if workload.endswith("_value") else _RUN_ONE, ROOT, workload] + extra, capture_output=True, text=True, env=env, timeout=600)
         last = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-300:]
         print(f"{lib:40s} {last}", flush=True)
 

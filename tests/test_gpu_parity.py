@@ -854,7 +854,7 @@ def test_dynamics_error_and_its_jacobian(rd, torch_, name):
     I = np.eye(n)[None]
     assert np.abs(o.as_matrix(J1) - np.concatenate([I + 0.5 * h[:, :, None] * A, h[:, :, None] * Bm], axis=2)).max() < 1e-10
     assert np.abs(o.as_matrix(J2) - np.concatenate([0.5 * h[:, :, None] * A - I, np.zeros((N, n, m))], axis=2)).max() < 1e-10
-    assert np.array_equal(e3, ei)
+    assert np.abs(e3 - ei).max() < 1e-13                          # (plain and dual evaluations of f may round differently)
     # the residual vanishes at the implicit step, and the two Jacobians give the step's Jacobian by the implicit function theorem
     xn = gm._h.discrete_dynamics(IM, Z1, dt)
     assert np.abs(gm._h.dynamics_error(IM, Z1, np.ascontiguousarray(xn), dt)).max() < 1e-10
@@ -989,7 +989,7 @@ def test_general_liestate_two_rotations(rd, torch_):
             Lq0c = np.array([[q0[0], q0[1], q0[2], q0[3]], [-q0[1], q0[0], q0[3], -q0[2]], [-q0[2], -q0[3], q0[0], q0[1]], [-q0[3], q0[2], -q0[1], q0[0]]])
             e = Lq0c @ q                                                   # conj(q0) (x) q
             ref[e0:e0 + 3] = e[1:] / e[0]
-        assert np.abs(d[k] - ref).max() < 1e-13
+        assert np.abs(d[k] - ref).max() < 1e-13 * max(1.0, np.abs(ref).max())       # Cayley errors of near-half-turn rotations are large
     H = o.as_matrix(model._h.grad_errstate_jacobian(X, X0))
     for k in range(0, N, 13):
         ref = np.zeros((14, 14))
