@@ -208,9 +208,10 @@ int rdb_trajectory_rollout(rdb_trajectory* traj, int integrator, void* stream);
  * J (n, n+m, ntraj, K) — or, error_state != 0, Jbar (nerr, nerr+m, ntraj, K) as rdb_discrete_error_jacobian — host or device;
  * xn (n, ntraj, K) or NULL.  Terminal knots (dt = 0) give [I 0]. */
 int rdb_trajectory_linearize(rdb_trajectory* traj, int integrator, int error_state, void* J, void* xn, void* stream);
-/* Forward pass + linearisation in one call, pipelined on two internal streams: the rollout — sequential in k —
- * runs in `chunks` (0 = default 8) chunks of knots; the Jacobians of a finished chunk (a contiguous row range of the knot-major
- * batch) are evaluated at full-GPU rate while the next chunk is rolled out.  Joined back into `stream`; graph-capturable. */
+/* Forward pass + linearisation in one call.  chunks <= 1 (default): two phases on `stream` — the rollout writes
+ * z = [x;u] rows in place, one Jacobian launch then streams all K * ntraj knots at full-GPU rate.  chunks > 1: the measured
+ * alternative, a pipeline on two internal streams (rollout in chunks of knots, Jacobians of each finished chunk — a contiguous row
+ * range of the knot-major batch — meanwhile), joined back into `stream`; on B200 it is slower than the two phases. */
 int rdb_trajectory_rollout_linearize(rdb_trajectory* traj, int integrator, int error_state, int chunks, void* J, void* stream);
 
 #ifdef __cplusplus

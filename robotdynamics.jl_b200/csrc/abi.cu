@@ -932,10 +932,14 @@ int rdb_trajectory_linearize(rdb_trajectory* T, int integrator, int error_state,
     return knot_op(T->M, Q, T->dtype, RDB_AOS, 1, T->ntraj * T->K, T->Z, T->t, T->dt, 0.0, J, xn, stream, error_state ? 1 : 0);
 }
 
-// Forward pass + linearisation as a two-stream pipeline: the rollout (latency-bound: one thread per trajectory, sequential in k) runs
-// in chunks of knots on one stream; as soon as a chunk's states exist, the Jacobians of that chunk — a contiguous range of rows in
-// the knot-major batch — are evaluated at full-GPU rate on the other stream while the next chunk is rolled out.  Fork / join by
-// events from the caller's stream, so the whole call is still one asynchronous unit of work on `stream` (and is graph-capturable).
+// Forward pass + linearisation in one call.  Default (chunks <= 1): TWO PHASES on the caller's stream — the rollout kernel (latency-bound:
+// one thread per trajectory, sequential in k) writes z = [x;u] rows in place, then ONE Jacobian launch streams all K * ntraj knots at
+// full-GPU rate.  chunks > 1 is the measured alternative, a two-stream pipeline: the rollout runs in chunks of knots on one stream and the
+// Jacobians of a finished chunk (a contiguous row range of the knot-major batch) on another while the next chunk is rolled out, forked
+// from / joined into `stream` by events.  On B200 it LOSES (4096 x 256 quadrotor fp32: two-phase 0.44 ms, pipelined 0.61-0.77 ms;
+// profiles/rollout_r02.md): a Jacobian CTA fills its SM's register file, so the two kernels exclude each other SM by SM, the rollout
+// warps that do share an SM lose issue slots to FP32-issue-bound neighbours, and the sequential stage — the critical path — gets
+// slower; packing the rollout onto 16 SMs and capping the Jacobian grid to the other 132 was worse still (0.67-0.70 ms).
 int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int error_state, int chunks, void* J, void* stream) {
     const int Q = map_q(integrator);
     if (!T || Q < 0 || !J || chunks < 0) return RDB_ERR_ARG;
@@ -948,9 +952,13 @@ int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int erro
         if (int rc = rdb_trajectory_rollout(T, integrator, stream)) return rc;
         return rdb_trajectory_linearize(T, integrator, error_state, J, nullptr, stream);
     }
+    if (chunks <= 1) {
+        if (int rc = rdb_trajectory_rollout(T, integrator, stream)) return rc;
+        return rdb_trajectory_linearize(T, integrator, error_state, J, nullptr, stream);
+    }
     std::lock_guard<std::mutex> lock(T->mu);
     const int steps = T->K - 1;
-    int nch = chunks > 0 ? chunks : 8;
+    int nch = chunks;
     if (nch > steps) nch = steps > 0 ? steps : 1;
     while ((int)T->ev_chunk.size() < nch) {
         cudaEvent_t ev;
@@ -963,20 +971,12 @@ int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int erro
     const int NZ = M->n + M->m, E = err ? M->nerr * (M->nerr + M->m) : M->n * NZ;
     RDB_CUDA(cudaEventRecord(T->ev_fork, st));
     for (auto& a : T->aux) RDB_CUDA(cudaStreamWaitEvent(a, T->ev_fork, 0));
-    // Spatial split of the GPU between the two stages.  A Jacobian CTA fills the register file of its SM, so a rollout warp can only run
-    // on an SM that holds none: with one-warp rollout CTAs spread over all SMs the two kernels would exclude each other and the pipeline
-    // would serialise (measured: slower than running the stages back to back).  Packed 8 warps per CTA the rollout needs R = ntraj / 256
-    // SMs — two latency-bound warps per scheduler cost it little — and the Jacobian kernel is launched for the other sm_count - R.
-    int R = nch > 1 ? int((T->ntraj + 255) / 256) : 0;
-    if (R > c->sm_count / 4) R = c->sm_count / 4;
-    const int rollout_block = (nch > 1 && T->ntraj >= 256) ? 256 : 0;
     long long row_lo = 0;                                // first knot whose Jacobian has not been enqueued yet
     for (int ch = 0; ch < nch; ++ch) {
         const int kb = int((long long)steps * ch / nch), ke = int((long long)steps * (ch + 1) / nch);
         if (ke > kb) {
             KnotRequest r = traj_request(T, Q, 0);
             r.op = OP_ROLLOUT; r.zmode = 1; r.kb = kb; r.ke = ke; r.X = T->Z; r.ntraj = T->ntraj; r.K = T->K; r.stream = T->aux[0];
-            r.rollout_block = rollout_block;
             if (int rc = dispatch(M, T->dtype, &r)) return rc;
         }
         RDB_CUDA(cudaEventRecord(T->ev_chunk[ch], T->aux[0]));
@@ -985,8 +985,6 @@ int rdb_trajectory_rollout_linearize(rdb_trajectory* T, int integrator, int erro
         if (row_hi > row_lo) {
             KnotRequest r = traj_request(T, Q, err);
             r.op = OP_KNOT; r.with_j = 1; r.N = (row_hi - row_lo) * T->ntraj; r.stream = T->aux[1];
-            if (rollout_block) r.dev.sm_count = c->sm_count - R;        // leave R SMs to the rollout (not after its last chunk)
-            if (ch == nch - 1) r.dev.sm_count = c->sm_count;
             r.Z = (const char*)T->Z + size_t(row_lo) * T->ntraj * NZ * es;
             r.dt = T->dt + row_lo * T->ntraj; if (r.t) r.t = T->t + row_lo * T->ntraj;
             r.J = (char*)J + size_t(row_lo) * T->ntraj * E * es;

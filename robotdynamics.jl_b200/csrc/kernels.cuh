@@ -664,6 +664,202 @@ __global__ void __launch_bounds__(128) implicit_midpoint_warp_kernel(const Model
     }
 }
 
+// ---- ImplicitMidpoint, group-cooperative (round 2) -------------------------------------------------------------------------------------
+// The warp kernel above spends one warp on ONE knot and broadcasts every multiplier of the elimination by a shuffle that serves one
+// knot: ~730 shuffles per knot, and 32 lanes evaluating f with one partial each.  Here a group of L lanes (4 for fp32, 8 for fp64:
+// 8 / 4 knots per warp) shares a knot and lane g owns the columns c = g, g + L, g + 2L, ... of every matrix, in registers:
+//   * [A B] by ONE forward-mode evaluation of f per lane with S = ceil((n+m)/L) run-time-seeded partials (slot s of lane g is column
+//     s L + g);
+//   * M = h/2 A - I and the right-hand sides are eliminated by Gauss-Jordan with partial pivoting: the lane that owns pivot column k
+//     finds the pivot and the multipliers, ONE shuffle per multiplier serves all the knots of the warp, and every lane updates its own
+//     columns (the pivot-row entries it needs are its own);  the Newton residual is replicated on the lanes and eliminated along.
+// Same iteration as the reference (src/integration.jl:422-463: Newton from x2 = x1, at most 10 iterations, residual and Jacobians
+// evaluated before the test ||r||_2 < tol) and the same implicit-function-theorem Jacobian (src/integration.jl:524-543).
+template <class T, int S, int L, int I>
+__device__ __forceinline__ auto group_dual(T v, int g) {
+    SD<T, ((mask_t(1) << S) - 1u)> r; r.v = v;
+#pragma unroll
+    for (int s = 0; s < S; ++s) r.d[s] = PK<T>::splat((s * L + g == I) ? T(1) : T(0));
+    return r;
+}
+template <class T, int S, int L, size_t... Is>
+__device__ __forceinline__ auto load_group_seeded(const T* z, int g, rstd::index_sequence<Is...>) { return vec(group_dual<T, S, L, int(Is)>(z[Is], g)...); }
+
+// Gauss-Jordan on [M | R | b]: lane g of each L-lane group holds the columns s L + g of M (SA slots) and of R (SR slots, may be 0) and a
+// replicated copy of b.  On return R and b hold M^{-1} R and M^{-1} b.  Rows are swapped only when some group of the warp needs it.
+template <class T, int N_, int SA, int SR, int L, bool WITH_B>
+__device__ __forceinline__ void group_gauss_jordan(T (&M)[SA][N_], T (&R)[SR > 0 ? SR : 1][N_], T (&b)[N_], int g) {
+    constexpr unsigned FULL = 0xffffffffu;
+    T pinv[N_];
+#pragma unroll
+    for (int k = 0; k < N_; ++k) {
+        constexpr int dummy = 0; (void)dummy;
+        const int sk = k / L, gk = k % L;              // slot and owner lane of pivot column k (compile-time after unrolling)
+        T mx = T(0);
+#pragma unroll
+        for (int i = k + 1; i < N_; ++i) mx = fmax(mx, fabs(M[sk][i]));
+        const int need = __shfl_sync(FULL, int(mx > fabs(M[sk][k])), gk, L);
+        if (__any_sync(FULL, need)) {
+            int p = k;
+            T best = fabs(M[sk][k]);
+#pragma unroll
+            for (int i = k + 1; i < N_; ++i) { const T v = fabs(M[sk][i]); if (v > best) { best = v; p = i; } }
+            p = __shfl_sync(FULL, p, gk, L);
+#pragma unroll
+            for (int s = 0; s < SA; ++s) {
+                const T wk = M[s][k]; T wp = wk;
+#pragma unroll
+                for (int i = k + 1; i < N_; ++i) { wp = sel_eq(p, i, M[s][i], wp); M[s][i] = sel_eq(p, i, wk, M[s][i]); }
+                M[s][k] = wp;
+            }
+            if constexpr (SR > 0) {
+#pragma unroll
+                for (int s = 0; s < SR; ++s) {
+                    const T wk = R[s][k]; T wp = wk;
+#pragma unroll
+                    for (int i = k + 1; i < N_; ++i) { wp = sel_eq(p, i, R[s][i], wp); R[s][i] = sel_eq(p, i, wk, R[s][i]); }
+                    R[s][k] = wp;
+                }
+            }
+            if constexpr (WITH_B) {
+                const T wk = b[k]; T wp = wk;
+#pragma unroll
+                for (int i = k + 1; i < N_; ++i) { wp = sel_eq(p, i, b[i], wp); b[i] = sel_eq(p, i, wk, b[i]); }
+                b[k] = wp;
+            }
+        }
+        const T inv = T(1) / M[sk][k];
+        pinv[k] = __shfl_sync(FULL, inv, gk, L);
+#pragma unroll
+        for (int i = 0; i < N_; ++i) {
+            if (i == k) continue;
+            const T l = __shfl_sync(FULL, M[sk][i] * inv, gk, L);
+#pragma unroll
+            for (int s = sk; s < SA; ++s) M[s][i] = fma_(-l, M[s][k], M[s][i]);       // columns left of the pivot are already e_c D_c
+            if constexpr (SR > 0) {
+#pragma unroll
+                for (int s = 0; s < SR; ++s) R[s][i] = fma_(-l, R[s][k], R[s][i]);
+            }
+            if constexpr (WITH_B) b[i] = fma_(-l, b[k], b[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N_; ++i) {
+        if constexpr (WITH_B) b[i] *= pinv[i];
+        if constexpr (SR > 0) {
+#pragma unroll
+            for (int s = 0; s < SR; ++s) R[s][i] *= pinv[i];
+        }
+    }
+}
+
+// threads per CTA of the group kernel: two warps, so that the per-warp output image (below) stays a static allocation for fp64
+constexpr int IMG_THREADS = 64;
+template <class Model, class T, bool WITH_J, int L>
+__global__ void __launch_bounds__(IMG_THREADS) implicit_midpoint_group_kernel(const Model model, const KnotArgs<T> a) {
+    constexpr int n = Model::n, m = Model::m, NZ = n + m;
+    constexpr int SA = (n + L - 1) / L, SZ = (NZ + L - 1) / L;
+    static_assert(SZ <= 8 && (32 % L) == 0, "group size too small for this model");
+    // The Jacobians of the 32 / L knots of a warp are ONE contiguous byte range of J.  Each lane owns scattered columns of them, so the
+    // columns are assembled in a per-warp shared-memory image and leave by full-line coalesced stores (the direct form — 4-byte stores
+    // 52 bytes apart within a knot and 884 bytes apart between knots — showed up as lg_throttle / long_scoreboard stalls in ncu).
+    constexpr int KPW = 32 / L, E = n * NZ;
+    constexpr bool STAGE = WITH_J && size_t(IMG_THREADS / 32) * KPW * E * sizeof(T) <= 40 * 1024;
+    __shared__ T jimg[STAGE ? (IMG_THREADS / 32) * KPW * E : 1];
+    constexpr mask_t DENSE = (mask_t(1) << SZ) - 1u;
+    constexpr unsigned FULL = 0xffffffffu;
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int g = int(threadIdx.x) % L;
+    const bool valid = gtid / L < a.N;
+    const long long k = valid ? gtid / L : a.N - 1;           // lanes past the end shadow the last knot (shuffles stay convergent)
+    const T* zg = a.Z + k * NZ;
+    const T h = T(a.dt ? a.dt[k] : a.dt0);
+    T tm = T(0);
+    if constexpr (uses_time<Model>::value) tm = T(a.t ? a.t[k] : 0.0) + T(0.5) * h;
+    const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);
+    T z[NZ], zm[NZ], x2[n], W[SZ][n], r[n];
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) { z[i] = zg[i]; zm[i] = z[i]; }
+#pragma unroll
+    for (int i = 0; i < n; ++i) x2[i] = z[i];
+    bool done = false;
+#pragma unroll 1
+    for (int iter = 0; iter < 10; ++iter) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) zm[i] = (z[i] + x2[i]) * T(0.5);
+        model.reset();
+        {
+            auto zz = load_group_seeded<T, SZ, L>(zm, g, rstd::make_index_sequence<size_t(NZ)>{});
+            auto f = feval<T>(model, slice<0, n>(zz), slice<n, m>(zz), tm);
+            put_vals(f, r, rstd::make_index_sequence<size_t(n)>{});
+            put_cols<n, DENSE, false>(f, &W[0][0], rstd::make_index_sequence<size_t(SZ)>{});      // W[s][i] = d f_i / d z_{s L + g}
+        }
+        T nrm = T(0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { r[i] = z[i] + h * r[i] - x2[i]; nrm += r[i] * r[i]; }
+        const bool conv = sqrt(nrm) < tol;                     // the residual is replicated: uniform within the group
+        if (!done && conv) done = true;
+        if (__all_sync(FULL, done)) break;
+        T Mc[SA][n], none[1][n];
+#pragma unroll
+        for (int s = 0; s < SA; ++s)
+#pragma unroll
+            for (int i = 0; i < n; ++i) Mc[s][i] = (s * L + g < n) ? T(0.5) * h * W[s][i] - ((s * L + g == i) ? T(1) : T(0)) : T(0);
+        group_gauss_jordan<T, n, SA, 0, L, true>(Mc, none, r, g);   // all lanes take part; groups that are done discard the step
+        if (!done) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) x2[i] -= r[i];
+        }
+    }
+    if (valid && g == 0 && a.out) { T* o = a.out + k * n;
+#pragma unroll
+        for (int i = 0; i < n; ++i) o[i] = x2[i]; }
+    if constexpr (WITH_J) {
+        if (a.J) {                                             // uniform over the grid
+            // J = -(h/2 A - I) \ [I + h/2 A, h B] from the last evaluated iterate, one column per (lane, slot)
+            T Mc[SA][n];
+#pragma unroll
+            for (int s = 0; s < SA; ++s)
+#pragma unroll
+                for (int i = 0; i < n; ++i) Mc[s][i] = (s * L + g < n) ? T(0.5) * h * W[s][i] - ((s * L + g == i) ? T(1) : T(0)) : T(0);
+#pragma unroll
+            for (int s = 0; s < SZ; ++s)
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const int c = s * L + g;
+                    const T ha = h * W[s][i];
+                    W[s][i] = c < n ? T(0.5) * ha + ((c == i) ? T(1) : T(0)) : (c < NZ ? ha : T(0));
+                }
+            group_gauss_jordan<T, n, SA, SZ, L, false>(Mc, W, r, g);
+            if constexpr (STAGE) {
+                const int lane = int(threadIdx.x) & 31, warp = int(threadIdx.x) >> 5;
+                T* img = jimg + warp * (KPW * E);
+#pragma unroll
+                for (int s = 0; s < SZ; ++s) {
+                    const int c = s * L + g;
+                    if (c < NZ) { T* col = img + (lane / L) * E + n * c;
+#pragma unroll
+                        for (int i = 0; i < n; ++i) col[i] = -W[s][i]; }
+                }
+                __syncwarp();
+                const long long k0w = (gtid - lane) / L;                       // first knot of this warp
+                const long long left = a.N - k0w;
+                const int cnt = left >= KPW ? KPW * E : (left > 0 ? int(left) * E : 0);
+                T* Jo = a.J + k0w * (long long)E;
+                for (int e = lane; e < cnt; e += 32) Jo[e] = img[e];
+            } else {
+#pragma unroll
+                for (int s = 0; s < SZ; ++s) {
+                    const int c = s * L + g;
+                    if (valid && c < NZ) { T* Jo = a.J + k * (long long)(n * NZ) + n * c;
+#pragma unroll
+                        for (int i = 0; i < n; ++i) Jo[i] = -W[s][i]; }
+                }
+            }
+        }
+    }
+}
+
 // ---- dynamics_error / dynamics_error_jacobian! for ImplicitMidpoint ---------------------------------------------------------------
 // e = x1 + h f((x1 + x2)/2, u1, t + h/2) - x2   (reference: src/integration.jl:640-654);  J1 = de/dz1 = [I + h/2 A, h B],
 // J2 = de/dz2 = [h/2 A - I, 0]  (src/integration.jl:674-700), A, B the continuous Jacobian at the midpoint (evaluated at t + h/2 like

@@ -1,6 +1,7 @@
 // launch.cuh — per-(model, dtype) tiling configuration and the host-side launcher of knot_kernel.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link dependency)
 #include "kernels.cuh"
 
@@ -306,7 +307,25 @@ inline int run_implicit(const KnotRequest& r) {
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
     if constexpr (ModelT<T>::n >= RDB_IMPLICIT_WARP_MIN_N && ModelT<T>::n + ModelT<T>::m <= 32) {
-        // rigid bodies: one knot per group of GS lanes, one column of [A B] per lane, LU across the lanes by warp shuffles
+        // rigid bodies: a group of lanes per knot, the columns of [A B] dealt round-robin to the lanes, Gauss-Jordan across the group
+        // (kernels.cuh: implicit_midpoint_group_kernel).  RDB200_IMPLICIT_WARP=1 selects the round-1 kernel (one warp-wide group per knot,
+        // one column per lane) for comparison.
+        static const bool use_warp = []() { const char* e = std::getenv("RDB200_IMPLICIT_WARP"); return e && e[0] == '1'; }();
+        if (!use_warp) {
+            // lanes per knot: 4 (8 knots per warp) measured best for both dtypes (quadrotor fp32 612 vs 710 us with 8 lanes; satellite{MRP}
+            // fp64 1230 vs 1656 us; quadrotor fp64 equal); RDB200_IMPLICIT_L=4|8 overrides it for experiments
+            static const int forced = []() { const char* e = std::getenv("RDB200_IMPLICIT_L"); return e ? std::atoi(e) : 0; }();
+            const int L = forced == 4 || forced == 8 ? forced : 4;
+            const unsigned grid = unsigned((r.N * L + IMG_THREADS - 1) / IMG_THREADS);
+            if (L == 4) {
+                if (r.with_j) implicit_midpoint_group_kernel<ModelT<T>, T, true, 4><<<grid, IMG_THREADS, 0, r.stream>>>(model, a);
+                else implicit_midpoint_group_kernel<ModelT<T>, T, false, 4><<<grid, IMG_THREADS, 0, r.stream>>>(model, a);
+            } else {
+                if (r.with_j) implicit_midpoint_group_kernel<ModelT<T>, T, true, 8><<<grid, IMG_THREADS, 0, r.stream>>>(model, a);
+                else implicit_midpoint_group_kernel<ModelT<T>, T, false, 8><<<grid, IMG_THREADS, 0, r.stream>>>(model, a);
+            }
+            return int(cudaGetLastError());
+        }
         constexpr int GS = (ModelT<T>::n + ModelT<T>::m <= 16) ? 16 : 32;
         const unsigned grid = unsigned((r.N * GS + 127) / 128);
         if (r.with_j) implicit_midpoint_warp_kernel<ModelT<T>, T, true, GS><<<grid, 128, 0, r.stream>>>(model, a);

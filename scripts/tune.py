@@ -83,6 +83,9 @@ VARIANTS = {
         "t64_minb8": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=8),
         "t64_minb7": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=7),
         "roll1_minb16": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=16, RDB_TUNE_ROLL=1),
+        "t64_minb9": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=9),
+        "t96_minb6": dict(RDB_TUNE_TILE=96, RDB_TUNE_MINB=6),
+        "t128_minb4": dict(RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
     },
     "satellite": {
         "base": {},
@@ -157,8 +160,10 @@ def build_variants(workload):
         os.remove(obj)
         return tag, info
 
+    only = os.environ.get("TUNE_ONLY")
+    items = [(k, v) for k, v in VARIANTS[workload].items() if not only or k in only.split(",")]
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
-        for tag, info in ex.map(lambda kv: one(*kv), VARIANTS[workload].items()):
+        for tag, info in ex.map(lambda kv: one(*kv), items):
             print(f"{workload}_{tag}: {info}", flush=True)
 
 
