@@ -258,10 +258,12 @@ def _full_size_check(rd, torch, gm, om, Q, N, dtype, dt, tol):
     Zd = dev(torch, Z)
     xn = torch.empty((N, n), dtype=Zd.dtype, device="cuda")
     J = gm._h.discrete_jacobian(Q, Zd, dt, xn=xn)
-    # (a) strided sample against the oracle
-    idx = np.arange(0, N, 997)
-    Jo = o.discrete_jacobian(om, Q, Z[idx].astype(np.float64), dt)
-    assert np.abs(J[torch.from_numpy(idx).cuda()].cpu().numpy() - Jo).max() < tol
+    # (a) EVERY knot of the full-size batch against the oracle (all host threads: a few hundred milliseconds), x+ too
+    Jo = o.discrete_jacobian(om, Q, Z.astype(np.float64), dt, nthreads=o.num_procs())
+    assert np.abs(J.cpu().numpy() - Jo).max() < tol
+    xo = o.discrete_dynamics(om, Q, Z.astype(np.float64), dt, nthreads=o.num_procs())
+    assert np.abs(xn.cpu().numpy() - xo).max() < tol
+    del Jo, xo
     # (b) directional finite difference of the GPU's own discrete_dynamics agrees with J d (fp64 arithmetic for the check)
     Z64 = Zd.double()
     d = torch.from_numpy(rng.standard_normal((N, n + m))).cuda()
@@ -1018,3 +1020,17 @@ def test_general_liestate_two_rotations(rd, torch_):
         sk = np.array([[0, -pp[2], pp[1]], [pp[2], 0, -pp[0]], [-pp[1], pp[0], 0]])
         ref = np.eye(7); ref[:3, :3] = (1 - pp @ pp) * np.eye(3) + 2 * (sk + np.outer(pp, pp))
         assert np.abs(Gm2[k] - ref).max() < 1e-14
+
+
+def test_c_abi_from_plain_c_on_the_gpu(tmp_path):
+    """examples/c_abi_example.c — plain C99 against include/rdb200.h, no Python, no torch in the process — computes on the GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "rdb_example")
+    libdir = os.path.join(root, "robotdynamics.jl_b200")
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_example.c"),
+                        "-o", exe, "-L", libdir, "-lrdb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "[A B] of knot 0" in r.stdout, r.stdout + r.stderr
