@@ -9,7 +9,7 @@
 # NOT executed in this repository's build image (no Julia there; see DESIGN.md §3).  The Python mirror of the same interface
 # (robotdynamics.jl_b200/api.py) runs the equivalent assertions in tests/test_gpu_parity.py::test_reference_api_*.
 using Test
-using RobotDynamics, Rotations, StaticArrays, ForwardDiff, LinearAlgebra, Random
+using RobotDynamics, Rotations, StaticArrays, ForwardDiff, FiniteDiff, LinearAlgebra, Random
 const RD = RobotDynamics
 const REF = get(ENV, "RD_REF", pkgdir(RobotDynamics))
 include(joinpath(REF, "test", "cartpole_model.jl"))

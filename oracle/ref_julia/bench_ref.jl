@@ -8,7 +8,7 @@
 # TEST / BASELINE INFRASTRUCTURE ONLY; not executed in this repository's build image (no Julia there).
 import Pkg
 haskey(ENV, "RD_REF") && Pkg.develop(path=ENV["RD_REF"])
-using RobotDynamics, Rotations, StaticArrays, ForwardDiff, LinearAlgebra, Random
+using RobotDynamics, Rotations, StaticArrays, ForwardDiff, FiniteDiff, LinearAlgebra, Random   # (@autodiff-generated methods name ForwardDiff / FiniteDiff in the caller's module)
 const RD = RobotDynamics
 const REF = get(ENV, "RD_REF", pkgdir(RobotDynamics))
 include(joinpath(REF, "test", "cartpole_model.jl"))

@@ -29,7 +29,7 @@ if haskey(ENV, "RD_REF")
     Pkg.develop(path=ENV["RD_REF"])
 end
 
-using RobotDynamics, Rotations, StaticArrays, ForwardDiff, LinearAlgebra
+using RobotDynamics, Rotations, StaticArrays, ForwardDiff, FiniteDiff, LinearAlgebra   # (@autodiff-generated methods name ForwardDiff / FiniteDiff in the caller's module)
 const RD = RobotDynamics
 
 const REPO = normpath(joinpath(@__DIR__, "..", ".."))
