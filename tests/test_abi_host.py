@@ -197,3 +197,57 @@ def test_user_rigid_body_wrench_compiles_without_a_gpu():
     assert ok, log
     ok, log = rd._abi.custom_rigid_check(rd._abi.ROT_MRP, 1, 4, "return vec(get<0>(u), oops);", 0)
     assert not ok and "oops" in log
+
+
+# ---- round 2: host-side logic that needs no GPU --------------------------------------------------------------------------------------
+def test_buffer_validation_refuses_what_would_be_out_of_bounds():
+    """_abi.check_buffer: caller-supplied arrays are bare pointers for the C ABI, so kind / dtype / shape / contiguity mismatches are
+    refused in the host mirror (ADVICE: a float32 or short J with a float64 Z would be an out-of-bounds write)."""
+    import rdb200
+    cb = rdb200._abi.check_buffer
+    Z = np.zeros((8, 5))
+    assert cb("J", None, (8, 5, 4), Z) is None
+    assert cb("J", np.empty((8, 5, 4)), (8, 5, 4), Z).shape == (8, 5, 4)
+    with pytest.raises(TypeError):
+        cb("J", np.empty((8, 5, 4), dtype=np.float32), (8, 5, 4), Z)
+    with pytest.raises(ValueError):
+        cb("J", np.empty((7, 5, 4)), (8, 5, 4), Z)
+    with pytest.raises(ValueError):
+        cb("J", np.empty((8, 4, 5)).transpose(0, 2, 1), (8, 5, 4), Z)
+    with pytest.raises(ValueError):
+        cb("J", [[0.0]], (1, 1), Z)
+    import torch
+    with pytest.raises(rdb200.RDBError) as e:
+        cb("J", torch.empty((8, 5, 4), dtype=torch.float64), (8, 5, 4), Z)          # torch tensor with numpy inputs
+    assert e.value.code == rdb200._abi.ERR_POINTER_MIX
+
+
+def test_liestate_index_algebra_matches_the_reference_examples():
+    """LieState / QuatState (src/liestate.jl:75-132): the docstring example QuatState(16, (4, 10)) is [v3, q, v2, q, v3]."""
+    import rdb200 as rd
+    ls = rd.QuatState(16, (4, 10))
+    assert ls.P == (3, 2, 3) and len(ls) == 16
+    assert rd.QuatState(13, (4,)).P == (3, 6) and len(rd.LieState(rd.MRP, 3, 6)) == 12         # RigidBody's LieState(R, (3, 6))
+    assert len(rd.LieState(rd.RodriguesParam, (0, 4))) == 7 and rd.LieState(rd.QuatRotation, 0, 0, 0).P == (0, 0, 0)
+
+
+def test_plan_and_trajectory_entry_points_refuse_bad_arguments_without_a_gpu():
+    import rdb200
+    L = _lib()
+    vp = ctypes.c_void_p()
+    assert L.rdb_plan_create(None, 3, 3, 1, 0, 8, None, None, None, 0.01, None, None, ctypes.byref(vp)) == rdb200._abi.ERR_ARG
+    assert L.rdb_plan_launch(None, None) == rdb200._abi.ERR_ARG and L.rdb_plan_destroy(None) == 0
+    assert L.rdb_trajectory_create(None, 1, 4, 16, ctypes.byref(vp)) == rdb200._abi.ERR_ARG
+    assert L.rdb_trajectory_rollout(None, 3, None) == rdb200._abi.ERR_ARG and L.rdb_trajectory_destroy(None) == 0
+    assert L.rdb_dynamics_error(None, 3, 1, 8, None, None, 5, None, None, 0.01, None, None) == rdb200._abi.ERR_ARG
+    parts = (ctypes.c_int * 3)(3, 2, 3)
+    assert L.rdb_model_create_custom_lie(None, 1, 3, parts, 2, b"return x;", None, 0, ctypes.byref(vp)) == rdb200._abi.ERR_ARG
+
+
+def test_user_model_bodies_with_time_compile_without_a_gpu():
+    """dynamics(model, x, u, t): a user body may read `t` (a plain scalar); checked by the compile-only entry point (NVRTC, sm_100a)."""
+    import rdb200 as rd
+    ok, log = rd._abi.custom_check(2, 1, "return vec(get<1>(x), cos_(T(3) * t) * get<0>(u) - p[0] * sin_(get<0>(x)) + t * get<1>(x));", 1)
+    assert ok, log
+    ok, log = rd._abi.custom_check(2, 1, "return vec(get<1>(x), tt * get<0>(u));", 0, rd.F32)
+    assert not ok and "tt" in log
