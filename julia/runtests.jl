@@ -129,7 +129,7 @@ end
     @test h.ptr != C_NULL
 end
 
+struct NoKernel <: RD.ContinuousDynamics end          # (type definitions must be at top level)
 @testset "Errors map to the reference's exceptions" begin
-    struct NoKernel <: RD.ContinuousDynamics end
     @test_throws RD.NotImplementedError B.handle(NoKernel())
 end

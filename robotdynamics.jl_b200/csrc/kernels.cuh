@@ -388,11 +388,24 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
 
     long long tile = blockIdx.x;
     if (tile < ntiles && tile_tma(tile) && tid == 0) load_tile(tile, 0);
+    // Per-knot steps and times (KnotPoint.dt / .t as arrays: trajectories, the mixed sweep) are plain global loads, one per thread.
+    // Issued where they are used they cost every warp of the CTA a DRAM round trip at the top of EVERY tile (all warps of a
+    // register-filling rigid-body CTA stall together: ~10 % of the tile time); they are therefore requested ONE TILE AHEAD — the volatile
+    // load is issued here, its register is first read a whole tile of arithmetic later.
+    auto knot_scalar = [&](const double* p, long long k) -> double { return (p && k < N) ? *reinterpret_cast<const volatile double*>(p + k) : 0.0; };
+    double h_next = 0.0, t_next = 0.0;
+    if constexpr (Q != Q_CONTINUOUS) { if (a.dt) h_next = knot_scalar(a.dt, tile * TILE + kt); }
+    if constexpr (uses_time<Model>::value) t_next = knot_scalar(a.t, tile * TILE + kt);
     uint32_t phase[2] = {0, 0};
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
         const long long k0 = tile * TILE;
         const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
+        const double h_cur = h_next, t_cur = t_next;
+        if (tile + gridDim.x < ntiles) {
+            if constexpr (Q != Q_CONTINUOUS) { if (a.dt) h_next = knot_scalar(a.dt, (tile + gridDim.x) * TILE + kt); }
+            if constexpr (uses_time<Model>::value) t_next = knot_scalar(a.t, (tile + gridDim.x) * TILE + kt);
+        }
         const long long nxt = tile + gridDim.x;
         // (1) prefetch the next tile's [x;u] rows (buffer s^1 was last read before the previous iteration's barriers)
         if (tid == 0 && nxt < ntiles && tile_tma(nxt)) load_tile(nxt, s ^ 1);
@@ -404,10 +417,10 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         const T* zrow = SOA ? in_img[s] + kt : in_img[s] + kt * NZ;
         constexpr int ES = SOA ? TILE : 1;                     // element stride of the images
         T h = T(0);
-        if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? (kt < cnt ? a.dt[k0 + kt] : 0.0) : a.dt0);
+        if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? h_cur : a.dt0);
         T tk = T(0);                                           // KnotPoint.t: only time-varying (user) models read it
-        if constexpr (uses_time<Model>::value) tk = T(a.t && kt < cnt ? a.t[k0 + kt] : 0.0);
-        (void)cnt;
+        if constexpr (uses_time<Model>::value) tk = T(t_cur);
+        (void)cnt; (void)t_cur; (void)h_cur;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
         dispatch_role<Model, Q, T, WITH_J, ERR, Chunks, NTHR, ROLL, S::ISSUERS, S::ROWSTORE && !SOA, ES>(
