@@ -46,6 +46,9 @@ struct KnotArgs {
     T* out;              // xdot or x+, (N, n);  may be nullptr
     long long N;
     int use_jmap;        // jmap describes J as a 2-D tensor (E x N); used by the padded-image store of the n = 12 models
+    int stream_out = 0;  // outputs of this launch exceed what the L2 can keep for a consumer (knot_stream_out): their stores carry the
+                         // L2 evict_first hint — written lines leave the 126 MB write-back L2 promptly and in order instead of by LRU
+                         // among the reads (C2 skeleton, scripts/micro/stream_mix.cu: 39.7 -> 37.7 us); small batches keep J in L2
     TensorMap jmap;      // (component-major kernels, SOA = true: J as the tensor N x E, inner extent = knots)
     TensorMap zmap;      // component-major kernels only: Z as the tensor N x (n+m), out as N x n
     TensorMap omap;
@@ -88,6 +91,23 @@ __device__ __forceinline__ void tensor_load_2d(uint32_t dst_smem, const TensorMa
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst_smem), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// the same stores with an L2 eviction-priority hint (64-bit policy from createpolicy), and L2 prefetches of a tile's input rows
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const TensorMap* tm, uint32_t src_smem, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(tm), "r"(src_smem), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tensor_prefetch_2d_l2(const TensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+// Outputs larger than this do not survive in the L2 for a consumer anyway (126 MB, shared with the input stream): stream them out.
+__host__ __device__ constexpr bool knot_stream_out(long long N, long long out_bytes_per_knot) { return N * out_bytes_per_knot > (64ll << 20); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -379,14 +399,25 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         else bulk_load(smem_u32(in_img[buf]), a.Z + tile * TILE * NZ, uint32_t(S::in_bytes), bar0 + 8 * buf);
     };
 
-    if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
+    long long tile = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init();
+        // L2 prefetch of this CTA's first tile, issued BEFORE the dependency wait below: a prefetch only moves lines into the L2 — the
+        // point of coherence, which a still-running producer kernel writes through — so it cannot expose stale data, and the DRAM
+        // latency of the first tile overlaps the tail of the previous kernel in the stream.
+#ifndef RDB_TUNE_NO_PREFETCH
+        if (tile < ntiles && tile_tma(tile)) {
+            if constexpr (SOA) tensor_prefetch_2d_l2(&a.zmap, int(tile * TILE), 0);
+            else bulk_prefetch_l2(a.Z + tile * TILE * NZ, uint32_t(S::in_bytes));
+        }
+#endif
+    }
     __syncthreads();
     // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; nothing
-    // below (first global access) may start before that kernel's memory is visible.  No-ops without the launch attribute.
+    // below (first global access that returns data) may start before that kernel's memory is visible.  No-ops without the launch attribute.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    long long tile = blockIdx.x;
     if (tile < ntiles && tile_tma(tile) && tid == 0) load_tile(tile, 0);
     // Per-knot steps and times (KnotPoint.dt / .t as arrays: trajectories, the mixed sweep) are plain global loads, one per thread.
     // Issued where they are used they cost every warp of the CTA a DRAM round trip at the top of EVERY tile (all warps of a
@@ -397,6 +428,12 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     if constexpr (Q != Q_CONTINUOUS) { if (a.dt) h_next = knot_scalar(a.dt, tile * TILE + kt); }
     if constexpr (uses_time<Model>::value) t_next = knot_scalar(a.t, tile * TILE + kt);
     uint32_t phase[2] = {0, 0};
+#ifdef RDB_TUNE_NO_STREAMOUT
+    const bool stream_out = false;
+#else
+    const bool stream_out = a.stream_out != 0;
+#endif
+    const uint64_t pol_out = l2_policy_evict_first();
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
         const long long k0 = tile * TILE;
@@ -431,15 +468,25 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
             __syncthreads();
             if constexpr (SOA) {
                 if (tid == 0) {
-                    if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), int(k0), 0);
-                    if (want_o) tensor_store_2d(&a.omap, smem_u32(o_img), int(k0), 0);
+                    if (stream_out) {
+                        if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), int(k0), 0, pol_out);
+                        if (want_o) tensor_store_2d(&a.omap, smem_u32(o_img), int(k0), 0, pol_out);
+                    } else {
+                        if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), int(k0), 0);
+                        if (want_o) tensor_store_2d(&a.omap, smem_u32(o_img), int(k0), 0);
+                    }
                     bulk_commit();
                 }
             } else if constexpr (S::ROWSTORE) {
                 if (a.use_jmap) {
                     if (tid == 0) {
-                        if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), 0, int(k0));
-                        if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                        if (stream_out) {
+                            if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), 0, int(k0), pol_out);
+                            if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes), pol_out);
+                        } else {
+                            if (want_j) tensor_store_2d(&a.jmap, smem_u32(j_img), 0, int(k0));
+                            if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                        }
                         bulk_commit();
                     }
                 } else if (tid < TILE) {
@@ -448,8 +495,13 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
                     bulk_commit();
                 }
             } else if (tid == 0) {
-                if (want_j) bulk_store(a.J + k0 * E, smem_u32(j_img), uint32_t(S::j_dense_bytes));
-                if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                if (stream_out) {
+                    if (want_j) bulk_store(a.J + k0 * E, smem_u32(j_img), uint32_t(S::j_dense_bytes), pol_out);
+                    if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes), pol_out);
+                } else {
+                    if (want_j) bulk_store(a.J + k0 * E, smem_u32(j_img), uint32_t(S::j_dense_bytes));
+                    if (want_o) bulk_store(a.out + k0 * n, smem_u32(o_img), uint32_t(S::o_bytes));
+                }
                 bulk_commit();
             }
         } else {
@@ -458,7 +510,9 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
             if (want_o) coop_store(o_img, n, a.out, k0, cnt, n, tid, NTHR);
         }
     }
-    if (tid < S::ISSUERS) bulk_wait0();
+    // the CTA may retire once its last stores have READ the shared-memory images (the writes themselves complete, like every other
+    // outstanding memory operation, before the grid does)
+    if (tid < S::ISSUERS) bulk_wait_read0();
 }
 
 // ---- ImplicitMidpoint ----------------------------------------------------------------------------------------------------

@@ -289,6 +289,10 @@ inline int run_one(const KnotRequest& r) {
     KnotArgs<T> a;
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0; a.t = r.t;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
+    {
+        constexpr long long JR = ERR ? ModelT<T>::nerr : ModelT<T>::n, JC = JR + ModelT<T>::m;
+        a.stream_out = knot_stream_out(r.N, (long long)sizeof(T) * ((WITH_J && r.J ? JR * JC : 0) + (r.out ? ModelT<T>::n : 0))) ? 1 : 0;
+    }
     if (r.soa) {
         if constexpr (RDB_SOA_KERNELS) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, true>::run(model, a, r.dev, r.stream, r.ld);
         else return -2;

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) errstate_jacobian_kernel(int rot, LiePart
 // knot) and one TMA bulk store ships the image; the two images alternate so a store drains while the next tile is prepared.
 // Pure store stream: HBM-write bound.
 template <class T, int NP, int TILE>
-__global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, long long N, const T* __restrict__ X, int ldx, T* __restrict__ G) {
+__global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, long long N, const T* __restrict__ X, int ldx, T* __restrict__ G, int stream_out) {
     constexpr int n = 9 + NP, ne = 12, PER = n * ne;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* img[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw) + TILE * PER};
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int it = 0;
+    const uint64_t pol_out = l2_policy_evict_first();
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const long long k0 = tile * TILE;
         const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
@@ -137,9 +138,13 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
         }
         fence_proxy_async();
         __syncthreads();
-        if (threadIdx.x == 0) { bulk_store(G + k0 * PER, smem_u32(im), uint32_t(cnt * PER * sizeof(T))); bulk_commit(); }
+        if (threadIdx.x == 0) {      // outputs larger than the L2 keeps for a consumer leave with the evict_first hint (kernels.cuh: knot_stream_out)
+            if (stream_out) bulk_store(G + k0 * PER, smem_u32(im), uint32_t(cnt * PER * sizeof(T)), pol_out);
+            else bulk_store(G + k0 * PER, smem_u32(im), uint32_t(cnt * PER * sizeof(T)));
+            bulk_commit();
+        }
     }
-    if (threadIdx.x == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait_read0();
 }
 
 // ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p); one 3x3 block per rotation on
@@ -318,7 +323,7 @@ int lie_errstate_jacobian(int dtype, int rot, const LieParts& parts, int n, int 
                 if (e != cudaSuccess) return int(e);
                 configured[kid].fetch_or(bit, std::memory_order_release);
             }
-            kern<<<g, TILE, smem, st>>>(rot, N, x, ldx, out);
+            kern<<<g, TILE, smem, st>>>(rot, N, x, ldx, out, knot_stream_out(N, (long long)(9 + np) * 12 * (dtype == 0 ? 4 : 8)) ? 1 : 0);
             return int(cudaGetLastError());
         };
         if (dtype == 0) return np == 4 ? go(0, errstate_jacobian_tma_kernel<float, 4, 64>, (const float*)X, (float*)G)

@@ -56,6 +56,10 @@ struct Cartpole {
         const auto& qd1 = get<3>(x);
         const auto& uu = get<0>(u);
         const T thv = val(th), w = val(qd1), uv = val(uu);
+#ifdef RDB_TUNE_NULLMODEL   // tuning experiments only: the kernel skeleton with (almost) no arithmetic = the data-movement ceiling
+        { const T d0[3] = {T(1), T(0.5), T(2)}, d1[3] = {T(-1), T(0.25), T(3)}; const auto in = vec(th, qd1, uu);
+          return vec(qd0, qd1, chain<T>(thv + w, d0, in), chain<T>(uv - w, d1, in)); }
+#endif
         T s, c;
         if (!cached) { sincos_(thv, s, c); th0 = thv; s0 = s; c0 = c; cached = true; }
         else sincos_near(thv, th0, s0, c0, s, c);

@@ -303,6 +303,22 @@ RDB_HD void sincos_near(T a, T a0, T s0, T c0, T& s, T& c) {
     const T d = a - a0;
     if (d > T(0.25) || d < T(-0.25)) { sincos_far(a, s, c); return; }
     const T d2 = d * d;
+#ifndef RDB_TUNE_NO_NEAR8
+    if (d2 < T(1.0 / 1024)) {                                 // |d| < 1/32 (h w of a typical step): degree 7 / 8 truncate below 1e-19
+        T ps = T(-1.9841269841269841e-04);
+        ps = ps * d2 + T(8.3333333333333332e-03);
+        ps = ps * d2 + T(-1.6666666666666666e-01);
+        const T sd = d + d * (d2 * ps);
+        T pc = T(2.4801587301587302e-05);
+        pc = pc * d2 + T(-1.3888888888888889e-03);
+        pc = pc * d2 + T(4.1666666666666664e-02);
+        pc = pc * d2 + T(-0.5);
+        const T cdm1 = d2 * pc;
+        s = s0 + (s0 * cdm1 + c0 * sd);
+        c = c0 + (c0 * cdm1 - s0 * sd);
+        return;
+    }
+#endif
     T ps = T(-2.5052108385441720e-08);                       // -1/11!
     ps = ps * d2 + T(2.7557319223985893e-06);                //  1/9!
     ps = ps * d2 + T(-1.9841269841269841e-04);               // -1/7!

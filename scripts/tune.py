@@ -116,6 +116,23 @@ VARIANTS["quadmrp64"] = {
     "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
     "4r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
 }
+VARIANTS["cartpole"].update({"null": dict(RDB_TUNE_NULLMODEL=1), "null_t128": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
+                             "null_t32": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=16),
+                             "near8": dict(RDB_TUNE_NEAR8=1), "nopf": dict(RDB_TUNE_NO_PREFETCH=1), "nostream": dict(RDB_TUNE_NO_STREAMOUT=1),
+                             "nopf_nostream": dict(RDB_TUNE_NO_PREFETCH=1, RDB_TUNE_NO_STREAMOUT=1), "t128_minb4": dict(RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
+                             "t128_minb3": dict(RDB_TUNE_TILE=128, RDB_TUNE_MINB=3)})
+VARIANTS["cartpole"].update({"dense": dict(RDB_TUNE_ROWSTORE=0), "dense_nostream": dict(RDB_TUNE_ROWSTORE=0, RDB_TUNE_NO_STREAMOUT=1),
+                             "dense_t128": dict(RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4), "dense_t256": dict(RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=256, RDB_TUNE_MINB=2),
+                             "t256": dict(RDB_TUNE_TILE=256, RDB_TUNE_MINB=2), "null_dense": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_ROWSTORE=0),
+                             "null_dense_t128": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
+                             "null_dense_t256": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=256, RDB_TUNE_MINB=2),
+                             "null_dense_nostream": dict(RDB_TUNE_NULLMODEL=1, RDB_TUNE_ROWSTORE=0, RDB_TUNE_NO_STREAMOUT=1)})
+VARIANTS["cartpole"].update({"estrin": dict(RDB_TUNE_ESTRIN=1), "estrin_dense_t128": dict(RDB_TUNE_ESTRIN=1, RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
+                             "near8_dense_t128": dict(RDB_TUNE_NEAR8=1, RDB_TUNE_ROWSTORE=0, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4),
+                             "near8_dense": dict(RDB_TUNE_NEAR8=1, RDB_TUNE_ROWSTORE=0), "estrin_dense": dict(RDB_TUNE_ESTRIN=1, RDB_TUNE_ROWSTORE=0),
+                             "near8_t128": dict(RDB_TUNE_NEAR8=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=4)})
+for _w in ("quadrotor", "satellite"):
+    VARIANTS[_w].update({"nopf": dict(RDB_TUNE_NO_PREFETCH=1), "nostream": dict(RDB_TUNE_NO_STREAMOUT=1), "nopf_nostream": dict(RDB_TUNE_NO_PREFETCH=1, RDB_TUNE_NO_STREAMOUT=1)})
 VARIANTS["cartpole_value"] = {"base": {}, "t128_minb8": dict(RDB_TUNE_V_TILE=128, RDB_TUNE_V_MINB=8), "t64_minb16": dict(RDB_TUNE_V_TILE=64, RDB_TUNE_V_MINB=16),
                               "t64_minb12": dict(RDB_TUNE_V_TILE=64, RDB_TUNE_V_MINB=12), "t32_minb24": dict(RDB_TUNE_V_TILE=32, RDB_TUNE_V_MINB=24), "t256_minb4": dict(RDB_TUNE_V_TILE=256, RDB_TUNE_V_MINB=4)}
 UNIT["cartpole_value"] = UNIT["cartpole"]
