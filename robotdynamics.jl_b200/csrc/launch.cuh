@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cuda.h>            // CUtensorMap types only; the encoder is fetched through the runtime (no libcuda link dependency)
 #include "kernels.cuh"
+#include "implicit_block.cuh"
 
 namespace rdb {
 
@@ -310,6 +311,13 @@ inline int run_implicit(const KnotRequest& r) {
     a.Z = static_cast<const T*>(r.Z); a.dt = r.dt; a.dt0 = r.dt0; a.t = r.t;
     a.J = static_cast<T*>(r.J); a.out = static_cast<T*>(r.out); a.N = r.N; a.use_jmap = 0;
     if (r.N <= 0) return 0;
+    if constexpr (mp_block_ok<ModelT<T>, T>()) {
+        // df/dx is block lower-triangular under the model's declared ordering: block forward substitution, one thread per knot
+        // (implicit_block.cuh).  RDB200_IMPLICIT_BLOCK=0 selects the dense kernels below for comparison.
+        static const bool dense = []() { const char* e = std::getenv("RDB200_IMPLICIT_BLOCK"); return e && e[0] == '0'; }();
+        if (!dense) return r.with_j ? MidpointBlockLaunch<ModelT<T>, T, true>::run(model, a, r.dev.sm_count, r.stream)
+                                    : MidpointBlockLaunch<ModelT<T>, T, false>::run(model, a, r.dev.sm_count, r.stream);
+    }
     if constexpr (ModelT<T>::n >= RDB_IMPLICIT_WARP_MIN_N && ModelT<T>::n + ModelT<T>::m <= 32) {
         // rigid bodies: a group of lanes per knot, the columns of [A B] dealt round-robin to the lanes, Gauss-Jordan across the group
         // (kernels.cuh: implicit_midpoint_group_kernel).  RDB200_IMPLICIT_WARP=1 selects the round-1 kernel (one warp-wide group per knot,

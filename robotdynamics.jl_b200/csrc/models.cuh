@@ -45,6 +45,10 @@ struct Cartpole {
     mutable T th0, s0, c0;
     mutable bool cached;
     RDB_HD void reset() const { cached = false; }
+    // ordering under which df/dx is block lower-triangular (implicit_block.cuh): [theta, w | v | p]
+    static constexpr int mp_nblocks = 3;
+    RDB_HD static constexpr int mp_size(int b) { return b == 0 ? 2 : 1; }
+    RDB_HD static constexpr int mp_idx(int b, int k) { return b == 0 ? (k == 0 ? 1 : 3) : (b == 1 ? 2 : 0); }
     // qdd(theta, w, u) is ONE elemental operation: values on plain scalars, its 2 x 3 local Jacobian by hand (the reference ships the
     // same thing as its UserDefined analytic Jacobian, test/cartpole_model.jl:57-96), partials by chain() — 14 FMAs per stage for the
     // three live columns {theta, w, u} where forward mode through every intermediate of the 2x2 solve spends ~70 (the C2 kernel is
@@ -101,6 +105,9 @@ struct DoubleIntegrator {
     static constexpr int n = 2 * D, m = D, nerr = 2 * D, rot = ROT_NONE;
     ModelParams<T> p;
     RDB_HD void reset() const {}
+    static constexpr int mp_nblocks = 2;                       // [v | p]  (implicit_block.cuh)
+    RDB_HD static constexpr int mp_size(int) { return D; }
+    RDB_HD static constexpr int mp_idx(int b, int k) { return b == 0 ? D + k : k; }
     template <class X, class U>
     RDB_HD auto f(const X& x, const U& u) const { return cat(slice<D, D>(x), u); }
 };
@@ -375,6 +382,11 @@ template <class T, int KIND, int ROT, int FRAME>
 struct RigidBody {
     static constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
     static constexpr int n = 9 + np, m = (KIND == KIND_QUADROTOR) ? 4 : 6, nerr = 12, rot = ROT, frame = FRAME;
+    // ordering under which df/dx is block lower-triangular (implicit_block.cuh): [w | att | v | r]  (src/rigidbody.jl:213-236: w' reads
+    // w and u, att' reads att and w, v' reads att, v, w, u, r' reads att and v)
+    static constexpr int mp_nblocks = 4;
+    RDB_HD static constexpr int mp_size(int b) { return b == 1 ? np : 3; }
+    RDB_HD static constexpr int mp_idx(int b, int k) { return b == 0 ? 6 + np + k : b == 1 ? 3 + k : b == 2 ? 3 + np + k : k; }
     // The reference Quadrotor stores its inertia as Diagonal{Float64} (test/quadrotor.jl:25-26): only the diagonal exists.
     // Body/Satellite carry a full SMatrix{3,3} (test/rigidbody_test.jl:24, examples/single_satellite.jl:9).
     static constexpr bool diag_inertia = (KIND == KIND_QUADROTOR);
