@@ -546,8 +546,16 @@ static void errstate_jacobian(const Model& M, const double* x, double* G /* n x 
     for (int i = 0; i < 6; ++i) G[(3 + np + i) + n * (6 + i)] = 1;
 }
 
-// ∇errstate_jacobian!: ∇²differential(R, b) on the rotation block, zeros elsewhere (nerr x nerr).
-//   quat: -(q·b) I3 (q normalised).  MRP/RP: d/dδ [∇differential(p ∘ δ)ᵀ b] at δ = 0 = [∂(G(p)ᵀ b)/∂p] G(p).
+// ∇errstate_jacobian!: ∇²differential(R, b) on the rotation block, zeros elsewhere (nerr x nerr) — src/liestate.jl:300-320.
+// Rotations.jl defines ∇²differential(R, b) = ∇²composition1(R, I, b): the Jacobian with respect to δ, at δ = 0, of
+// [∂(R ∘ δ)/∂δ]ᵀ b, i.e. the Hessians of the components of the composition R ∘ δ contracted with b (the second-order term of the
+// retraction that Altro adds to Gᵀ ∇²f G).  With δ parameterised like R:
+//   quat: q ∘ φ(δ), φ = [1; δ]/sqrt(1 + |δ|²)         ->  -(q·b) I3   (q normalised; pinned by test/liestate.jl:96-99)
+//   MRP : p ∘ δ = [(1-|p|²) δ + (1-|δ|²) p + 2 p×δ] / (1 + |p|²|δ|² - 2 p·δ)
+//                                                   ->  -2 (1+|p|²)(p·b) I + 2 (a pᵀ + p aᵀ) + 8 (p·b) p pᵀ,   a = (1-|p|²) b - 2 p×b
+//   RP  : g ∘ δ = (g + δ + g×δ) / (1 - g·δ)            ->  a gᵀ + g aᵀ + 2 (g·b) g gᵀ,                           a = b - g×b
+// (round 2: the MRP / RP rows used to be d/dδ [∇differential(p ∘ δ)ᵀ b], a different object; the present formulas agree with second
+// differences of scipy's Rotation composition to 1e-8, tests/test_oracle.py::test_rotation_conventions_vs_scipy.)
 static void grad_errstate_jacobian(const Model& M, const double* x, const double* b, double* H) {
     const int ne = M.nerr;
     for (int i = 0; i < ne * ne; ++i) H[i] = 0;
@@ -559,20 +567,14 @@ static void grad_errstate_jacobian(const Model& M, const double* x, const double
         for (int i = 0; i < 3; ++i) H[(3 + i) + ne * (3 + i)] = d;
         return;
     }
-    double G[9]; grad_differential(M.rot, p, G, 3);
-    double pb = p[0] * bb[0] + p[1] * bb[1] + p[2] * bb[2];
-    double skb[3][3] = {{0, -bb[2], bb[1]}, {bb[2], 0, -bb[0]}, {-bb[1], bb[0], 0}};
-    double dG[3][3];
+    const double pb = p[0] * bb[0] + p[1] * bb[1] + p[2] * bb[2], n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    const double pxb[3] = {p[1] * bb[2] - p[2] * bb[1], p[2] * bb[0] - p[0] * bb[2], p[0] * bb[1] - p[1] * bb[0]};
+    double a[3];
+    for (int i = 0; i < 3; ++i) a[i] = (M.rot == ROT_MRP) ? (1 - n2) * bb[i] - 2 * pxb[i] : bb[i] - pxb[i];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double I = (i == j) ? 1.0 : 0.0;
-        if (M.rot == ROT_MRP)   // G'b = (1-n2) b + 2 (b x p) + 2 p (p.b)
-            dG[i][j] = -2 * bb[i] * p[j] + 2 * skb[i][j] + 2 * (pb * I + p[i] * bb[j]);
-        else                    // G'b = b + (b x p) + p (p.b)
-            dG[i][j] = skb[i][j] + pb * I + p[i] * bb[j];
-    }
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double s = 0; for (int k = 0; k < 3; ++k) s += dG[i][k] * G[k + 3 * j];
-        H[(3 + i) + ne * (3 + j)] = s;
+        const double I = (i == j) ? 1.0 : 0.0;
+        H[(3 + i) + ne * (3 + j)] = (M.rot == ROT_MRP) ? -2 * (1 + n2) * pb * I + 2 * (a[i] * p[j] + p[i] * a[j]) + 8 * pb * p[i] * p[j]
+                                                       : a[i] * p[j] + p[i] * a[j] + 2 * pb * p[i] * p[j];
     }
 }
 

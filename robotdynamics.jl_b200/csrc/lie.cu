@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(TILE) errstate_jacobian_tma_kernel(int rot, lo
     if (threadIdx.x == 0) bulk_wait_read0();
 }
 
-// ∇²differential(R, b): quat -(q.b) I3;  MRP/RP: d/dδ [∇differential(p∘δ)' b] at 0 = [∂(G(p)' b)/∂p] G(p); one 3x3 block per rotation on
-// the diagonal, zeros elsewhere (reference: src/liestate.jl:300-320)
+// ∇²differential(R, b) = ∇²composition1(R, I, b): the Hessians of the components of R ∘ δ with respect to δ at 0, contracted with b (δ
+// parameterised like R) — quat: -(q.b) I3;  MRP: -2 (1+|p|²)(p.b) I + 2 (a p' + p a') + 8 (p.b) p p',  a = (1-|p|²) b - 2 p x b;
+// RP: a g' + g a' + 2 (g.b) g g',  a = b - g x b.  One 3x3 block per rotation on the diagonal, zeros elsewhere (reference:
+// src/liestate.jl:300-320).  (Round 2: the MRP / RP rows were d/dδ [∇differential(p∘δ)' b] before — not the package's definition.)
 template <class T>
 __global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, LieParts parts, int n, int ne, long long N, const T* __restrict__ X, int ldx,
                                                                      const T* __restrict__ B, int ldb, T* __restrict__ H) {
@@ -168,16 +170,14 @@ __global__ void __launch_bounds__(256) grad_errstate_jacobian_kernel(int rot, Li
             if (rot == ROT_QUAT) {
                 if (a == c) { T q[4]; unit_quat(rot, p, q); v = -(q[0] * b[0] + q[1] * b[1] + q[2] * b[2] + q[3] * b[3]); }
             } else {
-                const T pb = p[0] * b[0] + p[1] * b[1] + p[2] * b[2];
-                const T skb[3][3] = {{T(0), -b[2], b[1]}, {b[2], T(0), -b[0]}, {-b[1], b[0], T(0)}};
-                T s = T(0);
-                for (int r = 0; r < 3; ++r) {
-                    const T I = (a == r) ? T(1) : T(0);
-                    const T dG = (rot == ROT_MRP) ? (T(-2) * b[a] * p[r] + T(2) * skb[a][r] + T(2) * (pb * I + p[a] * b[r]))
-                                                  : (skb[a][r] + pb * I + p[a] * b[r]);
-                    s += dG * grad_differential(rot, p, r, c);
-                }
-                v = s;
+                const T pb = p[0] * b[0] + p[1] * b[1] + p[2] * b[2], n2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+                const T pxb[3] = {p[1] * b[2] - p[2] * b[1], p[2] * b[0] - p[0] * b[2], p[0] * b[1] - p[1] * b[0]};
+                const bool mrp = rot == ROT_MRP;
+                const T aa = mrp ? (T(1) - n2) * b[a] - T(2) * pxb[a] : b[a] - pxb[a];
+                const T ac = mrp ? (T(1) - n2) * b[c] - T(2) * pxb[c] : b[c] - pxb[c];
+                const T I = (a == c) ? T(1) : T(0);
+                v = mrp ? T(-2) * (T(1) + n2) * pb * I + T(2) * (aa * p[c] + p[a] * ac) + T(8) * pb * p[a] * p[c]
+                        : aa * p[c] + p[a] * ac + T(2) * pb * p[a] * p[c];
             }
         }
         H[idx] = v;

@@ -6,7 +6,9 @@ The reference ships no golden vectors and Julia is unavailable (SURVEY.md Â§4, Â
  (3) the hand-verified known answers of SURVEY.md Appendix C;
  (4) the committed fixtures in tests/golden/ (regression pin);
  (5) sympy / 50-digit mpmath restatements (oracle/highprec.py): the symbolic Cartpole Jacobian, the reference's own hand-derived
-     analytic Jacobian (test/cartpole_model.jl:57-96), and high-precision differences of the composed RK maps.
+     analytic Jacobian (test/cartpole_model.jl:57-96), and high-precision differences of the composed RK maps;
+ (6) scipy.spatial.transform.Rotation â€” an independent third-party implementation â€” for everything the path takes from Rotations.jl on
+     the manifold: q*v, q\\F, kinematics, âˆ‡differential, âˆ‡Â²differential, the Cayley error (all three attitude parameterisations).
 """
 import numpy as np
 import pytest
@@ -169,7 +171,8 @@ def test_errstate_structure_and_state_diff():
 
 
 def test_grad_errstate_is_derivative_of_Gt_b():
-    """âˆ‡errstate_jacobian = d/dÎ´ [G(x âŠ• Î´)áµ€ b] at Î´ = 0, checked by central differences through the oracle's own G."""
+    """âˆ‡errstate_jacobian = âˆ‡Â²differential(q, b) = -(qÂ·b) I3 for quaternions (test/liestate.jl:96-99); zeros outside the rotation block.  The
+    MRP / RodriguesParam forms are checked against second differences of scipy's composition in test_rotation_conventions_vs_scipy."""
     rng = np.random.default_rng(11)
     m = o.body(o.ROT_QUAT)
     X = rand_inputs(13, 6, 4, rng)[:, :13]
@@ -374,3 +377,85 @@ def test_implicit_midpoint_vs_50_digit_root_and_differences():
             J[:, j] = [float((a - b) / (2 * eps)) for a, b in zip(solve(zp, hh), solve(zm, hh))]
         assert np.abs(o.discrete_dynamics(m, o.IMPLICIT_MIDPOINT, Z[k:k + 1], h)[0] - xn).max() < 1e-12
         assert np.abs(o.as_matrix(o.discrete_jacobian(m, o.IMPLICIT_MIDPOINT, Z[k:k + 1], h))[0] - J).max() < 1e-10
+
+
+# ---- (6) the Rotations.jl boundary against an independent third-party implementation (scipy.spatial.transform) ------------------------
+def _scipy_rot(rn, att):
+    """The rotation Rotations.jl builds for an attitude: QuatRotation [w,x,y,z] (Hamilton, active), MRP p = v / (1 + w), RodriguesParam
+    g = v / w  (SURVEY.md Â§8c).  scipy: quaternions are [x,y,z,w]; MRPs are tan(theta/4) axis; a Gibbs vector is tan(theta/2) axis."""
+    from scipy.spatial.transform import Rotation as R
+    if rn == "quat":
+        return R.from_quat(np.r_[att[1:], att[0]])
+    if rn == "mrp":
+        return R.from_mrp(att)
+    nrm = np.linalg.norm(att)
+    return R.from_rotvec(2.0 * np.arctan(nrm) * att / nrm)
+
+
+def _scipy_att(rn, rot, like=None):
+    if rn == "quat":
+        q = rot.as_quat()
+        q = np.r_[q[3], q[:3]]
+        return -q if like is not None and q @ like < 0 else q
+    if rn == "mrp":
+        return rot.as_mrp()
+    v = rot.as_rotvec()
+    th = np.linalg.norm(v)
+    return np.tan(th / 2.0) * v / th
+
+
+@pytest.mark.parametrize("rn,rc", [("quat", o.ROT_QUAT), ("mrp", o.ROT_MRP), ("rp", o.ROT_RP)])
+def test_rotation_conventions_vs_scipy(rn, rc):
+    """What the reference takes from Rotations.jl â€” `q * v`, `q \\ F`, `kinematics(q, w)`, `rotation_error(.., CayleyMap())`, `âˆ‡differential`
+    (src/rigidbody.jl:224-230, src/liestate.jl:216-217,291) â€” compared with scipy's Rotation class on the manifold: active Hamilton
+    rotations, body-frame angular velocity (right multiplication), MRP = tan(theta/4) axis, Rodrigues = tan(theta/2) axis, Cayley error =
+    Gibbs vector of R0' R.  An independent implementation, not the reference: it pins conventions, not off-manifold behaviour."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(77)
+    m = o.body(rc, o.BODYFRAME)                      # mass 2, J = diag(2,3,1): r' = q*v, v' = q\(F/m) - w x v, F_world = q*u[:3]
+    n, na = m.n, m.n - 9
+    Z = rand_inputs(n, 6, 6, rng)
+    xd = o.dynamics(m, Z)
+    G = o.errstate_jacobian(m, Z[:, :n])
+    X0 = rand_inputs(n, 6, 6, rng)[:, :n]
+    d = o.state_diff(m, Z[:, :n], X0)
+    eps = 1e-6
+    for k in range(Z.shape[0]):
+        att, v, w, u = Z[k, 3:3 + na], Z[k, 3 + na:6 + na], Z[k, 6 + na:9 + na], Z[k, n:]
+        rot = _scipy_rot(rn, att)
+        assert np.allclose(xd[k, :3], rot.apply(v), atol=1e-12)                                        # r' = q * v
+        Fw = rot.apply(u[:3])                                                                         # F_world = q * u[1:3]
+        assert np.allclose(xd[k, 3 + na:6 + na], rot.inv().apply(Fw / 2.0) - np.cross(w, v), atol=1e-12)   # v' = q \ (F/m) - w x v
+        # kinematics: d/dt of the attitude parameters when R(t + e) = R(t) exp(e w^)   (central difference on the manifold)
+        ap = _scipy_att(rn, rot * R.from_rotvec(eps * w), like=att if rn == "quat" else None)
+        am = _scipy_att(rn, rot * R.from_rotvec(-eps * w), like=att if rn == "quat" else None)
+        assert np.allclose(xd[k, 3:3 + na], (ap - am) / (2 * eps), atol=1e-8)
+        # errstate_jacobian attitude block = âˆ‡differential = d att(R * dR(delta)) / d delta at 0, where delta parameterises the small right
+        # perturbation dR the way the attitude itself is parameterised: the vector part of a quaternion [1, delta] (= a Gibbs vector) for
+        # QuatRotation, a Gibbs vector for RodriguesParam, an MRP for MRP
+        Gk = G[k].T[3:3 + na, 3:6]
+        for j in range(3):
+            dl = np.zeros(3); dl[j] = eps
+            small = (lambda s: R.from_mrp(s * dl)) if rn == "mrp" else (lambda s: R.from_rotvec(2.0 * np.arctan(eps) * s * dl / eps))
+            col = (_scipy_att(rn, rot * small(+1), like=att if rn == "quat" else None) -
+                   _scipy_att(rn, rot * small(-1), like=att if rn == "quat" else None)) / (2 * eps)
+            assert np.allclose(Gk[:, j], col, atol=1e-6)
+        # âˆ‡errstate_jacobian attitude block = âˆ‡Â²differential(att, b) = sum_k b_k dÂ²att_k(R * dR(delta)) / d deltaÂ² at 0: the second-order
+        # term of the retraction (for quaternions -(q.b) I3, test/liestate.jl:96-99), by second central differences of scipy's composition
+        b = rng.random(n)
+        H = o.grad_errstate_jacobian(m, Z[k:k + 1, :n], b[None])[0].T[3:6, 3:6]
+        e2 = 1e-4
+        def comp(dv):
+            nd = np.linalg.norm(dv)
+            dR = R.from_mrp(dv) if rn == "mrp" else R.from_rotvec(2.0 * np.arctan(nd) * dv / nd)
+            return _scipy_att(rn, rot * dR, like=att if rn == "quat" else None) @ b[3:3 + na]
+        for i in range(3):
+            for j in range(3):
+                ei, ej = np.eye(3)[i] * e2, np.eye(3)[j] * e2
+                hij = (comp(ei + ej) - comp(ei - ej) - comp(-ei + ej) + comp(-ei - ej)) / (4 * e2 * e2) if i != j else \
+                      (comp(ei) - 2 * (att @ b[3:3 + na]) + comp(-ei)) / (e2 * e2)
+                assert abs(H[i, j] - hij) < 2e-6, (rn, i, j, H[i, j], hij)
+        # state_diff attitude part = Cayley map of R0' R = its Gibbs vector
+        rel = _scipy_rot(rn, X0[k, 3:3 + na]).inv() * rot
+        rv = rel.as_rotvec(); th = np.linalg.norm(rv)
+        assert np.allclose(d[k, 3:6], np.tan(th / 2.0) * rv / th, atol=1e-11)
