@@ -206,6 +206,9 @@ template <class Model, class T> struct mp_block_check<Model, T, true> {
 };
 template <class Model, class T> constexpr bool mp_block_ok() { return mp_block_check<Model, T>::value; }
 
+#ifndef RDB_IMPLICIT_IMG_BUDGET
+#define RDB_IMPLICIT_IMG_BUDGET 0      // tuning experiments: bytes of per-warp image (0 = default rule below)
+#endif
 // CG: Jacobian columns staged per flush of the per-warp image (all n+m when the image fits; fewer for the fp64 rigid bodies)
 template <class Model, class T, bool WITH_J, int CG>
 __global__ void __launch_bounds__(32) implicit_midpoint_block_kernel(const Model model, const KnotArgs<T> a) {
@@ -305,10 +308,14 @@ __global__ void __launch_bounds__(32) implicit_midpoint_block_kernel(const Model
 template <class Model, class T, bool WITH_J>
 struct MidpointBlockLaunch {
     static constexpr int n = Model::n, m = Model::m, NZ = n + m;
-    // stage all columns when the image stays under ~32 KB per warp (7 warps per SM), otherwise two or three groups
+    // Columns staged per flush: the kernel is latency-bound (ncu: 29 % issue utilisation at 6 warps per SM with the whole 28 KB image
+    // staged), so the image is kept small enough for the REGISTER-limited number of warps per SM — 16 at <= 128 registers (fp32), 8 at
+    // <= 255 (fp64) — at the price of two or three flushes per tile.
     static constexpr int cg_for(int groups) { return (NZ + groups - 1) / groups; }
     static constexpr size_t img_bytes(int cg) { return size_t(32) * (n * cg + 1) * sizeof(T); }
-    static constexpr int CG = !WITH_J ? 1 : img_bytes(NZ) <= 30 * 1024 ? NZ : img_bytes(cg_for(2)) <= 30 * 1024 ? cg_for(2) : cg_for(3);
+    static constexpr size_t budget = RDB_IMPLICIT_IMG_BUDGET > 0 ? size_t(RDB_IMPLICIT_IMG_BUDGET) : (sizeof(T) == 4 ? 10 * 1024 + 512 : 22 * 1024);
+    static constexpr int groups() { for (int g = 1; g < NZ; ++g) if (img_bytes(cg_for(g)) <= budget) return g; return NZ; }
+    static constexpr int CG = !WITH_J ? 1 : cg_for(groups());
     static constexpr size_t smem = size_t(32) * (NZ + n) * sizeof(T) + (WITH_J ? img_bytes(CG) : 0) + 16;
     static int run(const Model& model, const KnotArgs<T>& a, int sm_count, cudaStream_t st) {
         auto kern = implicit_midpoint_block_kernel<Model, T, WITH_J, CG>;
