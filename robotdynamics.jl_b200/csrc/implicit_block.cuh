@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(32) implicit_midpoint_block_kernel(const Model
     using MF = MidpointF<Model, T>;
     using F = typename MF::type;
     using S = MidpointStructure<Model, F>;
+    static_assert(S::ok(), "df/dx of this model is not block lower-triangular under its declared ordering (mp_nblocks / mp_size / mp_idx)");
     constexpr mask_t ALL = MF::ALL;
     constexpr int NG = (NZ + CG - 1) / CG;                       // flushes per tile
     constexpr int GW = n * CG, PJ = (GW % 2) ? GW : GW + 1;      // image row: one knot's columns of a group, odd pitch
@@ -305,18 +306,28 @@ __global__ void __launch_bounds__(32) implicit_midpoint_block_kernel(const Model
     }
 }
 
+// Columns staged per flush, as plain integers (shared by the launcher below and by custom.cu, which only knows a user model's dimensions
+// at run time).  The kernel is latency-bound (ncu: 29 % issue utilisation at 6 warps per SM with the whole 28 KB image staged), so the
+// image is kept small enough for the REGISTER-limited number of warps per SM — 16 at <= 128 registers (fp32), 8 at <= 255 (fp64) — at
+// the price of two or three flushes per tile.
+__host__ __device__ constexpr size_t mp_img_bytes(int n, int cg, int es) { return size_t(32) * size_t(n * cg + 1) * size_t(es); }
+__host__ __device__ constexpr int mp_cols_per_flush(int n, int m, int es, bool with_j) {
+    if (!with_j) return 1;
+    const size_t budget = RDB_IMPLICIT_IMG_BUDGET > 0 ? size_t(RDB_IMPLICIT_IMG_BUDGET) : (es == 4 ? 10 * 1024 + 512 : 22 * 1024);
+    const int NZ = n + m;
+    for (int g = 1; g < NZ; ++g) { const int cg = (NZ + g - 1) / g; if (mp_img_bytes(n, cg, es) <= budget) return cg; }
+    return 1;
+}
+__host__ __device__ constexpr size_t mp_smem_bytes(int n, int m, int es, bool with_j) {
+    return size_t(32) * size_t(2 * n + m) * size_t(es) + (with_j ? mp_img_bytes(n, mp_cols_per_flush(n, m, es, with_j), es) : 0) + 16;
+}
+
+#ifndef __CUDACC_RTC__
 template <class Model, class T, bool WITH_J>
 struct MidpointBlockLaunch {
     static constexpr int n = Model::n, m = Model::m, NZ = n + m;
-    // Columns staged per flush: the kernel is latency-bound (ncu: 29 % issue utilisation at 6 warps per SM with the whole 28 KB image
-    // staged), so the image is kept small enough for the REGISTER-limited number of warps per SM — 16 at <= 128 registers (fp32), 8 at
-    // <= 255 (fp64) — at the price of two or three flushes per tile.
-    static constexpr int cg_for(int groups) { return (NZ + groups - 1) / groups; }
-    static constexpr size_t img_bytes(int cg) { return size_t(32) * (n * cg + 1) * sizeof(T); }
-    static constexpr size_t budget = RDB_IMPLICIT_IMG_BUDGET > 0 ? size_t(RDB_IMPLICIT_IMG_BUDGET) : (sizeof(T) == 4 ? 10 * 1024 + 512 : 22 * 1024);
-    static constexpr int groups() { for (int g = 1; g < NZ; ++g) if (img_bytes(cg_for(g)) <= budget) return g; return NZ; }
-    static constexpr int CG = !WITH_J ? 1 : cg_for(groups());
-    static constexpr size_t smem = size_t(32) * (NZ + n) * sizeof(T) + (WITH_J ? img_bytes(CG) : 0) + 16;
+    static constexpr int CG = mp_cols_per_flush(n, m, int(sizeof(T)), WITH_J);
+    static constexpr size_t smem = mp_smem_bytes(n, m, int(sizeof(T)), WITH_J);
     static int run(const Model& model, const KnotArgs<T>& a, int sm_count, cudaStream_t st) {
         auto kern = implicit_midpoint_block_kernel<Model, T, WITH_J, CG>;
         static std::atomic<int> occ_cache[64];
@@ -336,5 +347,6 @@ struct MidpointBlockLaunch {
         return int(cudaGetLastError());
     }
 };
+#endif   // !__CUDACC_RTC__
 
 }  // namespace rdb

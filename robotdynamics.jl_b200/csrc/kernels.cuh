@@ -320,11 +320,12 @@ __host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(
 #define RDB_ROWSTORE_MINWAY 16   // pad the image when the dense one would put at least this many lanes of a warp on one bank
 #endif
 __host__ __device__ constexpr bool knot_rowstore(int jr, int jc, bool with_j, int es) {
-    // rigid bodies: pad when the dense image would put >= 16 lanes on one bank (the 8-way case E = 216 fp32 measured equal);
-    // small fp64 models (Cartpole: rows of 20 doubles, 8 lanes per bank): padding pays from 8-way on (C2 39.9 -> 38.7 us)
+    // rigid bodies: pad when the dense image would put >= 16 lanes on one bank (the 8-way case E = 216 fp32 measured equal).
+    // The small fp64 models (Cartpole: rows of 20 doubles, 8 lanes per bank) were padded too for a while (C2 39.9 -> 38.7 us); since
+    // the streamed-out stores carry the L2 evict_first hint the dense image with its ONE 1-D bulk store is the faster one again
+    // (37.8 against 38.2 us, three alternating runs each) and saves the per-launch tensor-map encode on the host.
     const int ways = cgcd(jr * jc * es / 4, 32);
-    return RDB_TUNE_ROWSTORE && with_j && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) &&
-           ((jr >= 12 && ways >= RDB_ROWSTORE_MINWAY) || (jr < 12 && es == 8 && ways >= 8));
+    return RDB_TUNE_ROWSTORE && with_j && ((jr * jc) % 2 == 0) && ((jr * es) % 16 == 0) && jr >= 12 && ways >= RDB_ROWSTORE_MINWAY;
 }
 __host__ __device__ constexpr int knot_pitch(int jr, int jc, bool with_j, int es) {
     const int E = jr * jc, u = (E * es + 15) / 16;

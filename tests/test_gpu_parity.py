@@ -926,6 +926,40 @@ def test_implicit_midpoint_for_user_models(rd, torch_):
     assert np.abs(o.as_matrix(Jc) - sol).max() < 1e-9        # and its Jacobian is the implicit-function-theorem one
 
 
+def test_implicit_midpoint_for_user_rigid_bodies(rd, torch_):
+    """RigidBody{R} with a user wrench under ImplicitMidpoint: a wrench with the built-in structure (forces read the attitude and the
+    controls) takes the block-triangular kernel (implicit_block.cuh) and must equal the checker's quadrotor; a wrench that reads the
+    POSITION makes v' depend on r, fails that kernel's compile-time structure check and falls back to the dense group kernel — its step
+    must solve the midpoint equation and its Jacobian must be the implicit-function-theorem one."""
+    from test_abi_host import QUAD_WRENCH
+    IM = rd._abi.IMPLICIT_MIDPOINT
+    rng = np.random.default_rng(190)
+    for Rname, rc, frame in (("QuatRotation", o.ROT_QUAT, o.WORLD), ("MRP", o.ROT_MRP, o.BODYFRAME)):
+        om = o.quadrotor(rc, frame)
+        um = rd.CustomRigidBody(getattr(rd, Rname), 4, QUAD_WRENCH, mass=0.5, J=(0.0023, 0.0023, 0.004),
+                                params=[1.0, 0.0245, 0.175, 0.0, 0.0, -9.81], bodyframe=bool(frame))
+        N = 333
+        Z, dt = rand_inputs(om.n, om.m, N, rng), rng.uniform(0.005, 0.1, N)
+        xn = np.empty((N, om.n))
+        J = um._h.discrete_jacobian(IM, Z, dt, xn=xn)
+        assert np.abs(J - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z, dt)).max() < 1e-10
+        assert np.abs(xn - o.discrete_dynamics(om, o.IMPLICIT_MIDPOINT, Z, dt)).max() < 1e-10
+        J32 = um._h.discrete_jacobian(IM, dev(torch_, Z.astype(np.float32)), dt).cpu().numpy()
+        assert np.abs(J32 - o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z.astype(np.float32).astype(np.float64), dt)).max() < 1e-4
+    spring = """
+                return vec(-p[0] * get<0>(r) + get<0>(u), -p[0] * get<1>(r) + get<1>(u), -p[0] * get<2>(r) + get<2>(u) - T(9.81) * mass,
+                           get<3>(u), get<4>(u), get<5>(u));
+    """
+    sm = rd.CustomRigidBody(rd.QuatRotation, 6, spring, mass=2.0, J=(2.0, 3.0, 1.0), params=[4.0])
+    Zs, hs = rand_inputs(13, 6, 200, rng), rng.uniform(0.01, 0.1, 200)
+    x2 = sm._h.discrete_dynamics(IM, Zs, hs)
+    J2, J1, e = sm._h.dynamics_error(IM, Zs, np.ascontiguousarray(x2), hs, jacobian=True)
+    assert np.abs(e).max() < 1e-10
+    Js = sm._h.discrete_jacobian(IM, Zs, hs)
+    sol = -np.linalg.solve(o.as_matrix(J2)[:, :, :13], o.as_matrix(J1))
+    assert np.abs(o.as_matrix(Js) - sol).max() < 1e-8
+
+
 # ---- general LieState{R,P}: several rotations, any partition (src/liestate.jl:75-132, 210-320) ---------------------------------------
 TWO_BODY = """
         // state [w1 (3), q1 (4), s (2), q2 (4), w2 (3)]: two attitudes driven by their body rates, a planar slider driven by u
