@@ -331,12 +331,13 @@ __host__ __device__ constexpr int knot_pitch(int jr, int jc, bool with_j, int es
     const int E = jr * jc, u = (E * es + 15) / 16;
     return knot_rowstore(jr, jc, with_j, es) ? ((u % 2 == 0) ? u + 1 : u) * 16 / es : E;
 }
-__host__ __device__ constexpr size_t knot_smem_total(int n, int m, int jr, int jc, int TILE, bool with_j, int es) {
+// nscal: per-knot scalar arrays staged next to the [x;u] rows (dt; dt and t for time-varying models), double-buffered like them
+__host__ __device__ constexpr size_t knot_smem_total(int n, int m, int jr, int jc, int TILE, bool with_j, int es, int nscal) {
     const size_t a16 = 15;
     const size_t in_b = (size_t(TILE) * size_t(n + m) * es + a16) & ~a16;
     const size_t j_b = with_j ? ((size_t(TILE) * size_t(knot_pitch(jr, jc, with_j, es)) * es + a16) & ~a16) : 0;
     const size_t o_b = (size_t(TILE) * size_t(n) * es + a16) & ~a16;
-    return 2 * in_b + j_b + o_b + 16;
+    return 2 * in_b + j_b + o_b + size_t(2) * size_t(nscal) * size_t(TILE) * 8 + 16;
 }
 template <class Model, int TILE, bool WITH_J, class T, bool ERR = false>
 struct KnotSmem {
@@ -361,9 +362,13 @@ struct KnotSmem {
     static constexpr size_t off_in1 = align16(in_bytes);
     static constexpr size_t off_j = off_in1 + align16(in_bytes);
     static constexpr size_t off_o = off_j + align16(j_bytes);
-    static constexpr size_t off_bar = off_o + align16(o_bytes);
+    // per-knot steps (and times, for models that read them): [buffer][array][knot] doubles, staged by the same TMA transaction as the rows
+    static constexpr int NSCAL = uses_time<Model>::value ? 2 : 1;
+    static constexpr size_t sc_bytes = size_t(TILE) * 8;
+    static constexpr size_t off_sc = off_o + align16(o_bytes);
+    static constexpr size_t off_bar = off_sc + 2 * NSCAL * sc_bytes;
     static constexpr size_t total = off_bar + 16;
-    static_assert(total == knot_smem_total(n, Model::m, JR, JC, TILE, WITH_J, int(sizeof(T))), "smem layout and knot_smem_total disagree");
+    static_assert(total == knot_smem_total(n, Model::m, JR, JC, TILE, WITH_J, int(sizeof(T)), NSCAL), "smem layout and knot_smem_total disagree");
 };
 
 
@@ -394,10 +399,24 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     const bool tma_ok = SOA || ((reinterpret_cast<uintptr_t>(a.Z) | reinterpret_cast<uintptr_t>(a.J) |
                                                            reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
     auto tile_tma = [&](long long tile) { return tma_ok && (SOA || (tile + 1) * TILE <= N); };
+    // Per-knot steps / times (KnotPoint.dt / .t as arrays: trajectories, the mixed sweep) ride on the tile's TMA transaction when their
+    // tile is a whole 16-byte-aligned range: one more bulk copy of TILE doubles per array into sc_img[buffer][array][knot].  As plain
+    // per-thread global loads they cost 14 % of the kernel time for 0.8 - 4 % more bytes (quadrotor fp32 2^20: 172.9 -> 198.0 us,
+    // Cartpole fp64 37.4 -> 42.6 us), even when requested a tile ahead; they remain the fallback for ragged tiles and odd alignments.
+    double* sc_img = reinterpret_cast<double*>(smem_raw + S::off_sc);
+    const bool dt_tma = (Q != Q_CONTINUOUS) && a.dt != nullptr && (reinterpret_cast<uintptr_t>(a.dt) & 15) == 0;
+    const bool t_tma = uses_time<Model>::value && a.t != nullptr && (reinterpret_cast<uintptr_t>(a.t) & 15) == 0;
+    auto sc_tma = [&](long long tile) { return (tile + 1) * TILE <= N && tile_tma(tile); };   // scalars staged for this tile?
     auto load_tile = [&](long long tile, int buf) {           // thread 0: one TMA copy of the tile's [x;u] rows into image `buf`
-        mbar_expect_tx(bar0 + 8 * buf, uint32_t(S::in_bytes));
+        const bool sc = sc_tma(tile);
+        const uint32_t extra = sc ? uint32_t(S::sc_bytes) * ((dt_tma ? 1u : 0u) + (t_tma ? 1u : 0u)) : 0u;
+        mbar_expect_tx(bar0 + 8 * buf, uint32_t(S::in_bytes) + extra);
         if constexpr (SOA) tensor_load_2d(smem_u32(in_img[buf]), &a.zmap, int(tile * TILE), 0, bar0 + 8 * buf);
         else bulk_load(smem_u32(in_img[buf]), a.Z + tile * TILE * NZ, uint32_t(S::in_bytes), bar0 + 8 * buf);
+        if (sc && dt_tma) bulk_load(smem_u32(sc_img + (buf * S::NSCAL) * TILE), a.dt + tile * TILE, uint32_t(S::sc_bytes), bar0 + 8 * buf);
+        if constexpr (uses_time<Model>::value) {
+            if (sc && t_tma) bulk_load(smem_u32(sc_img + (buf * S::NSCAL + 1) * TILE), a.t + tile * TILE, uint32_t(S::sc_bytes), bar0 + 8 * buf);
+        }
     };
 
     long long tile = blockIdx.x;
@@ -426,8 +445,10 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
     // load is issued here, its register is first read a whole tile of arithmetic later.
     auto knot_scalar = [&](const double* p, long long k) -> double { return (p && k < N) ? *reinterpret_cast<const volatile double*>(p + k) : 0.0; };
     double h_next = 0.0, t_next = 0.0;
-    if constexpr (Q != Q_CONTINUOUS) { if (a.dt) h_next = knot_scalar(a.dt, tile * TILE + kt); }
-    if constexpr (uses_time<Model>::value) t_next = knot_scalar(a.t, tile * TILE + kt);
+    if (tile < ntiles) {
+        if constexpr (Q != Q_CONTINUOUS) { if (a.dt && !(dt_tma && sc_tma(tile))) h_next = knot_scalar(a.dt, tile * TILE + kt); }
+        if constexpr (uses_time<Model>::value) { if (!(t_tma && sc_tma(tile))) t_next = knot_scalar(a.t, tile * TILE + kt); }
+    }
     uint32_t phase[2] = {0, 0};
 #ifdef RDB_TUNE_NO_STREAMOUT
     const bool stream_out = false;
@@ -440,9 +461,10 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         const long long k0 = tile * TILE;
         const int cnt = int((N - k0) < TILE ? (N - k0) : TILE);
         const double h_cur = h_next, t_cur = t_next;
-        if (tile + gridDim.x < ntiles) {
-            if constexpr (Q != Q_CONTINUOUS) { if (a.dt) h_next = knot_scalar(a.dt, (tile + gridDim.x) * TILE + kt); }
-            if constexpr (uses_time<Model>::value) t_next = knot_scalar(a.t, (tile + gridDim.x) * TILE + kt);
+        if (tile + gridDim.x < ntiles) {                       // (only tiles whose scalars do not come through the TMA transaction)
+            const long long tn = tile + gridDim.x;
+            if constexpr (Q != Q_CONTINUOUS) { if (a.dt && !(dt_tma && sc_tma(tn))) h_next = knot_scalar(a.dt, tn * TILE + kt); }
+            if constexpr (uses_time<Model>::value) { if (!(t_tma && sc_tma(tn))) t_next = knot_scalar(a.t, tn * TILE + kt); }
         }
         const long long nxt = tile + gridDim.x;
         // (1) prefetch the next tile's [x;u] rows (buffer s^1 was last read before the previous iteration's barriers)
@@ -454,10 +476,11 @@ knot_kernel(const Model model, const __grid_constant__ KnotArgs<T> a) {
         // (3) compute in registers
         const T* zrow = SOA ? in_img[s] + kt : in_img[s] + kt * NZ;
         constexpr int ES = SOA ? TILE : 1;                     // element stride of the images
+        const bool sc = tma && sc_tma(tile);
         T h = T(0);
-        if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? h_cur : a.dt0);
+        if constexpr (Q != Q_CONTINUOUS) h = T(a.dt ? ((sc && dt_tma) ? sc_img[(s * S::NSCAL) * TILE + kt] : h_cur) : a.dt0);
         T tk = T(0);                                           // KnotPoint.t: only time-varying (user) models read it
-        if constexpr (uses_time<Model>::value) tk = T(t_cur);
+        if constexpr (uses_time<Model>::value) tk = T((sc && t_tma) ? sc_img[(s * S::NSCAL + 1) * TILE + kt] : t_cur);
         (void)cnt; (void)t_cur; (void)h_cur;
         // (4) evaluate; inside, all threads meet at images_free_barrier() before touching the output images
         //     (rows past the ragged end compute on stale smem and are never copied out)
