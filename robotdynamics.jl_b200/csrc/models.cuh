@@ -327,8 +327,16 @@ template <class T, class A> RDB_HD auto diag3_mul(T d0, T d1, T d2, const A& x) 
 // SCALED: return c * f(x,u) instead of f(x,u) (the integrators ask for the stage increment h a_s f(X_s) directly, integrators.cuh).
 // The factor is folded into constants and into elements with few partials — the inverse inertia, w before the kinematics, v before
 // a body-frame rotation — so that almost no partial is multiplied by it; the WRENCH MUST ALREADY RETURN c * F/m (and tau unscaled).
-template <class T, int ROT, int FRAME, bool DIAG_INERTIA, bool SCALED = false, class X, class U, class Wrench>
+//
+// SPLIT (body-frame built-in models): the wrench returns vec(Fb (3), Gw (3), tau (3)) with F/m = q * Fb' + Gw — a body-frame part and a
+// world-frame part (plain constants or Zero) — where Fb = |q|^4 Fb' already.  The reference evaluates q \ (q * Fb' + Gw)
+// (test/quadrotor.jl:74 `m*g + q*F`, then src/rigidbody.jl:229-230 `q \ (F ./ m)`); for the un-normalised polynomial rotation
+// R(q)' R(q) = |q|^4 I identically (R(q) = |q|^2 x a rotation), so q \ (q * Fb') == |q|^4 Fb' as polynomials in q: same value and same
+// derivatives up to rounding, without pushing ~17 columns of partials through two rotations.  (Unit quaternions built from MRP /
+// Rodrigues vectors have |q| = 1 by construction: the factor is 1 and its derivative 0.)
+template <class T, int ROT, int FRAME, bool DIAG_INERTIA, bool SCALED = false, bool SPLIT = false, class X, class U, class Wrench>
 RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const Wrench& wrench, T c = T(1)) {
+    static_assert(!SPLIT || FRAME == FRAME_BODY, "the split force is a body-frame form");
     constexpr int np = (ROT == ROT_QUAT) ? 4 : 3;
     auto r = slice<0, 3>(x);
     auto att = slice<3, np>(x);
@@ -338,7 +346,7 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
     const AttRot<T, ROT, decltype(att)> R(att);
     auto xi = wrench(R, q, r, v, w, u);
     auto Fm = slice<0, 3>(xi);
-    auto tau = slice<3, 3>(xi);
+    auto tau = slice<(SPLIT ? 6 : 3), 3>(xi);
     auto qdot = [&]() {
         if constexpr (ROT == ROT_QUAT) { if constexpr (SCALED) return rot_kinematics<T, ROT>(att, w, c); else return rot_kinematics<T, ROT>(att, w); }
         else return rot_kinematics_el<T, ROT>(att, w, SCALED ? c : T(1));
@@ -367,12 +375,20 @@ RDB_HD auto rigid_body_f(const ModelParams<T>& p, const X& x, const U& u, const 
         if constexpr (SCALED) return cat(vscale(c, v), qdot, Fm, wdot);
         else return cat(v, qdot, Fm, wdot);
     } else {
+        // q \ (F/m): the generic form rotates the world-frame force back; the split form only its world-frame part (if any)
+        auto qF = [&]() {
+            if constexpr (SPLIT) {
+                using G0 = rstd::remove_cv_t<rstd::remove_reference_t<decltype(get<3>(xi))>>;
+                if constexpr (rstd::is_same<G0, Zero>::value) return Fm;
+                else return vadd(Fm, R.template rot<true>(slice<3, 3>(xi)));
+            } else return R.template rot<true>(Fm);
+        }();
         if constexpr (SCALED) {            // c (q*v) = q*(c v),  c (q\F/m - w x v) = q\(c F/m) - w x (c v)
             auto cv = vscale(c, v);
-            return cat(R.template rot<false>(cv), qdot, vsub(R.template rot<true>(Fm), cross3<T>(w, cv)), wdot);
+            return cat(R.template rot<false>(cv), qdot, vsub(qF, cross3<T>(w, cv)), wdot);
         } else {
             auto rdot = R.template rot<false>(v);
-            auto vdot = vsub(R.template rot<true>(Fm), cross3<T>(w, v));
+            auto vdot = vsub(qF, cross3<T>(w, v));
             return cat(rdot, qdot, vdot, wdot);
         }
     }
@@ -403,25 +419,41 @@ struct RigidBody {
         // wrench: F/m in the world frame (the 1/m of vdot = F/m — and the stage factor c — are folded into the few scalars that
         // build F, instead of scaling every partial of the rotated vector), tau in the body frame
         const T im = SCALED ? c * p.inv_mass : p.inv_mass;
-        return rigid_body_f<T, ROT, FRAME, diag_inertia, SCALED>(p, x, u, [&](const auto& R, const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
+        constexpr bool SPLIT = (FRAME == FRAME_BODY);
+        return rigid_body_f<T, ROT, FRAME, diag_inertia, SCALED, SPLIT>(p, x, u, [&](const auto& R, const auto& q, const auto&, const auto&, const auto&, const auto& uu) {
+            // |q|^4 for the state quaternion (rigid_body_f: SPLIT); 1 for the unit quaternions of the 3-parameter attitudes
+            auto s4 = [&]() {
+                if constexpr (SPLIT && ROT == ROT_QUAT) return sq_(sqadd<T>(get<3>(q), sqadd<T>(get<2>(q), sqadd<T>(get<1>(q), sq_(get<0>(q))))));
+                else return T(1);
+            }();
             if constexpr (KIND == KIND_QUADROTOR) {
                 auto F1 = relu_(p.kf * get<0>(uu));
                 auto F2 = relu_(p.kf * get<1>(uu));
                 auto F3 = relu_(p.kf * get<2>(uu));
                 auto F4 = relu_(p.kf * get<3>(uu));
-                // thrust along the body z axis: the third column of R(q) for the state quaternion (quat_rotate_z: 18 products per partial),
-                // the elemental rotation of [0, 0, s] for the 3-parameter attitudes (12 FMAs per partial instead of to_quat + rotate)
-                auto qF = [&]() {
-                    if constexpr (ROT == ROT_QUAT) return quat_rotate_z<T>(q, im * (F1 + F2 + F3 + F4));
-                    else return R.template rot<false>(vec(Zero{}, Zero{}, im * (F1 + F2 + F3 + F4)));
-                }();
-                const T g0 = p.mg[0] * im, g1 = p.mg[1] * im, g2 = p.mg[2] * im;
-                auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
                 auto tau = vec(p.motor_dist * (F2 - F4), p.motor_dist * (F3 - F1),
                                p.km * (get<0>(uu) - get<1>(uu) + get<2>(uu) - get<3>(uu)));
-                return cat(Fm, tau);
+                const T g0 = p.mg[0] * im, g1 = p.mg[1] * im, g2 = p.mg[2] * im;
+                if constexpr (SPLIT) {      // thrust stays in the body frame, gravity is the world-frame part
+                    auto Fz = im * (F1 + F2 + F3 + F4);
+                    if constexpr (ROT == ROT_QUAT) return cat(vec(Zero{}, Zero{}, s4 * Fz), vec(g0, g1, g2), tau);
+                    else return cat(vec(Zero{}, Zero{}, Fz), vec(g0, g1, g2), tau);
+                } else {
+                    // thrust along the body z axis: the third column of R(q) for the state quaternion (quat_rotate_z: 18 products per partial),
+                    // the elemental rotation of [0, 0, s] for the 3-parameter attitudes (12 FMAs per partial instead of to_quat + rotate)
+                    auto qF = [&]() {
+                        if constexpr (ROT == ROT_QUAT) return quat_rotate_z<T>(q, im * (F1 + F2 + F3 + F4));
+                        else return R.template rot<false>(vec(Zero{}, Zero{}, im * (F1 + F2 + F3 + F4)));
+                    }();
+                    auto Fm = vec(g0 + get<0>(qF), g1 + get<1>(qF), g2 + get<2>(qF));
+                    return cat(Fm, tau);
+                }
             } else {
-                return cat(R.template rot<false>(vscale(im, slice<0, 3>(uu))), slice<3, 3>(uu));
+                if constexpr (SPLIT) {      // the force input is a body-frame vector and there is no world-frame part
+                    auto Fb = vscale(im, slice<0, 3>(uu));
+                    if constexpr (ROT == ROT_QUAT) return cat(vscale(s4, Fb), vec(Zero{}, Zero{}, Zero{}), slice<3, 3>(uu));
+                    else return cat(Fb, vec(Zero{}, Zero{}, Zero{}), slice<3, 3>(uu));
+                } else return cat(R.template rot<false>(vscale(im, slice<0, 3>(uu))), slice<3, 3>(uu));
             }
         }, c);
     }

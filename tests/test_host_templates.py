@@ -25,7 +25,11 @@ CASES = [(0, 0, 0, 3, 0), (0, 0, 0, 2, 0), (0, 0, 0, 1, 0),
          (1, 1, 1, 3, 1),      # quadrotor, body frame, RK4 rolled: two elemental rotations per stage
          (2, 2, 0, 1, 0),      # satellite-type body, MRP, RK2 increment form (BASELINE C4's kernel)
          (1, 2, 0, 3, 1),      # quadrotor{MRP}: elemental thrust rotation + elemental MRP kinematics
-         (2, 3, 1, 3, 0)]      # body, Rodrigues, body frame, RK4 unrolled increment form
+         (2, 3, 1, 3, 0),      # body, Rodrigues, body frame, RK4 unrolled increment form
+         (1, 1, 1, 2, 0),      # body-frame models: q \ (q * Fb + Gw) evaluated as |q|^4 Fb + q \ Gw (models.cuh, SPLIT) — quadrotor, RK3
+         (2, 1, 1, 3, 0),      # ... body with a body-frame force input, state quaternion (|q|^4 factor live off the manifold)
+         (1, 2, 1, 3, 0),      # ... quadrotor{MRP}, body frame
+         (2, 2, 1, 1, 1)]      # ... body{MRP}, body frame, RK2
 
 
 @pytest.fixture(scope="module")
@@ -52,6 +56,8 @@ def test_device_templates_on_host_match_the_checker(bindir, kind, rot, frame, ru
     Z = rand_inputs(om.n, om.m, N, np.random.default_rng(5))
     if kind == 1:
         Z[::7, om.n] = 0.0; Z[::5, om.n + 1] = -0.3          # thrust clamp: exact ties and negative controls
+    if om.n == 13:
+        Z[::3, 3:7] *= np.linspace(0.8, 1.2, len(Z[::3]))[:, None]      # off-manifold state quaternions (never renormalised by the path)
     text = " ".join(map(repr, pr)) + f"\n{N} {h}\n" + "\n".join(" ".join(repr(float(v)) for v in row) for row in Z) + "\n"
     out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout
     rows = np.array([[float(v) for v in ln.split()] for ln in out.strip().splitlines()])
