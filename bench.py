@@ -355,6 +355,30 @@ class SweepWorkload:
             plans[i % len(plans)].launch(st.cuda_stream)
             self.B.launches += 1
 
+    def measure_with_allgather(self, steps, warmup):
+        """SURVEY.md §8e's optional epilogue, reported separately: every rank ends the step holding the Jacobians of ALL trajectories
+        (ncclAllGather of each segment's J on that segment's stream, right behind its kernel).  Not part of `value`: the path itself has
+        no exchange step, and the number shows why a consumer should stay sharded (or all-gather the 40 / 68-byte inputs and recompute)."""
+        torch, dist = self.B.torch, self.B.dist
+        full = [torch.empty((self.B.world,) + tuple(plans[0].J.shape), dtype=plans[0].J.dtype, device="cuda") for _, plans, _ in self.work]
+
+        def step(i):
+            for (_, plans, st), out in zip(self.work, full):
+                pl = plans[i % len(plans)]
+                pl.launch(st.cuda_stream)
+                with torch.cuda.stream(st):
+                    dist.all_gather_into_tensor(out, pl.J)
+                self.B.launches += 1
+
+        ms, _ = self.B.timed(step, steps, warmup, streams=self.streams)
+        per_rank = self.B.gather(ms / steps)
+        ms_step = max(per_rank)
+        # parity of the gathered copy: this rank's slice of the last step equals its own J
+        ok = all(bool(torch.equal(out[self.B.rank], plans[(steps - 1) % len(plans)].J)) for (_, plans, _), out in zip(self.work, full))
+        return {"ms_per_step": ms_step, "per_rank_ms_per_step": per_rank, "value": self.ntraj * self.K / (ms_step * 1e-3),
+                "gathered_bytes_per_rank_per_step": int(sum(o.numel() * o.element_size() for o in full)), "gathered_equals_local": ok,
+                "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) per segment, on the segment's stream"}
+
     def measure(self, steps, warmup, peak):
         ms, _ = self.B.timed(self.step, steps, warmup, streams=self.streams)
         per_rank = self.B.gather(ms / steps)
@@ -443,6 +467,8 @@ def run_ours(args):
             torch.cuda.empty_cache()
         sw = SweepWorkload(B)
         extra["sweep_c5"] = sw.measure(args.steps, args.warmup, peak)
+        if B.world > 1:
+            extra["sweep_c5_with_allgather_of_J"] = sw.measure_with_allgather(min(args.steps, 20), args.warmup)
         del sw
         torch.cuda.empty_cache()
 

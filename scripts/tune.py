@@ -142,6 +142,47 @@ VARIANTS["satellite32"] = {"base": {}, "pad8": dict(RDB_ROWSTORE_MINWAY=8), "c9"
                            "c18": dict(RDB_TUNE_C0="0x3FFFFu", RDB_TUNE_TILE=64, RDB_TUNE_MINB=2)}
 
 
+# round 2, after the split body-frame force (models.cuh: |q|^4 Fb + q \\ Gw): the balance between the roles moved
+UNIT["bodybody"] = ("body_quat_body_f32", dict(RDB_KIND=2, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=0))
+UNIT["bodybody64"] = ("body_quat_body_f64", dict(RDB_KIND=2, RDB_ROT=1, RDB_FRAME=1, RDB_DTYPE=1))
+UNIT["quadmrpbody"] = ("quad_mrp_body_f32", dict(RDB_KIND=1, RDB_ROT=2, RDB_FRAME=1, RDB_DTYPE=0))
+VARIANTS["quadbody"] = {
+    "base": {},
+    "s12": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+    "s9": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x1FE00u"),
+    "s11": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0x1F800u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+    "3r_t64_m1": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+    "unroll": dict(RDB_TUNE_ROLL=0),
+}
+VARIANTS["bodybody"] = {   # NZ = 19: r 0-2, q 3-6, v 7-9, w 10-12, u 13-18
+    "base": {},
+    "s12": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x7F000u"),
+    "s9": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1FFu", RDB_TUNE_C1="0x7FE00u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x7E000u"),
+}
+VARIANTS["quadmrpbody"] = {   # NZ = 16: r 0-2, p 3-5, v 6-8, w 9-11, u 12-15
+    "base": {},
+    "s11": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7FFu", RDB_TUNE_C1="0xF800u"),
+    "s8": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFu", RDB_TUNE_C1="0xFF00u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=2, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0xFC0u", RDB_TUNE_C2="0xF000u"),
+}
+VARIANTS["quadbody64"] = {
+    "base": {},
+    "5r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x1E0u", RDB_TUNE_C2="0xE00u", RDB_TUNE_C3="0x7000u", RDB_TUNE_C4="0x18000u"),
+    "4r_b": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x780u", RDB_TUNE_C2="0x3800u", RDB_TUNE_C3="0x1C000u"),
+    "4r_c": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x3E0u", RDB_TUNE_C2="0x1C00u", RDB_TUNE_C3="0x1E000u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x1E000u"),
+    "4r_t32_m2": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=2),
+}
+VARIANTS["bodybody64"] = {
+    "base": {},
+    "4r_b": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x780u", RDB_TUNE_C2="0x7800u", RDB_TUNE_C3="0x78000u"),
+    "5r_t32": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0x1E0u", RDB_TUNE_C2="0x1E00u", RDB_TUNE_C3="0xE000u", RDB_TUNE_C4="0x70000u"),
+    "3r_t64": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x7Fu", RDB_TUNE_C1="0x1F80u", RDB_TUNE_C2="0x7E000u"),
+}
+
+
 def build_variants(workload):
     import build as B
     os.makedirs(OUT, exist_ok=True)
@@ -193,15 +234,18 @@ import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
 wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor", "bodyquat": "quadrotor",
+      "bodybody": "quadrotor", "bodybody64": "quadrotor", "quadmrpbody": "quadrotor",
       "quadbody64": "quadrotor", "quadmrp64": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"
-if name in ("quadrotor64", "quadbody64", "quadmrp64"): dtn = "float64"
+if name in ("quadrotor64", "quadbody64", "quadmrp64", "bodybody64"): dtn = "float64"
 if len(sys.argv) > 3: N = int(sys.argv[3])
 mk, Q = bench.gpu_model(wl, rd)
 if name in ('quadbody', 'quadbody64'): mk = lambda: rd.Quadrotor(bodyframe=True)
 if name in ('quadmrp', 'quadmrp64'): mk = lambda: rd.Quadrotor(rd.MRP)
 if name == 'bodyquat': mk = lambda: rd.Body()
+if name in ('bodybody', 'bodybody64'): mk = lambda: rd.Body(bodyframe=True)
+if name == 'quadmrpbody': mk = lambda: rd.Quadrotor(rd.MRP, bodyframe=True)
 model = mk(); h = model._h
 n, m = h.n, h.m
 nsets = 4
@@ -221,6 +265,8 @@ omk, oQ = bench.oracle_model(wl)
 if name in ('quadbody', 'quadbody64'): omk = lambda: o.quadrotor(o.ROT_QUAT, o.BODYFRAME)
 if name in ('quadmrp', 'quadmrp64'): omk = lambda: o.quadrotor(o.ROT_MRP)
 if name == 'bodyquat': omk = lambda: o.body()
+if name in ('bodybody', 'bodybody64'): omk = lambda: o.body(o.ROT_QUAT, o.BODYFRAME)
+if name == 'quadmrpbody': omk = lambda: o.quadrotor(o.ROT_MRP, o.BODYFRAME)
 idx = np.arange(0, N, 4099)
 if ERR:
     err = 0.0

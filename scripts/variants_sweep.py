@@ -2,6 +2,9 @@
 rotating buffer sets larger than L2, CUDA events, launch gate as in bench.py; fraction of the measured HBM peak.
 
     python scripts/variants_sweep.py [N] > profiles/variants_rNN.md
+
+Under ncu (per-launch instruction counts and pipe utilisation of the same kernels; scripts/variants_roofline.py merges both):
+    RDB_SWEEP_STEPS=1 RDB_SWEEP_WARM=1 ncu --metrics ... -k regex:knot_kernel --csv --log-file variants_ncu.csv python scripts/variants_sweep.py
 """
 import json, os, sys
 import numpy as np
@@ -31,10 +34,10 @@ for name in names:
             Zs = [torch.from_numpy(rand_inputs(n, m, Nn, np.random.default_rng(i)).astype(dtn)).cuda() for i in range(nsets)]
             Js = [torch.empty((Nn, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
             plans = [rd._abi.Plan(h, rd._abi.OP_DISCRETE_JACOBIAN, Q.code, Z, 0.01, J=J) for Z, J in zip(Zs, Js)]
-            for i in range(5):
+            for i in range(int(os.environ.get("RDB_SWEEP_WARM", "5"))):
                 plans[i % nsets].launch()
             torch.cuda.synchronize()
-            steps = 50
+            steps = int(os.environ.get("RDB_SWEEP_STEPS", "50"))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda._sleep(2_000_000)
             e0.record()
