@@ -43,7 +43,10 @@ struct KnotConfigDefault<Model, float, true, Q, std::enable_if_t<(Model::n >= 12
     // RK3 / RK4: two wide roles.  World-frame quaternion models split after w1 ({r,q,v,w0,w1} {w2,u}: C3 51 us, Body 67 -> 58 us);
     // body-frame and 3-parameter attitudes couple more rows to v and w and balance better split after v ({r,att,v} {w,u}:
     // quadrotor body frame 162 -> 137 us, quadrotor{MRP} 78 -> 74 us; profiles/tuning_r01.md).
-    static constexpr int split = (Model::rot == ROT_QUAT && Model::frame == FRAME_WORLD) ? n - 1 : n - 3;
+    // After the split body-frame force (models.cuh) the body-frame rows are lighter and every body-frame model balances best split after
+    // w1 as well: quadrotor body frame 85.8 -> 76.2 us, quadrotor{MRP} body frame 80.8 -> 78.9 us, Body{Quat} body frame 71.6 -> 71.7 us
+    // (profiles/tuning_r02.md); only the world-frame 3-parameter attitudes keep {r,att,v} {w,u}.
+    static constexpr int split = (Model::rot == ROT_QUAT || Model::frame == FRAME_BODY) ? n - 1 : n - 3;
     using Heavy = MaskList<range_mask(0, split), range_mask(split, NZ)>;
     using Light = std::conditional_t<m == 4, MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, NZ)>,            // {r,att} {v,w} {u}
                                               MaskList<range_mask(0, n - 6), range_mask(n - 6, n), range_mask(n, n + 3), range_mask(n + 3, NZ)>>;

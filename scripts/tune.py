@@ -183,6 +183,18 @@ VARIANTS["bodybody64"] = {
 }
 
 
+# small-batch latency (N <= a few thousand knots: one wave, the time is one thread's dependent chain): narrow tiles, more / narrower roles
+UNIT["quadlat"] = UNIT["quadrotor"]
+VARIANTS["quadlat"] = {
+    "base": {},
+    "t32_2r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFFFu", RDB_TUNE_C1="0x1F000u"),
+    "t32_4r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x3Fu", RDB_TUNE_C1="0x7C0u", RDB_TUNE_C2="0x3800u", RDB_TUNE_C3="0x1C000u"),
+    "t32_6r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0xE0u", RDB_TUNE_C2="0x700u", RDB_TUNE_C3="0x1800u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
+    "t32_8r": dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0xFu", RDB_TUNE_C1="0x30u", RDB_TUNE_C2="0xC0u", RDB_TUNE_C3="0x300u", RDB_TUNE_C4="0xC00u", RDB_TUNE_C5="0x3000u", RDB_TUNE_C6="0xC000u", RDB_TUNE_C7="0x10000u"),
+    "t32_6r_unroll": dict(RDB_TUNE_ROLL=0, RDB_TUNE_TILE=32, RDB_TUNE_MINB=1, RDB_TUNE_C0="0x1Fu", RDB_TUNE_C1="0xE0u", RDB_TUNE_C2="0x700u", RDB_TUNE_C3="0x1800u", RDB_TUNE_C4="0x6000u", RDB_TUNE_C5="0x18000u"),
+}
+
+
 def build_variants(workload):
     import build as B
     os.makedirs(OUT, exist_ok=True)
@@ -234,7 +246,7 @@ import bench
 from oracle import rd_oracle as o
 name = sys.argv[2]
 wl = {"satellite32": "satellite", "quadrotor64": "quadrotor", "quadbody": "quadrotor", "quaderr": "quadrotor", "quadmrp": "quadrotor", "bodyquat": "quadrotor",
-      "bodybody": "quadrotor", "bodybody64": "quadrotor", "quadmrpbody": "quadrotor",
+      "bodybody": "quadrotor", "bodybody64": "quadrotor", "quadmrpbody": "quadrotor", "quadlat": "quadrotor",
       "quadbody64": "quadrotor", "quadmrp64": "quadrotor"}.get(name, name)
 desc, n, m, N, dtn, dt = bench.WORKLOADS[wl]
 if name == "satellite32": dtn = "float32"

@@ -34,7 +34,7 @@ def main(table, ncu):
     rows = [ln for ln in open(table).read().splitlines() if ln.startswith("| ") and not ln.startswith("| model") and not ln.startswith("|---")]
     prof = ncu_rows(ncu)
     assert len(prof) == 2 * len(rows), (len(prof), len(rows))
-    print("| model | dtype | rule | N | us | evals/s | algorithmic GB/s | of HBM peak | warp inst / knot x32 | regs | issue slots busy | FMA pipe | FP64 pipe | binding roofline: fraction | max err vs checker |")
+    print("| model | dtype | rule | N | us | evals/s | algorithmic GB/s | of HBM peak | warp inst / knot x32 | regs | issue slots busy | FMA pipe | FP64 pipe | most utilised resource (HBM = algorithmic fraction of the measured copy bandwidth; issue / pipes = ncu, single cold launch) | max err vs checker |")
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for ln, p in zip(rows, prof[1::2]):
         c = [x.strip() for x in ln.strip("|").split("|")]
