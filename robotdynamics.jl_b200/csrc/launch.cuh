@@ -91,6 +91,26 @@ struct KnotConfig<Model, T, false, Q> {
 };
 #endif
 
+// Small batches (a solver's 10^2 - 10^3 knots per call): one wave of CTAs, the launch lasts as long as ONE thread's dependent chain.
+// The long rigid-body RK3 / RK4 Jacobian chains then run faster on 32-knot tiles — four times as many CTAs, each warp on a scheduler of
+// its own instead of two per scheduler on few SMs — with the same roles (graph-replayed launch, Quadrotor RK4 fp32: 5.3 -> 3.2 us at
+// N <= 1024, 5.6 -> 4.3 us at 4096, equal at 16384; profiles/small_batch_r02.md).  Large batches keep the wide tiles (larger TMA
+// transactions).  `distinct` = this configuration exists as its own instantiation.
+#ifndef RDB_SMALL_N
+#define RDB_SMALL_N 8192
+#endif
+template <class Model, class T, bool WITH_J, int Q, class Enable = void>
+struct KnotConfigSmall : KnotConfig<Model, T, WITH_J, Q> { static constexpr bool distinct = false; };
+#ifndef RDB_TUNE_TILE
+template <class Model, class T, int Q>
+struct KnotConfigSmall<Model, T, true, Q, std::enable_if_t<(Model::n >= 12) && (Q == Q_RK3 || Q == Q_RK4)>> {
+    using D = KnotConfig<Model, T, true, Q>;
+    static constexpr int TILE = 32, MINB = 1, ROLL = D::ROLL;
+    using Chunks = typename D::Chunks;
+    static constexpr bool distinct = (D::TILE != 32);
+};
+#endif
+
 template <mask_t... Acc> struct nz_build {
     template <mask_t M> using add = std::conditional_t<M != 0, nz_build<Acc..., M>, nz_build<Acc...>>;
     using type = MaskList<Acc...>;
@@ -202,9 +222,10 @@ inline bool soa_tma_ok(const void* Z, const void* J, const void* out, long long 
 // shape seen by the tiling rules in error-state mode: nerr rows, nerr + m columns (like an n = 12 model)
 template <class Model> struct ErrShape { static constexpr int n = Model::nerr, m = Model::m, rot = ROT_QUAT, frame = FRAME_WORLD; };
 
-template <class Model, int Q, class T, bool WITH_J, bool ERR = false, bool SOA = false>
+template <class Model, int Q, class T, bool WITH_J, bool ERR = false, bool SOA = false, bool SMALL = false>
 struct KnotLaunch {
-    using Cfg = KnotConfig<std::conditional_t<ERR, ErrShape<Model>, Model>, T, WITH_J, Q>;
+    using Shape = std::conditional_t<ERR, ErrShape<Model>, Model>;
+    using Cfg = std::conditional_t<SMALL, KnotConfigSmall<Shape, T, WITH_J, Q>, KnotConfig<Shape, T, WITH_J, Q>>;
     using S = KnotSmem<Model, Cfg::TILE, WITH_J, T, ERR>;
     static constexpr int NTHR = Cfg::TILE * Cfg::Chunks::count;
     // ld: knots per component row of the caller's arrays (component-major kernels only)
@@ -300,6 +321,9 @@ inline int run_one(const KnotRequest& r) {
     if (r.soa) {
         if constexpr (RDB_SOA_KERNELS) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, true>::run(model, a, r.dev, r.stream, r.ld);
         else return -2;
+    }
+    if constexpr (KnotConfigSmall<typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape, T, WITH_J, Q>::distinct) {
+        if (r.N <= RDB_SMALL_N) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
     }
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }

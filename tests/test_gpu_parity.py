@@ -46,6 +46,14 @@ def test_discrete_jacobian_all_models(rd, torch_, name, dtype):
             torch_.cuda.synchronize()
             assert np.abs(J.cpu().numpy() - o.discrete_jacobian(om, Q, Z64, dt)).max() < TOL[dtype]
             assert np.abs(xn.cpu().numpy() - o.discrete_dynamics(om, Q, Z64, dt)).max() < TOL[dtype]
+    # above the small-batch threshold (launch.cuh: RDB_SMALL_N = 8192) the rigid-body RK3 / RK4 Jacobians run on their wide tiles:
+    # the same comparison there, every knot, ragged tail
+    Nb = 8192 + 4133
+    Zb = rand_inputs(om.n, om.m, Nb, np.random.default_rng(22)).astype(dtype)
+    for Q in (o.RK3, o.RK4):
+        Jb = gm._h.discrete_jacobian(Q, dev(torch_, Zb), 0.05)
+        torch_.cuda.synchronize()
+        assert np.abs(Jb.cpu().numpy() - o.discrete_jacobian(om, Q, Zb.astype(np.float64), 0.05)).max() < TOL[dtype]
     # continuous dynamics and Jacobian (dynamics / jacobian!)
     xd = torch_.empty((N, om.n), dtype=Zd.dtype, device="cuda")
     Jc = gm._h.jacobian(Zd, xdot=xd)
@@ -419,6 +427,12 @@ def test_discrete_error_jacobian(rd, torch_, name):
         ref = _error_jacobian_ref(om, o.RK4, Zt.astype(np.float64), dt)
         assert np.abs(o.as_matrix(Jd.cpu().numpy()) - ref).max() < tol
         assert np.array_equal(Js.cpu().numpy().T.reshape(N, om.nerr + om.m, om.nerr), Jd.cpu().numpy())
+        # wide-tile kernels (N above launch.cuh's RDB_SMALL_N)
+        Nb = 8192 + 777
+        Zb = np.tile(Zt, (Nb // N + 1, 1))[:Nb]
+        Jbig = gm._h.discrete_error_jacobian(o.RK4, dev(torch_, Zb), 0.05)
+        torch_.cuda.synchronize()
+        assert np.abs(o.as_matrix(Jbig.cpu().numpy()) - _error_jacobian_ref(om, o.RK4, Zb.astype(np.float64), 0.05)).max() < tol
     # reference-facing spelling, one knot
     dm = rd.DiscretizedDynamics(gm, rd.RK4)
     z = rd.KnotPoint(Z[0, :om.n], Z[0, om.n:], 0.0, 0.05)
