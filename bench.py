@@ -330,7 +330,7 @@ class SweepWorkload:
         self.B = B
         self.ntraj, self.K = 4096, 256
         segs = sh.partition_segments({"cartpole": self.ntraj // 2, "quadrotor": self.ntraj // 2}, B.world, B.rank)
-        self.work, self.bytes_local, self.knots_local = [], 0, 0
+        self.work, self.meta, self.bytes_local, self.knots_local = [], [], 0, 0
         for name, (lo, hi) in segs.items():
             _, n, m, _, dtn, _ = WORKLOADS[name]
             mk, Q = gpu_model(name, rd)
@@ -346,6 +346,7 @@ class SweepWorkload:
             Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
             plans = [rd._abi.Plan(model._h, rd._abi.OP_DISCRETE_JACOBIAN, Q.code, Z, dt, J=J) for Z, J in zip(Zs, Js)]
             self.work.append((model, plans, torch.cuda.Stream()))
+            self.meta.append((Q.code, n, m, self.ntraj // 2))
             self.bytes_local += cnt * per
             self.knots_local += cnt
         self.streams = [w[2] for w in self.work]
@@ -378,6 +379,38 @@ class SweepWorkload:
         return {"ms_per_step": ms_step, "per_rank_ms_per_step": per_rank, "value": self.ntraj * self.K / (ms_step * 1e-3),
                 "gathered_bytes_per_rank_per_step": int(sum(o.numel() * o.element_size() for o in full)), "gathered_equals_local": ok,
                 "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) per segment, on the segment's stream"}
+
+    def measure_replicated(self, steps, warmup):
+        """The alternative to gathering J: all-gather the INPUTS (40 / 68 bytes per knot instead of 160 / 884) and let every rank evaluate
+        the Jacobians of all trajectories itself — recomputing is cheaper than moving them over NVLink."""
+        torch, dist, rd, W = self.B.torch, self.B.dist, self.B.rd, self.B.world
+        full = []
+        for (model, plans, st), (qc, n, m, ntr) in zip(self.work, self.meta):
+            Zf = torch.empty((W,) + tuple(plans[0].Z.shape), dtype=plans[0].Z.dtype, device="cuda")
+            Jf = torch.empty((W * plans[0].Z.shape[0], n + m, n), dtype=Zf.dtype, device="cuda")
+            dt = torch.from_numpy(np.repeat(0.01 * (1 + np.arange(0, ntr) % 4), self.K)).cuda()
+            full.append((Zf, Jf, rd._abi.Plan(model._h, rd._abi.OP_DISCRETE_JACOBIAN, qc, Zf.view(-1, n + m), dt, J=Jf)))
+
+        def step(i):
+            for (_, plans, st), (Zf, Jf, pl) in zip(self.work, full):
+                with torch.cuda.stream(st):
+                    dist.all_gather_into_tensor(Zf, plans[i % len(plans)].Z)
+                pl.launch(st.cuda_stream)
+                self.B.launches += 1
+
+        ms, _ = self.B.timed(step, steps, warmup, streams=self.streams)
+        per_rank = self.B.gather(ms / steps)
+        ms_step = max(per_rank)
+        # this rank's slice of the replicated result equals what its own shard computes from the same inputs
+        ok = True
+        for (_, plans, st), (Zf, Jf, pl) in zip(self.work, full):
+            mine = plans[(steps - 1) % len(plans)]
+            mine.launch(st.cuda_stream); st.synchronize()
+            cnt = mine.Z.shape[0]
+            ok = ok and bool(torch.equal(Jf[self.B.rank * cnt:(self.B.rank + 1) * cnt], mine.J))
+        return {"ms_per_step": ms_step, "per_rank_ms_per_step": per_rank, "value": self.ntraj * self.K / (ms_step * 1e-3),
+                "gathered_bytes_per_rank_per_step": int(sum(f[0].numel() * f[0].element_size() for f in full)), "replica_equals_shard": ok,
+                "collective": "ncclAllGather of Z per segment, then the full-size Jacobian launch on every rank"}
 
     def measure(self, steps, warmup, peak):
         ms, _ = self.B.timed(self.step, steps, warmup, streams=self.streams)
@@ -469,6 +502,7 @@ def run_ours(args):
         extra["sweep_c5"] = sw.measure(args.steps, args.warmup, peak)
         if B.world > 1:
             extra["sweep_c5_with_allgather_of_J"] = sw.measure_with_allgather(min(args.steps, 20), args.warmup)
+            extra["sweep_c5_replicated_via_allgather_of_Z"] = sw.measure_replicated(min(args.steps, 20), args.warmup)
         del sw
         torch.cuda.empty_cache()
 
