@@ -79,6 +79,12 @@ int rdb_destroy(rdb_context* ctx);
 /* pinned host memory for the HOST-pointer path (optional; pageable memory also works, slower) */
 void* rdb_host_alloc(size_t bytes);
 void rdb_host_free(void* p);
+/* page-lock memory the caller already owns (a Julia Array{T,3} of Jacobians that a solver reuses every iteration,
+ * src/trajectories.jl:40-50 / Altro's per-knot DynamicsJacobian storage) so that the HOST-pointer path copies by DMA at PCIe
+ * speed instead of through the driver's pageable staging (~3x slower); register once, unregister before the array is freed.
+ * The range need not be page-aligned.  Returns 0, RDB_ERR_ARG for a null / empty range, or the CUDA error as a positive code. */
+int rdb_host_register(void* p, size_t bytes);
+int rdb_host_unregister(void* p);
 
 /* params packing per kind (doubles):
  *   CARTPOLE          [mc, mp, l, g]                                          test/cartpole_model.jl:9

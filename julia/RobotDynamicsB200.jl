@@ -35,6 +35,15 @@ end
 const CTX = Ref{Context}()
 context() = isassigned(CTX) ? CTX[] : (CTX[] = Context(0))
 
+"""
+    pin!(A::Array) / unpin!(A)
+
+Page-lock an array the solver already owns (the `Array{T,3}` of Jacobians it reuses every iteration, a `SampledTrajectory`'s gathered
+`(n+m) x N` buffer) so the host-pointer path moves it by DMA at PCIe speed; `unpin!` before the array is freed.
+"""
+pin!(A::Array) = (check(ccall((:rdb_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), pointer(A), sizeof(A)), "rdb_host_register"); A)
+unpin!(A::Array) = (check(ccall((:rdb_host_unregister, LIB), Cint, (Ptr{Cvoid},), pointer(A)), "rdb_host_unregister"); A)
+
 const KIND_CARTPOLE, KIND_QUADROTOR, KIND_BODY, KIND_DI = Cint(0), Cint(1), Cint(2), Cint(3)
 rotcode(::Type{<:QuatRotation}) = Cint(1); rotcode(::Type{<:MRP}) = Cint(2); rotcode(::Type{<:RodriguesParam}) = Cint(3)
 framecode(model) = RD.velocity_frame(model) == :body ? Cint(1) : Cint(0)          # src/rigidbody.jl:258

@@ -10,7 +10,7 @@ The directory name contains a dot, so it cannot be imported with a plain `import
 Importing the package loads librdb200.so (built by csrc/build.py); there is no CPU fallback.
 """
 from . import _abi
-from ._abi import (AOS, SOA, F32, F64, EULER, RK2 as RK2_CODE, Context, ModelHandle, PinnedArray, RDBError,
+from ._abi import (AOS, SOA, F32, F64, EULER, RK2 as RK2_CODE, Context, ModelHandle, PinnedArray, RegisteredArray, RDBError,
                    NotImplementedModelError, LIB_PATH, context)
 from .api import *  # noqa: F401,F403
 from .api import (InPlace, StaticReturn, ForwardAD, FiniteDifference, UserDefined, B200, Euler, RK2, RK3, RK4,

@@ -29,7 +29,7 @@ ERR_ARG, ERR_NOT_IMPLEMENTED, ERR_POINTER_MIX, ERR_NO_DEVICE, ERR_COMPILE = -1, 
 
 # every symbol include/rdb200.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free",
+    "rdb_version", "rdb_strerror", "rdb_create", "rdb_destroy", "rdb_host_alloc", "rdb_host_free", "rdb_host_register", "rdb_host_unregister",
     "rdb_model_create", "rdb_model_create_custom", "rdb_model_create_custom_rigid", "rdb_model_create_custom_lie", "rdb_custom_check", "rdb_custom_rigid_check", "rdb_last_log", "rdb_model_destroy", "rdb_model_dims", "rdb_dynamics", "rdb_discrete_dynamics",
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
@@ -72,6 +72,8 @@ def lib():
         L.rdb_host_alloc.restype = vp
         L.rdb_host_alloc.argtypes = [ctypes.c_size_t]
         L.rdb_host_free.argtypes = [vp]
+        L.rdb_host_register.argtypes = [vp, ctypes.c_size_t]
+        L.rdb_host_unregister.argtypes = [vp]
         L.rdb_model_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_model_create_custom.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
         L.rdb_model_create_custom_rigid.argtypes = [vp, i32, i32, i32, ctypes.c_char_p, dbl, ctypes.POINTER(dbl), ctypes.POINTER(dbl), i32, ctypes.POINTER(vp)]
@@ -272,6 +274,37 @@ class PinnedArray:
             if self._p:
                 lib().rdb_host_free(self._p)
                 self._p = None
+        except Exception:
+            pass
+
+
+class RegisteredArray:
+    """Page-locks a numpy array the caller already owns (rdb_host_register) for as long as this object lives: the host-pointer
+    path then moves it by DMA.  Use as a context manager or keep the object next to the array."""
+
+    def __init__(self, array):
+        if not isinstance(array, np.ndarray) or not array.flags.c_contiguous or array.nbytes == 0:
+            raise ValueError("RegisteredArray needs a non-empty C-contiguous numpy array")
+        self.array, self._p = array, array.ctypes.data
+        rc = lib().rdb_host_register(self._p, array.nbytes)
+        if rc != 0:
+            self._p = None
+            raise RDBError(f"rdb_host_register failed ({rc})")
+
+    def close(self):
+        if self._p:
+            lib().rdb_host_unregister(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

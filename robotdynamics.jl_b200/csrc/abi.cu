@@ -406,6 +406,18 @@ void* rdb_host_alloc(size_t bytes) {
     return p;
 }
 void rdb_host_free(void* p) { if (p) cudaFreeHost(p); }
+int rdb_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return RDB_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return int(e); }
+    return 0;
+}
+int rdb_host_unregister(void* p) {
+    if (!p) return RDB_ERR_ARG;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return int(e); }
+    return 0;
+}
 
 int rdb_model_create(rdb_context* ctx, int kind, int rot, int frame, const double* params, int np, rdb_model** model) {
     if (!ctx || !model || !params || np < 0) return RDB_ERR_ARG;

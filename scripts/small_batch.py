@@ -6,7 +6,8 @@ For N = 64 .. 16384 and each operation of the path, device pointers:
   stream   us per call, 300 calls enqueued back to back on one stream, CUDA events (launch-throughput bound)
   sync     us per call, each call followed by a device synchronize, host wall clock (what a solver loop that needs the result sees)
   graph    us per replay of a CUDA graph holding ONE call (captured through the same C-ABI entry point), events
-  host     us per call with HOST (numpy) pointers: staging H2D + kernel + D2H inside the library, wall clock
+  host     us per call with HOST (numpy) pointers: staging H2D + kernel + D2H inside the library, wall clock — pageable arrays, and
+           the same arrays page-locked in place with rdb_host_register
   plan     us per rdb_plan_launch of the same operation (validated once), back to back on one stream, events; and with a sync after each
 """
 import argparse
@@ -39,7 +40,7 @@ def main():
     ]
     PLAN_OPS = {"discrete_jacobian! RK4 Cartpole fp64": rd._abi.OP_DISCRETE_JACOBIAN, "discrete_jacobian! RK4 Quadrotor fp32": rd._abi.OP_DISCRETE_JACOBIAN,
                 "error-state Jacobian RK4 Quadrotor fp32": rd._abi.OP_DISCRETE_ERROR_JACOBIAN, "discrete_dynamics RK4 Quadrotor fp32": rd._abi.OP_DISCRETE_DYNAMICS}
-    lines = ["| op | N | stream us | sync us | graph us | host-pointer us | plan stream us | plan sync us |", "|---|---|---|---|---|---|---|---|"]
+    lines = ["| op | N | stream us | sync us | graph us | host-pointer us (pageable) | host-pointer us (rdb_host_register) | plan stream us | plan sync us |", "|---|---|---|---|---|---|---|---|---|"]
     for name, h, dtn, call, oshape in ops:
         for N in (64, 256, 1024, 4096, 16384):
             Zh = bench.make_inputs(h.n, h.m, N, dtn, 5)
@@ -81,6 +82,13 @@ def main():
             for _ in range(50):
                 call(h, Zh, outh)
             us_host = (time.perf_counter() - t0) / 50 * 1e6
+            with rd.RegisteredArray(Zh), rd.RegisteredArray(outh):            # the same arrays page-locked in place (rdb_host_register)
+                for _ in range(3):
+                    call(h, Zh, outh)
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    call(h, Zh, outh)
+                us_host_reg = (time.perf_counter() - t0) / 50 * 1e6
             us_plan = us_plan_sync = float("nan")
             if name in PLAN_OPS:
                 op = PLAN_OPS[name]
@@ -98,7 +106,7 @@ def main():
                 for _ in range(args.reps):
                     plan.launch(); torch.cuda.synchronize()
                 us_plan_sync = (time.perf_counter() - t0) / args.reps * 1e6
-            lines.append(f"| {name} | {N} | {us_stream:.1f} | {us_sync:.1f} | {us_graph:.1f} | {us_host:.1f} | {us_plan:.1f} | {us_plan_sync:.1f} |")
+            lines.append(f"| {name} | {N} | {us_stream:.1f} | {us_sync:.1f} | {us_graph:.1f} | {us_host:.1f} | {us_host_reg:.1f} | {us_plan:.1f} | {us_plan_sync:.1f} |")
             print(lines[-1], flush=True)
     if args.out:
         with open(args.out, "w") as f:

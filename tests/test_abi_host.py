@@ -42,6 +42,9 @@ def test_strerror_and_argument_errors():
     assert L.rdb_create(0, None) == rdb200._abi.ERR_ARG
     assert L.rdb_model_dims(None, None, None, None) == rdb200._abi.ERR_ARG
     assert L.rdb_discrete_jacobian(None, 3, 1, 0, 8, None, None, None, 0.01, None, None, None) == rdb200._abi.ERR_ARG
+    assert L.rdb_host_register(None, 16) == rdb200._abi.ERR_ARG and L.rdb_host_unregister(None) == rdb200._abi.ERR_ARG
+    buf = np.zeros(8)
+    assert L.rdb_host_register(buf.ctypes.data, 0) == rdb200._abi.ERR_ARG
 
 
 def test_fails_loudly_without_a_gpu():

@@ -1082,3 +1082,18 @@ def test_c_abi_from_plain_c_on_the_gpu(tmp_path):
     assert p.returncode == 0, p.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "[A B] of knot 0" in r.stdout, r.stdout + r.stderr
+
+
+def test_registered_caller_arrays_take_the_host_path(rd, torch_):
+    """rdb_host_register: arrays the caller already owns, page-locked in place, give the same results as pageable and pinned ones."""
+    om, gm = zoo()["quad_quat_world"][0](), zoo()["quad_quat_world"][1](rd)
+    N = 70001
+    Z = rand_inputs(om.n, om.m, N, np.random.default_rng(77)).astype(np.float32)
+    J_pageable = gm._h.discrete_jacobian(o.RK4, Z, 0.02)
+    J = np.empty((N, om.n + om.m, om.n), dtype=np.float32)
+    with rd.RegisteredArray(Z), rd.RegisteredArray(J):
+        gm._h.discrete_jacobian(o.RK4, Z, 0.02, J=J)
+    assert np.array_equal(J, J_pageable)
+    assert np.abs(J - o.discrete_jacobian(om, o.RK4, Z.astype(np.float64), 0.02)).max() < TOL[np.float32]
+    with pytest.raises(ValueError):
+        rd.RegisteredArray(np.empty((0, 3)))
