@@ -1,6 +1,6 @@
 """Launches the error-state Jacobian kernel or the warp-cooperative ImplicitMidpoint kernel a few times (target of ncu captures).
 
-    python scripts/prof_extra.py err|implicit|soa
+    python scripts/prof_extra.py err|implicit|soa|body|body64
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,6 +26,12 @@ if __name__ == "__main__":
         J = torch.empty((N, 16, 12), dtype=torch.float32, device="cuda")
         for _ in range(8):
             qd._h.discrete_error_jacobian(3, Z, 0.01, J=J)
+    elif what in ("body", "body64"):   # body-frame quadrotor RK4 Jacobian (split force), fp32 / fp64: the issue- / FP64-latency-bound kernels
+        qb = rd.Quadrotor(bodyframe=True)
+        Zb = Z if what == "body" else Z.double()
+        J = torch.empty((N, 17, 13), dtype=Zb.dtype, device="cuda")
+        for _ in range(8):
+            qb._h.discrete_jacobian(3, Zb, 0.01, J=J)
     else:
         J = torch.empty((N, 17, 13), dtype=torch.float32, device="cuda")
         for _ in range(4):

@@ -58,3 +58,17 @@ tv._h.discrete_jacobian(o.RK4, rng.random((333, 3)), 0.05, t=rng.random(333))
 tv._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, torch.from_numpy(rng.random((333, 3))).cuda(), 0.05, t=rng.random(333))
 torch.cuda.synchronize()
 print("SANITY ROUND-2 DONE")
+
+# ---- late round 2: wide-tile kernels above the small-batch threshold (launch.cuh: RDB_SMALL_N), body-frame models with the split force,
+#      a per-knot dt array riding on the tile's TMA transaction
+for gm, om, n, m in ((rd.Quadrotor(), o.quadrotor(), 13, 4), (rd.Quadrotor(bodyframe=True), o.quadrotor(o.ROT_QUAT, o.BODYFRAME), 13, 4),
+                     (rd.Body(rd.MRP, bodyframe=True), o.body(o.ROT_MRP, o.BODYFRAME), 12, 6)):
+    Nb = 8192 + 411
+    Z = rigid(n, m, Nb).astype(np.float32)
+    dtv = rng.uniform(0.005, 0.05, Nb)
+    J = gm._h.discrete_jacobian(o.RK4, torch.from_numpy(Z).cuda(), dtv)
+    Jb = gm._h.discrete_error_jacobian(o.RK4, torch.from_numpy(Z).cuda(), dtv)
+    torch.cuda.synchronize()
+    idx = np.arange(0, Nb, 97)
+    assert np.abs(J.cpu().numpy()[idx] - o.discrete_jacobian(om, o.RK4, Z[idx].astype(np.float64), dtv[idx])).max() < 1e-4
+print("SANITY LATE ROUND-2 DONE")
