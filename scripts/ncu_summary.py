@@ -31,7 +31,8 @@ UNITS = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a report, or its raw page already exported on the GPU box (`ncu -i rep --page raw --csv > rep.csv`: the reports are too large to bring back)
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h = rows[0]
     return h, rows[1], rows[2:]
