@@ -201,6 +201,27 @@ for _w in ("quadrotor", "quadbody", "quadbody64", "quadmrp64", "quadrotor64"):
     VARIANTS[_w] = {"base": {}, "roll2": dict(RDB_TUNE_ROLL=2)}
 
 
+# instruction-cache experiment: the same thread layout, register pressure and amount of work per role, but every role runs the SAME code stream
+# (results are wrong by construction — timing only): if the mean of the single-stream variants is well below the default, the gap is instruction fetch
+def _same(mask, k, **kw):
+    d = dict(RDB_TUNE_ROLL=1, **kw)
+    for i in range(k):
+        d[f"RDB_TUNE_C{i}"] = mask
+    return d
+VARIANTS["quadbody64"] = {"base": {}, "A4": _same("0x3Fu", 4, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1), "B4": _same("0x7C0u", 4, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1),
+                          "C4": _same("0x3800u", 4, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1), "D4": _same("0x1C000u", 4, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1)}
+VARIANTS["quadbody"] = {"base": {}, "A2": _same("0xFFFu", 2, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1), "B2": _same("0x1F000u", 2, RDB_TUNE_TILE=128, RDB_TUNE_MINB=1)}
+
+
+# role balance (the single-stream experiment gave per-role times A 161 / B 184 / C 267 / D 274 us for the default fp64 split {0-5}{6-10}{11-13}{14-16}:
+# u and w columns are the heavy ones, v columns nearly free): non-contiguous chunks that spread u and w
+_T64 = dict(RDB_TUNE_ROLL=1, RDB_TUNE_TILE=64, RDB_TUNE_MINB=1)
+VARIANTS["quadbody64"] = {"base": {}, "bal1": dict(_T64, RDB_TUNE_C0="0x6387u", RDB_TUNE_C1="0x18000u", RDB_TUNE_C2="0xC08u", RDB_TUNE_C3="0x1070u"),
+                          "bal1c": dict(_T64, RDB_TUNE_C0="0x6187u", RDB_TUNE_C1="0x18200u", RDB_TUNE_C2="0xC08u", RDB_TUNE_C3="0x1070u")}
+VARIANTS["quadrotor64"] = {"base": {}, "bal1": dict(_T64, RDB_TUNE_C0="0x6387u", RDB_TUNE_C1="0x18000u", RDB_TUNE_C2="0xC08u", RDB_TUNE_C3="0x1070u")}
+VARIANTS["quadmrp64"] = {"base": {}, "balm": dict(_T64, RDB_TUNE_C0="0x23Fu", RDB_TUNE_C1="0xDC0u", RDB_TUNE_C2="0x3000u", RDB_TUNE_C3="0xC000u")}
+
+
 def build_variants(workload):
     import build as B
     os.makedirs(OUT, exist_ok=True)
