@@ -323,7 +323,9 @@ inline int run_one(const KnotRequest& r) {
         else return -2;
     }
     if constexpr (KnotConfigSmall<typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape, T, WITH_J, Q>::distinct) {
-        if (r.N <= RDB_SMALL_N) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
+        // RDB200_SMALL_N overrides the threshold (experiments: scripts/tile_threshold.py)
+        static const long long small_n = []() { const char* e = std::getenv("RDB200_SMALL_N"); return e ? std::atoll(e) : (long long)RDB_SMALL_N; }();
+        if (r.N <= small_n) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
     }
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }
