@@ -319,6 +319,9 @@ class KnotWorkload:
                 "knot_points_per_gpu": self.N, "buffer_sets": self.nsets}, window
 
 
+SWEEP_STREAMS = 2
+
+
 class SweepWorkload:
     """BASELINE configs[4]: 4096 trajectories x 256 knot points, first half Cartpole fp64, second half Quadrotor fp32, per-trajectory
     dt; STRONG scaling — every rank takes its contiguous share of both segments (sharding.partition_segments).  The two segments are
@@ -331,6 +334,10 @@ class SweepWorkload:
         self.ntraj, self.K = 4096, 256
         segs = sh.partition_segments({"cartpole": self.ntraj // 2, "quadrotor": self.ntraj // 2}, B.world, B.rank)
         self.work, self.meta, self.bytes_local, self.knots_local = [], [], 0, 0
+        # RDB_SWEEP_STREAMS=1: both segments back to back on one stream (experiments); default one stream per segment
+        shared = torch.cuda.Stream() if os.environ.get("RDB_SWEEP_STREAMS", str(SWEEP_STREAMS)) == "1" else None
+        if os.environ.get("RDB_SWEEP_ORDER") == "quadfirst":
+            segs = dict(reversed(list(segs.items())))
         for name, (lo, hi) in segs.items():
             _, n, m, _, dtn, _ = WORKLOADS[name]
             mk, Q = gpu_model(name, rd)
@@ -344,12 +351,13 @@ class SweepWorkload:
             Zs = [torch.from_numpy(make_inputs(n, m, cnt, dtn, 17 * B.rank + i)).cuda() for i in range(nsets)]
             dt = torch.from_numpy(np.repeat(0.01 * (1 + np.arange(lo, hi) % 4), self.K)).cuda()
             Js = [torch.empty((cnt, n + m, n), dtype=Zs[0].dtype, device="cuda") for _ in range(nsets)]
-            plans = [rd._abi.Plan(model._h, rd._abi.OP_DISCRETE_JACOBIAN, Q.code, Z, dt, J=J) for Z, J in zip(Zs, Js)]
-            self.work.append((model, plans, torch.cuda.Stream()))
+            # the two segments overlap on the GPU (one stream each): their plans say so (rdb_plan_set_shared)
+            plans = [rd._abi.Plan(model._h, rd._abi.OP_DISCRETE_JACOBIAN, Q.code, Z, dt, J=J, shared_gpu=shared is None) for Z, J in zip(Zs, Js)]
+            self.work.append((model, plans, shared if shared is not None else torch.cuda.Stream()))
             self.meta.append((Q.code, n, m, self.ntraj // 2))
             self.bytes_local += cnt * per
             self.knots_local += cnt
-        self.streams = [w[2] for w in self.work]
+        self.streams = list({id(w[2]): w[2] for w in self.work}.values())
 
     def step(self, i):
         for _, plans, st in self.work:

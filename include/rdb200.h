@@ -183,6 +183,11 @@ int rdb_dynamics_error_jacobian(const rdb_model* model, int integrator, int dtyp
 int rdb_plan_create(const rdb_model* model, int op, int integrator, int dtype, int layout, int64_t N, const void* Z, const double* t,
                     const double* dt, double dt0, void* J, void* out, rdb_plan** plan);
 int rdb_plan_launch(const rdb_plan* plan, void* stream);
+/* shared != 0: this plan's launches will run WHILE other kernels use the same GPU (another model's plan on a second stream, as in a
+ * mixed-model sweep).  Some rigid-body kernels are fastest on small CTAs, four to an SM, when they have the GPU to themselves; next to
+ * foreign CTAs those interleave SM by SM and both kernels slow down.  A shared plan keeps the wide tiling whose CTAs each fill an SM
+ * (mixed Cartpole + Quadrotor sweep: 106.7 us against 124.7 us).  Results are identical either way. */
+int rdb_plan_set_shared(rdb_plan* plan, int shared);
 int rdb_plan_destroy(rdb_plan* plan);
 
 /* ---- persistent device trajectory -------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ SYMBOLS = (
     "rdb_jacobian", "rdb_discrete_jacobian", "rdb_discrete_error_jacobian", "rdb_errstate_jacobian", "rdb_grad_errstate_jacobian",
     "rdb_state_diff", "rdb_rollout",
     "rdb_dynamics_error", "rdb_dynamics_error_jacobian",
-    "rdb_plan_create", "rdb_plan_launch", "rdb_plan_destroy",
+    "rdb_plan_create", "rdb_plan_launch", "rdb_plan_set_shared", "rdb_plan_destroy",
     "rdb_trajectory_create", "rdb_trajectory_destroy", "rdb_trajectory_dims", "rdb_trajectory_data", "rdb_trajectory_set_states",
     "rdb_trajectory_set_initial_state", "rdb_trajectory_set_controls", "rdb_trajectory_set_timesteps", "rdb_trajectory_get_states",
     "rdb_trajectory_get_controls", "rdb_trajectory_rollout", "rdb_trajectory_linearize", "rdb_trajectory_rollout_linearize",
@@ -97,6 +97,7 @@ def lib():
         L.rdb_plan_create.argtypes = [vp, i32, i32, i32, i32, i64, vp, vp, vp, dbl, vp, vp, ctypes.POINTER(vp)]
         L.rdb_plan_launch.argtypes = [vp, vp]
         L.rdb_plan_destroy.argtypes = [vp]
+        L.rdb_plan_set_shared.argtypes = [vp, i32]
         L.rdb_trajectory_create.argtypes = [vp, i32, i64, i32, ctypes.POINTER(vp)]
         L.rdb_trajectory_destroy.argtypes = [vp]
         L.rdb_trajectory_dims.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
@@ -529,7 +530,7 @@ class Plan:
     """rdb_plan: one validated knot operation on DEVICE tensors; launch() is a single kernel launch on the current stream (or under
     CUDA-graph capture).  The tensors are kept alive by the plan; it evaluates whatever they hold at execution time."""
 
-    def __init__(self, handle, op, Q, Z, dt, t=None, J=None, out=None, layout=AOS):
+    def __init__(self, handle, op, Q, Z, dt, t=None, J=None, out=None, layout=AOS, shared_gpu=False):
         if not (_is_torch(Z) and Z.is_cuda):
             raise RDBError(ERR_POINTER_MIX, "a plan needs device tensors")
         handle._zcheck(Z)
@@ -552,6 +553,8 @@ class Plan:
         pz, _ = ptr(Z); pj, _ = ptr(J); po, _ = ptr(out); pd, _ = ptr(dtv); pt, _ = ptr(tv)
         check(lib().rdb_plan_create(handle._h, int(op), int(Q), dtype_code(Z), layout, N, pz, pt, pd, dt0, pj, po, ctypes.byref(self._p)),
               "rdb_plan_create")
+        if shared_gpu:          # launches will overlap other kernels on the same GPU (rdb_plan_set_shared): keep SM-filling CTAs
+            check(lib().rdb_plan_set_shared(self._p, 1), "rdb_plan_set_shared")
         self._launch = lib().rdb_plan_launch
         import torch
         self._stream = torch.cuda.current_stream

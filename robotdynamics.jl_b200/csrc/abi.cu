@@ -777,6 +777,12 @@ int rdb_plan_launch(const rdb_plan* p, void* stream) {
     return p->layout == RDB_SOA ? dispatch_soa(p->M, p->dtype, r, r.N) : dispatch(p->M, p->dtype, &r);
 }
 
+int rdb_plan_set_shared(rdb_plan* p, int shared) {
+    if (!p) return RDB_ERR_ARG;
+    p->r.whole_sm = shared ? 1 : 0;
+    return 0;
+}
+
 int rdb_plan_destroy(rdb_plan* p) { delete p; return 0; }
 
 // ---- persistent device trajectory ------------------------------------------------------------------------------------------------------

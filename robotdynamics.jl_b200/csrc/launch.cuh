@@ -101,6 +101,17 @@ struct KnotConfig<Model, T, false, Q> {
 #endif
 template <class Model, class T, bool WITH_J, int Q, class Enable = void>
 struct KnotConfigSmall : KnotConfig<Model, T, WITH_J, Q> { static constexpr bool distinct = false; };
+// ... and some of them at EVERY size (measured at 262144 knots, all 12 variants x dtype, profiles/tuning_r02.md: four 64-thread CTAs per SM
+// overlap their load / compute / store phases better than one 256-thread CTA whose roles meet at one barrier): world-frame quaternion
+// models in fp32 (C3 45.5 -> 42.6 us, its error-state form 45.3 -> 42.8 us, Body{Quat} 51.0 -> 50.0 us) and the Body / Satellite family
+// with a 3-parameter attitude in fp64 or in the body frame (Body{MRP} body frame 74.0 -> 69.1 us fp32, 211 -> 191 us fp64; Body{MRP} fp64
+// 146.7 -> 139.6 us).  Every other variant is faster on the wide tiles from ~16k knots on (quadrotor{MRP} fp64 141.9 vs 157.7 us).
+template <class Shape, class T>
+constexpr bool prefers_narrow_tiles() {
+    if (Shape::rot == ROT_QUAT && Shape::frame == FRAME_WORLD) return sizeof(T) == 4;
+    if (Shape::m == 6 && Shape::rot != ROT_QUAT) return sizeof(T) == 8 || Shape::frame == FRAME_BODY;
+    return false;
+}
 #ifndef RDB_TUNE_TILE
 template <class Model, class T, int Q>
 struct KnotConfigSmall<Model, T, true, Q, std::enable_if_t<(Model::n >= 12) && (Q == Q_RK3 || Q == Q_RK4)>> {
@@ -283,6 +294,7 @@ struct KnotRequest {
     ModelParams<double> params;
     const void* Z; const double* dt; double dt0; void* J; void* out; long long N;   // knot-major, or component-major when soa != 0
     const double* t;         // per-knot times (N) or null; only time-varying (user) models read them
+    int whole_sm;            // plans that share the GPU with other kernels (rdb_plan_set_shared): keep the wide, SM-filling tiles
     int soa; long long ld;   // component-major arrays with ld knots per component row, served by the tensor-map kernels
     // OP_ROLLOUT: x0 (n, ntraj), U (m, K-1, ntraj), dt (K, ntraj) or null, X (n, K, ntraj)   [trajectory-major, zmode == 0]
     //             zmode != 0: X is the knot-major batch Z (K, ntraj, n+m) holding the controls; steps [kb, ke)   (kernels.cuh)
@@ -324,8 +336,13 @@ inline int run_one(const KnotRequest& r) {
     }
     if constexpr (KnotConfigSmall<typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape, T, WITH_J, Q>::distinct) {
         // RDB200_SMALL_N overrides the threshold (experiments: scripts/tile_threshold.py)
-        static const long long small_n = []() { const char* e = std::getenv("RDB200_SMALL_N"); return e ? std::atoll(e) : (long long)RDB_SMALL_N; }();
-        if (r.N <= small_n) return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
+        using Shape = typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape;
+        static const long long small_n = []() {
+            const char* e = std::getenv("RDB200_SMALL_N");
+            return e ? std::atoll(e) : (prefers_narrow_tiles<Shape, T>() ? (long long)1 << 62 : (long long)RDB_SMALL_N);
+        }();
+        if (r.N <= small_n && !(r.whole_sm && r.N > RDB_SMALL_N))
+            return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
     }
     return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::run(model, a, r.dev, r.stream);
 }

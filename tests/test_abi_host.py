@@ -240,6 +240,7 @@ def test_plan_and_trajectory_entry_points_refuse_bad_arguments_without_a_gpu():
     vp = ctypes.c_void_p()
     assert L.rdb_plan_create(None, 3, 3, 1, 0, 8, None, None, None, 0.01, None, None, ctypes.byref(vp)) == rdb200._abi.ERR_ARG
     assert L.rdb_plan_launch(None, None) == rdb200._abi.ERR_ARG and L.rdb_plan_destroy(None) == 0
+    assert L.rdb_plan_set_shared(None, 1) == rdb200._abi.ERR_ARG
     assert L.rdb_trajectory_create(None, 1, 4, 16, ctypes.byref(vp)) == rdb200._abi.ERR_ARG
     assert L.rdb_trajectory_rollout(None, 3, None) == rdb200._abi.ERR_ARG and L.rdb_trajectory_destroy(None) == 0
     assert L.rdb_dynamics_error(None, 3, 1, 8, None, None, 5, None, None, 0.01, None, None) == rdb200._abi.ERR_ARG

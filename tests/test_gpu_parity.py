@@ -1097,3 +1097,36 @@ def test_registered_caller_arrays_take_the_host_path(rd, torch_):
     assert np.abs(J - o.discrete_jacobian(om, o.RK4, Z.astype(np.float64), 0.02)).max() < TOL[np.float32]
     with pytest.raises(ValueError):
         rd.RegisteredArray(np.empty((0, 3)))
+
+
+def test_plans_relaunched_and_concurrent(rd, torch_):
+    """Plans over several waves of tiles, a ragged tail, per-knot dt arrays: relaunched, marked as sharing the GPU (rdb_plan_set_shared: wide
+    tiles) or not, and in flight at once on two streams — every sampled knot against the checker, bit for bit against the direct call."""
+    cases = [("cartpole", np.float64, 1 << 18), ("quad_quat_world", np.float32, 150000 + 77), ("body_mrp_body", np.float64, 40000 + 5)]
+    streams = [torch_.cuda.Stream(), torch_.cuda.Stream()]
+    plans, refs = [], []
+    for i, (name, dtype, N) in enumerate(cases):
+        om, gm = zoo()[name][0](), zoo()[name][1](rd)
+        Z = rand_inputs(om.n, om.m, N, np.random.default_rng(300 + i)).astype(dtype)
+        dt = np.random.default_rng(400 + i).uniform(0.005, 0.05, N)
+        Zd, dtd = dev(torch_, Z), dev(torch_, dt)
+        direct = gm._h.discrete_jacobian(o.RK4, Zd, dtd)
+        idx = np.arange(0, N, 13)
+        assert np.abs(direct.cpu().numpy()[idx] - o.discrete_jacobian(om, o.RK4, Z[idx].astype(np.float64), dt[idx])).max() < TOL[dtype]
+        for shared in (False, True):
+            plan = rd._abi.Plan(gm._h, rd._abi.OP_DISCRETE_JACOBIAN, o.RK4, Zd, dtd, shared_gpu=shared)
+            for rep in range(2):
+                plan.J.zero_()
+                plan.launch()
+                torch_.cuda.synchronize()
+                assert torch_.equal(plan.J, direct), (name, shared, rep)
+            plans.append(plan); refs.append(direct)
+    for p in plans:
+        p.J.zero_()
+    torch_.cuda.synchronize()
+    for rep in range(3):                                                       # concurrently: plans alternate between two streams
+        for k, p in enumerate(plans):
+            p.launch(streams[k % 2].cuda_stream)
+    torch_.cuda.synchronize()
+    for p, r in zip(plans, refs):
+        assert torch_.equal(p.J, r)
