@@ -222,6 +222,11 @@ VARIANTS["quadrotor64"] = {"base": {}, "bal1": dict(_T64, RDB_TUNE_C0="0x6387u",
 VARIANTS["quadmrp64"] = {"base": {}, "balm": dict(_T64, RDB_TUNE_C0="0x23Fu", RDB_TUNE_C1="0xDC0u", RDB_TUNE_C2="0x3000u", RDB_TUNE_C3="0xC000u")}
 
 
+# tile size between the two configurations in the library (wide 128 / narrow 32) for the fp32 rigid kernels: 64 knots, 2 CTAs per SM
+for _w in ("quadrotor", "quadbody", "quadmrp", "bodyquat"):
+    VARIANTS[_w] = {"t128": dict(RDB_TUNE_TILE=128, RDB_TUNE_MINB=1), "t64": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=1), "t32": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=1)}
+
+
 def build_variants(workload):
     import build as B
     os.makedirs(OUT, exist_ok=True)
