@@ -106,10 +106,17 @@ struct KnotConfigSmall : KnotConfig<Model, T, WITH_J, Q> { static constexpr bool
 // models in fp32 (C3 45.5 -> 42.6 us, its error-state form 45.3 -> 42.8 us, Body{Quat} 51.0 -> 50.0 us) and the Body / Satellite family
 // with a 3-parameter attitude in fp64 or in the body frame (Body{MRP} body frame 74.0 -> 69.1 us fp32, 211 -> 191 us fp64; Body{MRP} fp64
 // 146.7 -> 139.6 us).  Every other variant is faster on the wide tiles from ~16k knots on (quadrotor{MRP} fp64 141.9 vs 157.7 us).
-template <class Shape, class T>
+// The fused error-state kernels (ERR) were measured separately (profiles/err_tiles_r02.md): narrow wins everywhere except the quadrotor in
+// the body frame (fp32: 79.0 vs 84.3 us) and, in fp64, the quadrotor's body-frame and 3-parameter variants (150.5 vs 179.6 us).
+template <class Model, class T, bool ERR>
 constexpr bool prefers_narrow_tiles() {
-    if (Shape::rot == ROT_QUAT && Shape::frame == FRAME_WORLD) return sizeof(T) == 4;
-    if (Shape::m == 6 && Shape::rot != ROT_QUAT) return sizeof(T) == 8 || Shape::frame == FRAME_BODY;
+    constexpr bool quad = (Model::m == 4), quat_world = (Model::rot == ROT_QUAT && Model::frame == FRAME_WORLD);
+    if (ERR) {
+        if (sizeof(T) == 4) return !(quad && Model::frame == FRAME_BODY);
+        return !quad || quat_world;
+    }
+    if (quat_world) return sizeof(T) == 4;
+    if (!quad && Model::rot != ROT_QUAT) return sizeof(T) == 8 || Model::frame == FRAME_BODY;
     return false;
 }
 #ifndef RDB_TUNE_TILE
@@ -336,10 +343,9 @@ inline int run_one(const KnotRequest& r) {
     }
     if constexpr (KnotConfigSmall<typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape, T, WITH_J, Q>::distinct) {
         // RDB200_SMALL_N overrides the threshold (experiments: scripts/tile_threshold.py)
-        using Shape = typename KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR>::Shape;
         static const long long small_n = []() {
             const char* e = std::getenv("RDB200_SMALL_N");
-            return e ? std::atoll(e) : (prefers_narrow_tiles<Shape, T>() ? (long long)1 << 62 : (long long)RDB_SMALL_N);
+            return e ? std::atoll(e) : (prefers_narrow_tiles<ModelT<T>, T, ERR>() ? (long long)1 << 62 : (long long)RDB_SMALL_N);
         }();
         if (r.N <= small_n && !(r.whole_sm && r.N > RDB_SMALL_N))
             return KnotLaunch<ModelT<T>, Q, T, WITH_J, ERR, false, true>::run(model, a, r.dev, r.stream);
