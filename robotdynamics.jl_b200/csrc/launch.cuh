@@ -94,8 +94,8 @@ struct KnotConfig<Model, T, false, Q> {
 // Small batches (a solver's 10^2 - 10^3 knots per call): one wave of CTAs, the launch lasts as long as ONE thread's dependent chain.
 // The long rigid-body RK3 / RK4 Jacobian chains then run faster on 32-knot tiles — four times as many CTAs, each warp on a scheduler of
 // its own instead of two per scheduler on few SMs — with the same roles (graph-replayed launch, Quadrotor RK4 fp32: 5.3 -> 3.2 us at
-// N <= 1024, 5.6 -> 4.3 us at 4096, equal at 16384; profiles/small_batch_r02.md).  Large batches keep the wide tiles (larger TMA
-// transactions).  `distinct` = this configuration exists as its own instantiation.
+// N <= 1024, 5.6 -> 4.3 us at 4096, equal at 16384; profiles/small_batch_r02.md).  Above RDB_SMALL_N the wide tiles return, unless the
+// family prefers the narrow ones at every size (below).  `distinct` = this configuration exists as its own instantiation.
 #ifndef RDB_SMALL_N
 #define RDB_SMALL_N 8192
 #endif
