@@ -227,6 +227,9 @@ for _w in ("quadrotor", "quadbody", "quadmrp", "bodyquat"):
     VARIANTS[_w] = {"t128": dict(RDB_TUNE_TILE=128, RDB_TUNE_MINB=1), "t64": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=1), "t32": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=1)}
 
 
+VARIANTS["cartpole"].update({"t32_minb12": dict(RDB_TUNE_TILE=32, RDB_TUNE_MINB=12), "t64_minb6": dict(RDB_TUNE_TILE=64, RDB_TUNE_MINB=6)})
+
+
 def build_variants(workload):
     import build as B
     os.makedirs(OUT, exist_ok=True)
