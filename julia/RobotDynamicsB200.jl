@@ -222,6 +222,32 @@ function rollout_batch!(dmodel::RD.DiscretizedDynamics{L,Q}, X::Array{T,3}, x0::
                 C_NULL, C_NULL, dt, pointer(X), stream), "rdb_rollout")
 end
 
+# ---- pre-validated launches (rdb_plan_*): what a solver loop calls every iteration on device-resident data --------------------------------
+"""
+    LaunchPlan(dmodel, Z, dts, J; y=nothing, times=nothing, error_state=false, shared_gpu=false)
+
+Validates `jacobian!(sig, B200(), dmodel, J, y, Z)` once for DEVICE arrays (anything `pointer` works on: `CuArray`s — `Z` is `(n+m) x N`,
+`J` is `n x (n+m) x N`, or `n̄ x (n̄+m) x N` with `error_state`); `launch!(plan; stream)` is then a single kernel launch that evaluates
+whatever the arrays hold (6–7 µs of host time, capturable in a CUDA graph).  `shared_gpu=true` for plans whose launches overlap other
+kernels on the same GPU (rdb_plan_set_shared).  The reference has no counterpart (per-knot method calls, src/discretized_dynamics.jl:129-136).
+"""
+mutable struct LaunchPlan
+    ptr::Ptr{Cvoid}
+    keep::Any             # the arrays and the model handle the plan points at
+end
+function LaunchPlan(dmodel::RD.DiscretizedDynamics{L,Q}, Z, dts, J; y=nothing, times=nothing, error_state::Bool=false, shared_gpu::Bool=false) where {L,Q}
+    h = gethandle(dmodel.continuous_dynamics)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    op = error_state ? Cint(4) : Cint(3)          # RDB_OP_DISCRETE_ERROR_JACOBIAN / RDB_OP_DISCRETE_JACOBIAN
+    check(ccall((:rdb_plan_create, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                h.ptr, op, INTEGRATOR[Q], dtypecode(eltype(Z)), 0 #= RDB_AOS =#, size(Z, 2), pointer(Z), times === nothing ? C_NULL : pointer(times),
+                pointer(dts), 0.0, pointer(J), y === nothing ? C_NULL : pointer(y), r), "rdb_plan_create")
+    shared_gpu && check(ccall((:rdb_plan_set_shared, LIB), Cint, (Ptr{Cvoid}, Cint), r[], 1), "rdb_plan_set_shared")
+    finalizer(p -> ccall((:rdb_plan_destroy, LIB), Cint, (Ptr{Cvoid},), p.ptr), LaunchPlan(r[], (Z, dts, J, y, times, h)))
+end
+launch!(p::LaunchPlan; stream=C_NULL) = check(ccall((:rdb_plan_launch, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), p.ptr, stream), "rdb_plan_launch")
+
 # ---- persistent device trajectory (rdb_trajectory_*): the device mirror of SampledTrajectory ------------------------------------------
 """
     DeviceTrajectory(dmodel, Z::SampledTrajectory)            # one trajectory, uploaded once
