@@ -255,3 +255,19 @@ def test_user_model_bodies_with_time_compile_without_a_gpu():
     assert ok, log
     ok, log = rd._abi.custom_check(2, 1, "return vec(get<1>(x), tt * get<0>(u));", 0, rd.F32)
     assert not ok and "tt" in log
+
+
+def test_julia_shim_binds_only_exported_symbols():
+    """julia/RobotDynamicsB200.jl cannot be executed here (no Julia): at least every `ccall((:rdb_..., LIB), ...)` in it must name a symbol the
+    header declares and the library exports, with as many argument types as the C prototype has parameters."""
+    import rdb200
+    src = open(os.path.join(ROOT, "julia", "RobotDynamicsB200.jl")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rdb200.h")).read(), flags=re.S)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r"\b(rdb_[a-z_]+)\s*\(([^;{]*?)\)\s*;", hdr)}
+    calls = re.findall(r"ccall\(\(:(rdb_[a-z_]+), LIB\),\s*\w+,\s*\(([^)]*)\)", src)
+    assert len(calls) > 25
+    for name, argtypes in calls:
+        assert name in rdb200._abi.SYMBOLS, name
+        nargs_c = 0 if protos[name].strip() in ("", "void") else protos[name].count(",") + 1
+        nargs_jl = len([a for a in argtypes.split(",") if a.strip()])
+        assert nargs_c == nargs_jl, (name, nargs_c, nargs_jl)
