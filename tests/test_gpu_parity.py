@@ -1130,3 +1130,36 @@ def test_plans_relaunched_and_concurrent(rd, torch_):
     torch_.cuda.synchronize()
     for p, r in zip(plans, refs):
         assert torch_.equal(p.J, r)
+
+
+@pytest.mark.parametrize("name", ["quad_quat_body", "body_quat_body", "quad_mrp_body", "body_rp_body"])
+def test_body_frame_split_force_off_the_manifold(rd, torch_, name):
+    """Body-frame models evaluate q \\ (q * Fb + Gw) as |q|^4 Fb + q \\ Gw (models.cuh, SPLIT) where the checker composes the two rotations like
+    the reference (src/rigidbody.jl:229-230, test/quadrotor.jl:74): the same polynomial in q, so values and Jacobians must agree for state
+    quaternions far from unit norm too (|q| in [0.5, 1.5]; the path never renormalises), for every rule, the continuous Jacobian and the
+    ImplicitMidpoint rule."""
+    om, gm = zoo()[name][0](), zoo()[name][1](rd)
+    N = 2000
+    rng = np.random.default_rng(500)
+    Z = rand_inputs(om.n, om.m, N, rng)
+    if om.n == 13:
+        Z[:, 3:7] *= rng.uniform(0.5, 1.5, (N, 1))
+    if om.m == 4:
+        Z[::9, om.n] = 0.0; Z[::11, om.n + 2] = -0.2              # thrust clamp: ties and inactive rotors
+    for dtype in (np.float64, np.float32):
+        Zt = Z.astype(dtype); Z64 = Zt.astype(np.float64)
+        Zd = dev(torch_, Zt)
+        for Q in QS:
+            J = gm._h.discrete_jacobian(Q, Zd, 0.05)
+            torch_.cuda.synchronize()
+            ref = o.discrete_jacobian(om, Q, Z64, 0.05)
+            assert np.abs(J.cpu().numpy() - ref).max() < TOL[dtype] * max(1.0, np.abs(ref).max())
+        Jc = gm._h.jacobian(Zd)
+        torch_.cuda.synchronize()
+        refc = o.jacobian(om, Z64)
+        assert np.abs(Jc.cpu().numpy() - refc).max() < TOL[dtype] * max(1.0, np.abs(refc).max())
+    Zd = dev(torch_, Z)
+    Ji = gm._h.discrete_jacobian(rd._abi.IMPLICIT_MIDPOINT, Zd, 0.02)
+    torch_.cuda.synchronize()
+    refi = o.discrete_jacobian(om, o.IMPLICIT_MIDPOINT, Z, 0.02)
+    assert np.abs(Ji.cpu().numpy() - refi).max() < 1e-9 * max(1.0, np.abs(refi).max())
