@@ -459,3 +459,20 @@ def test_rotation_conventions_vs_scipy(rn, rc):
         rel = _scipy_rot(rn, X0[k, 3:3 + na]).inv() * rot
         rv = rel.as_rotvec(); th = np.linalg.norm(rv)
         assert np.allclose(d[k, 3:6], np.tan(th / 2.0) * rv / th, atol=1e-11)
+
+
+def test_unnormalised_rotation_identity_behind_the_split_body_frame_force():
+    """models.cuh (SPLIT) evaluates the body-frame q \\ (q * Fb + Gw) as |q|^4 Fb + q \\ Gw.  Symbolically, for the polynomial rotation the
+    reference path uses (q * r = (w^2 - v.v) r + 2 v (v.r) + 2 w (v x r), q \\ r = conj(q) * r, no normalisation: SURVEY §8c), the identity
+    q \\ (q * F) = |q|^4 F holds for EVERY quaternion — hence also for every derivative with respect to q and F."""
+    sympy = pytest.importorskip("sympy")
+    w, x, y, z, f0, f1, f2 = sympy.symbols("w x y z f0 f1 f2", real=True)
+
+    def rot(qw, v, r):
+        v, r = sympy.Matrix(v), sympy.Matrix(r)
+        return (qw**2 - v.dot(v)) * r + 2 * v * v.dot(r) + 2 * qw * v.cross(r)
+
+    F = sympy.Matrix([f0, f1, f2])
+    back = rot(w, [-x, -y, -z], rot(w, [x, y, z], F))
+    n2 = w**2 + x**2 + y**2 + z**2
+    assert all(sympy.expand(e) == 0 for e in (back - n2**2 * F))
